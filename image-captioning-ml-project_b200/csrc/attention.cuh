@@ -1,0 +1,48 @@
+// Attention stage kernels: argument blocks + launchers (attn_additive.cu, attn_mha.cu).
+#pragma once
+#include "common.cuh"
+
+namespace capdec {
+
+constexpr int kMaxRowsPerImage = 8;  // beams / samples of one image that share its feature tiles in one CTA
+
+enum AddAct : int { ACT_RELU = 0, ACT_TANH = 1 };
+
+// Additive attention over one image's region tiles, all `k` rows (beams) of the image at once:
+//   e[b,l]   = (w . act(att1[img,l,:] + att2[row_b,:]) + w_bias) / temperature   (masked -> -1e9)
+//   alpha    = softmax_l(e)
+//   ctx[b,:] = sum_l alpha[b,l] * feats[img,l,:]   (* gate[row_b,:] if gate != nullptr)
+// legacy:  models/decoder.py:152-161 (act = relu, gate = sigmoid(f_beta(h)))
+// soft:    src/models/attention.py:76-111 (act = tanh, value == key == features)
+struct AddAttnArgs {
+  const float* att1;                    // [B,L,A]  hoisted enc_att(enc) / key_proj(key), bias included
+  const float* att2; int64_t ld_att2;   // [R,A]    dec_att(h) / query_proj(q), bias included
+  const float* w;                       // [A]      att.weight / energy.weight
+  float w_bias, temperature;
+  const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr
+  const float* feats;                   // [B,L,D]
+  const float* gate; int64_t ld_gate;   // [R,D] or nullptr
+  float* ctx; int64_t ld_ctx;           // [R,D]
+  float* alpha; int64_t ld_alpha;       // [R,L] (row stride ld_alpha) or nullptr
+  int B, L, A, D, k;
+};
+int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s);
+
+// Multi-head dot-product attention on hoisted per-image K/V projections, all k rows of an image per CTA:
+//   s[b,h,l] = q[row_b,h,:] . K[img,l,h,:] / denom      (masked -> -1e9)
+//   p        = softmax_l(s);  out[row_b,h,:] = sum_l p[b,h,l] * V[img,l,h,:]
+//   alpha[row_b,l] = mean_h p[b,h,l]
+// src/models/attention.py:161-211 (the output_proj GEMM follows outside).
+struct MhaArgs {
+  const float* q; int64_t ld_q;         // [R,H] projected query
+  const float* kproj;                   // [B,L,H] hoisted key_proj(key)
+  const float* vproj;                   // [B,L,H] hoisted value_proj(value)
+  const uint8_t* mask;                  // [B,L] or nullptr
+  float denom;                          // temperature * sqrt(head_dim)
+  float* out; int64_t ld_out;           // [R,H] concatenated heads
+  float* alpha; int64_t ld_alpha;       // [R,L] head-mean weights or nullptr
+  int B, L, H, heads, k;
+};
+int mha_attention(const MhaArgs& a, cudaStream_t s);
+
+}  // namespace capdec

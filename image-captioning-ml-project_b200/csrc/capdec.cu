@@ -1,0 +1,855 @@
+// libcapdec C ABI + host-side decode programs (kernel sequencing on the caller's stream).
+//
+// Two decoder families share the stage kernels:
+//   legacy  models/decoder.py::Decoder         attention(h_old) -> gate -> LSTMCell -> fc(h_new)
+//   lstm    src/models/decoders.py::LSTMDecoder nn.LSTM([emb;prev_ctx]) -> attention(h_new) -> output_layer(ctx)
+// Time-invariant projections of the region features (enc_att(enc), key_proj/value_proj(features)) are
+// hoisted into a per-call prologue; the reference recomputes them every step (models/decoder.py:152,
+// src/models/attention.py:77,172-174).
+#include <math.h>
+#include <string.h>
+
+#include "handle.cuh"
+
+namespace capdec {
+
+static thread_local char g_err[1024] = "";
+int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm(int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
+  if (precision == CAPDEC_PREC_FP32) return gemm_ffma(a, epilogue, s);
+  return gemm_tc(precision, a, epilogue, s);
+}
+
+namespace {
+
+// dst[(G*j + g), col_off + c] (+)= src[j, c]   -- weight packing (concatenate / interleave gate rows)
+__global__ void scatter_rows_kernel(float* dst, int64_t ld_dst, int G, int g, int64_t col_off, const float* src,
+                                    int64_t ld_src, int nrows, int width, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nrows * width) return;
+  const int j = (int)(i / width), c = (int)(i - (int64_t)j * width);
+  float* d = dst + ((int64_t)G * j + g) * ld_dst + col_off + c;
+  const float v = src[(int64_t)j * ld_src + c];
+  *d = accumulate ? (*d + v) : v;
+}
+int scatter_rows(float* dst, int64_t ld_dst, int G, int g, int64_t col_off, const float* src, int64_t ld_src,
+                 int nrows, int width, bool accumulate, cudaStream_t s) {
+  const int64_t n = (int64_t)nrows * width;
+  scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ld_dst, G, g, col_off, src, ld_src, nrows, width,
+                                                                  accumulate ? 1 : 0);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+// adaptive attention elementwise pieces (src/models/attention.py:266-287)
+__global__ void sentinel_pre_kernel(const float* gate, int64_t ld_g, const float* cell, int64_t ld_c, float* out,
+                                    int64_t ld_o, int rows, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * H) return;
+  const int r = (int)(i / H), c = (int)(i - (int64_t)r * H);
+  out[(int64_t)r * ld_o + c] = gate[(int64_t)r * ld_g + c] * tanhf(cell[(int64_t)r * ld_c + c]);  // gate already sigmoid
+}
+__global__ void __launch_bounds__(128) adaptive_mix_kernel(const float* ctx, const float* sent, const float* w,
+                                                           float bias, float* out, int64_t ld_o, int H) {
+  // beta = sigmoid(w . [ctx ; s] + b);  out = beta*ctx + (1-beta)*s      one CTA per row
+  __shared__ float s_part[4];
+  __shared__ float s_beta;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* c = ctx + (int64_t)r * H;
+  const float* s = sent + (int64_t)r * H;
+  float acc = 0.f;
+  for (int i = tid; i < H; i += 128) acc += w[i] * c[i] + w[H + i] * s[i];
+  acc = warp_sum(acc);
+  if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) s_beta = sigmoidf_(s_part[0] + s_part[1] + s_part[2] + s_part[3] + bias);
+  __syncthreads();
+  const float beta = s_beta;
+  for (int i = tid; i < H; i += 128) out[(int64_t)r * ld_o + i] = beta * c[i] + (1.f - beta) * s[i];
+}
+
+bool is_legacy(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_LEGACY_SAT; }
+bool base_is_mha(const capdec_handle* h) {
+  const int a = h->cfg.attention;
+  if (a == CAPDEC_ATT_MULTI_HEAD) return true;
+  if (a == CAPDEC_ATT_SOFT) return false;
+  return h->cfg.num_heads > 1;  // attention.py:229-230, 308-309
+}
+std::string base_prefix(const capdec_handle* h) {
+  const int a = h->cfg.attention;
+  return (a == CAPDEC_ATT_AOA || a == CAPDEC_ATT_ADAPTIVE) ? "attention.base_attention." : "attention.";
+}
+
+// ---- per-call workspace layout --------------------------------------------------------------------------
+struct Session {
+  int B = 0, L = 0, k = 1, R = 0, T = 0;
+  // LSTM operands per layer: X[l] = [input_l | h_l], ld = in_l + H
+  std::vector<float*> X, c, cnew, hnew;
+  std::vector<int64_t> ldX;
+  float* logits = nullptr;
+  float* cand_lp = nullptr; int32_t* cand_idx = nullptr;
+  int32_t* next_tok = nullptr; int32_t* src_row = nullptr; float* step_lp = nullptr;
+  BeamState beam{};
+  // legacy
+  float* att1 = nullptr; float* meanb = nullptr; float* init = nullptr; float* hproj = nullptr;
+  // lstm arch attention
+  float* keyp = nullptr; float* valp = nullptr; float* qproj = nullptr; float* att_out = nullptr;
+  float* ctx = nullptr; float* cat = nullptr; float* qq = nullptr; float* sgate = nullptr; float* spre = nullptr;
+  float* sent = nullptr; float* base_ctx = nullptr;
+};
+
+enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
+
+int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, int T, Mode mode) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim, V = c.vocab_size;
+  S.B = B; S.L = L; S.k = k; S.R = B * k; S.T = T;
+  const size_t R = (size_t)S.R;
+  const int layers = c.num_layers;
+  if (mode != MODE_ATTENTION) {
+    S.X.resize(layers); S.c.resize(layers); S.cnew.resize(layers); S.hnew.resize(layers); S.ldX.resize(layers);
+    for (int l = 0; l < layers; ++l) {
+      const int in = l == 0 ? (is_legacy(h) ? E + D : E + H) : H;
+      S.ldX[l] = in + H;
+      S.X[l] = ar.take<float>(R * S.ldX[l]);
+      S.c[l] = ar.take<float>(R * H);
+      S.cnew[l] = ar.take<float>(R * H);
+      S.hnew[l] = ar.take<float>(R * (c.attention == CAPDEC_ATT_ADAPTIVE && l == layers - 1 && !is_legacy(h) ? 2 * H : H));
+    }
+    if (mode != MODE_TEACHER) S.logits = ar.take<float>(R * V);
+    S.next_tok = ar.take<int32_t>(R);
+    S.src_row = ar.take<int32_t>(R);
+    S.step_lp = ar.take<float>(R);
+    if (mode == MODE_BEAM) {
+      S.cand_lp = ar.take<float>(R * 2 * k);
+      S.cand_idx = ar.take<int32_t>(R * 2 * k);
+      for (int i = 0; i < 2; ++i) {
+        S.beam.run_seq[i] = ar.take<int32_t>(R * T);
+        S.beam.fin_seq[i] = ar.take<int32_t>(R * T);
+      }
+      S.beam.run_score = ar.take<float>(R);
+      S.beam.fin_score = ar.take<float>(R);
+      S.beam.fin_len = ar.take<int32_t>(R);
+      S.beam.fin_flag = ar.take<uint8_t>(R);
+      S.beam.unsatisfied = ar.take<uint8_t>(B);
+    } else if (mode == MODE_GREEDY) {
+      S.cand_lp = ar.take<float>(R);
+      S.cand_idx = ar.take<int32_t>(R);
+    }
+  }
+  if (is_legacy(h)) {
+    S.att1 = ar.take<float>((size_t)B * L * A);
+    S.meanb = ar.take<float>((size_t)B * D);
+    S.init = ar.take<float>((size_t)B * 2 * H);
+    S.hproj = ar.take<float>(R * (A + D));
+  } else {
+    S.keyp = ar.take<float>((size_t)B * L * H);
+    if (base_is_mha(h)) {
+      S.valp = ar.take<float>((size_t)B * L * H);
+      S.att_out = ar.take<float>(R * H);
+    }
+    S.qproj = ar.take<float>(R * H);
+    S.ctx = ar.take<float>(R * H);
+    if (mode != MODE_ATTENTION) S.init = ar.take<float>((size_t)B * 2 * H * layers);
+    if (c.attention == CAPDEC_ATT_AOA) S.cat = ar.take<float>(R * 2 * H);
+    if (c.attention == CAPDEC_ATT_ADAPTIVE) {
+      S.qq = ar.take<float>(R * 2 * H);
+      S.sgate = ar.take<float>(R * H);
+      S.spre = ar.take<float>(R * H);
+      S.sent = ar.take<float>(R * H);
+      S.base_ctx = ar.take<float>(R * H);
+    }
+  }
+  return CAPDEC_OK;
+}
+
+// ---- hoisted per-call projections ---------------------------------------------------------------------------
+int linear(const capdec_handle* h, const float* A, int64_t lda, const std::string& name, float* C, int64_t ldc, int M,
+           int epi, cudaStream_t s, float* C2 = nullptr, int64_t ldc2 = 0) {
+  const DevTensor* w = h->find(name + ".weight");
+  const DevTensor* b = h->find(name + ".bias");
+  CAPDEC_REQUIRE(w && w->shape.size() == 2, CAPDEC_ERR_STATE, "weight %s.weight missing", name.c_str());
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = w->p; g.ldw = w->shape[1]; g.bias = b ? b->p : nullptr;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = (int)w->shape[0]; g.K = (int)w->shape[1]; g.C2 = C2; g.ldc2 = ldc2;
+  return gemm(h->cfg.precision, g, epi, s);
+}
+
+int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool expand, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
+  // att1 = enc_att(enc)  (models/decoder.py:152, hoisted)
+  CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s));
+  // h0, c0 = h_lin(mean), c_lin(mean)  (:137-139)
+  CAPDEC_RETURN_IF(mean_regions(feats, S.B, S.L, D, S.meanb, s));
+  GemmArgs g{};
+  g.A = S.meanb; g.lda = D; g.W = h->w_init; g.ldw = D; g.bias = h->b_init; g.C = S.init; g.ldc = 2 * H;
+  g.M = S.B; g.N = 2 * H; g.K = D;
+  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_STORE, s));
+  if (expand) {
+    CAPDEC_RETURN_IF(expand_rows(S.init, 2 * H, S.X[0] + E + D, S.ldX[0], S.R, S.k, H, s));
+    CAPDEC_RETURN_IF(expand_rows(S.init + H, 2 * H, S.c[0], H, S.R, S.k, H, s));
+  }
+  return CAPDEC_OK;
+}
+
+int prologue_attention(const capdec_handle* h, Session& S, const float* feats, cudaStream_t s) {
+  const int H = h->cfg.hidden_dim;
+  const std::string p = base_prefix(h);
+  CAPDEC_RETURN_IF(linear(h, feats, H, p + "key_proj", S.keyp, H, S.B * S.L, EPI_STORE, s));
+  if (base_is_mha(h)) CAPDEC_RETURN_IF(linear(h, feats, H, p + "value_proj", S.valp, H, S.B * S.L, EPI_STORE, s));
+  return CAPDEC_OK;
+}
+
+int prologue_lstm(const capdec_handle* h, Session& S, const float* feats, const float* pooled, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, layers = c.num_layers;
+  CAPDEC_RETURN_IF(prologue_attention(h, S, feats, s));
+  // _init_hidden_states (decoders.py:122-135): [init_h ; init_c](pooled) -> [B, 2*layers*H]
+  GemmArgs g{};
+  g.A = pooled; g.lda = H; g.W = h->w_init; g.ldw = H; g.bias = h->b_init; g.C = S.init; g.ldc = 2 * layers * H;
+  g.M = S.B; g.N = 2 * layers * H; g.K = H;
+  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_STORE, s));
+  for (int l = 0; l < layers; ++l) {
+    const int in = l == 0 ? E + H : H;
+    CAPDEC_RETURN_IF(expand_rows(S.init + (size_t)l * H, 2 * layers * H, S.X[l] + in, S.ldX[l], S.R, S.k, H, s));
+    CAPDEC_RETURN_IF(expand_rows(S.init + (size_t)(layers + l) * H, 2 * layers * H, S.c[l], H, S.R, S.k, H, s));
+  }
+  // prev_ctx = 0 (decoders.py:265-266)
+  CAPDEC_CHECK_CUDA(cudaMemsetAsync(S.ctx, 0, (size_t)S.R * H * sizeof(float), s));
+  return CAPDEC_OK;
+}
+
+// ---- attention for the lstm arch: q [rows,H] -> ctx [rows,H] (S.ctx), alpha ------------------------------------
+int run_attention(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, const float* q,
+                  int64_t ld_q, const float* memory, int64_t ld_mem, const float* cell, int64_t ld_cell, int images,
+                  float* ctx_out, float* alpha, int64_t ld_alpha, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, k = S.k, rows = images * k;
+  const std::string p = base_prefix(h);
+  float* base_dst = ctx_out;
+  if (c.attention == CAPDEC_ATT_AOA) base_dst = S.cat;          // cat[:, 0:H], ld 2H
+  if (c.attention == CAPDEC_ATT_ADAPTIVE) base_dst = S.base_ctx;
+  const int64_t ld_base = c.attention == CAPDEC_ATT_AOA ? 2 * H : H;
+
+  if (c.attention == CAPDEC_ATT_ADAPTIVE) {
+    // sentinel (attention.py:266-272): s = sentinel_proj(sigmoid(W[q;mem]) * tanh(cell))
+    CAPDEC_REQUIRE(memory && cell, CAPDEC_ERR_INVALID, "AdaptiveAttention requires memory_state and cell_state");
+    GatherArgs ga{};
+    ga.rows = rows; ga.n_state = 2; ga.pos = -1;
+    ga.state_src[0] = q; ga.ld_src[0] = ld_q; ga.state_dst[0] = S.qq; ga.ld_dst[0] = 2 * H; ga.width[0] = H;
+    ga.state_src[1] = memory; ga.ld_src[1] = ld_mem; ga.state_dst[1] = S.qq + H; ga.ld_dst[1] = 2 * H; ga.width[1] = H;
+    if (!(q == S.qq && memory == S.qq + H)) CAPDEC_RETURN_IF(gather_rows(ga, s));
+    const DevTensor* w = h->find("attention.sentinel_gate.weight");
+    GemmArgs g{};
+    g.A = S.qq; g.lda = 2 * H; g.W = w->p; g.ldw = 2 * H; g.bias = h->W("attention.sentinel_gate.bias");
+    g.C = S.sgate; g.ldc = H; g.M = rows; g.N = H; g.K = 2 * H; g.n_split = 0;
+    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s));
+    const int64_t n = (int64_t)rows * H;
+    sentinel_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(S.sgate, H, cell, ld_cell, S.spre, H, rows, H);
+    CAPDEC_LAUNCH_CHECK();
+    CAPDEC_RETURN_IF(linear(h, S.spre, H, "attention.sentinel_proj", S.sent, H, rows, EPI_STORE, s));
+  }
+
+  CAPDEC_RETURN_IF(linear(h, q, ld_q, p + "query_proj", S.qproj, H, rows, EPI_STORE, s));
+  if (base_is_mha(h)) {
+    MhaArgs m{};
+    m.q = S.qproj; m.ld_q = H; m.kproj = S.keyp; m.vproj = S.valp; m.mask = mask;
+    m.denom = (float)((double)c.temperature * sqrt((double)(H / c.num_heads)));
+    m.out = S.att_out; m.ld_out = H; m.alpha = alpha; m.ld_alpha = ld_alpha;
+    m.B = images; m.L = S.L; m.H = H; m.heads = c.num_heads; m.k = k;
+    CAPDEC_RETURN_IF(mha_attention(m, s));
+    CAPDEC_RETURN_IF(linear(h, S.att_out, H, p + "output_proj", base_dst, ld_base, rows, EPI_STORE, s));
+  } else {
+    AddAttnArgs a{};
+    a.att1 = S.keyp; a.att2 = S.qproj; a.ld_att2 = H; a.w = h->W(p + "energy.weight");
+    a.w_bias = h->energy_bias; a.temperature = c.temperature; a.mask = mask; a.feats = feats;
+    a.gate = nullptr; a.ctx = base_dst; a.ld_ctx = ld_base; a.alpha = alpha; a.ld_alpha = ld_alpha;
+    a.B = images; a.L = S.L; a.A = H; a.D = H; a.k = k;
+    CAPDEC_RETURN_IF(additive_attention(a, ACT_TANH, s));
+  }
+
+  if (c.attention == CAPDEC_ATT_AOA) {
+    // attention.py:343-353: cat = [ctx ; query_proj(q)];  out = tanh(W_i cat) * sigmoid(W_g cat)
+    CAPDEC_RETURN_IF(linear(h, q, ld_q, "attention.query_proj", S.cat + H, 2 * H, rows, EPI_STORE, s));
+    GemmArgs g{};
+    g.A = S.cat; g.lda = 2 * H; g.W = h->w_aoa; g.ldw = 2 * H; g.bias = h->b_aoa; g.C = ctx_out; g.ldc = H;
+    g.M = rows; g.N = 2 * H; g.K = 2 * H;
+    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_AOA, s));
+  } else if (c.attention == CAPDEC_ATT_ADAPTIVE) {
+    adaptive_mix_kernel<<<rows, 128, 0, s>>>(S.base_ctx, S.sent, h->W("attention.adaptive_weight.weight"),
+                                             h->adaptive_bias, ctx_out, H, H);
+    CAPDEC_LAUNCH_CHECK();
+  }
+  return CAPDEC_OK;
+}
+
+// ---- one decode step: state in X/c -> logits (+ hnew/cnew) -----------------------------------------------------
+int step_legacy(const capdec_handle* h, Session& S, const float* feats, int images, float* logits, int64_t ld_logits,
+                float* alpha, int64_t ld_alpha, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim, V = c.vocab_size;
+  const int rows = images * S.k;
+  // [dec_att(h) | sigmoid(f_beta(h))]   (models/decoder.py:153,160)
+  GemmArgs g{};
+  g.A = S.X[0] + E + D; g.lda = S.ldX[0]; g.W = h->w_hproj; g.ldw = H; g.bias = h->b_hproj;
+  g.C = S.hproj; g.ldc = A + D; g.M = rows; g.N = A + D; g.K = H; g.n_split = A;
+  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s));
+  // scores -> softmax -> gated context, written straight into the LSTM operand (:154-161)
+  AddAttnArgs a{};
+  a.att1 = S.att1; a.att2 = S.hproj; a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
+  a.temperature = 1.f; a.mask = nullptr; a.feats = feats; a.gate = S.hproj + A; a.ld_gate = A + D;
+  a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;
+  a.B = images; a.L = S.L; a.A = A; a.D = D; a.k = S.k;
+  CAPDEC_RETURN_IF(additive_attention(a, ACT_RELU, s));
+  // LSTMCell([emb ; ctx], (h, c)) with the cell update fused into the gate GEMM (:168)
+  GemmArgs l{};
+  l.A = S.X[0]; l.lda = S.ldX[0]; l.W = h->w_gates[0]; l.ldw = E + D + H; l.bias = h->b_gates[0];
+  l.C = S.hnew[0]; l.ldc = H; l.M = rows; l.N = 4 * H; l.K = E + D + H;
+  l.c_in = S.c[0]; l.ldcin = H; l.c_out = S.cnew[0]; l.ldcout = H;
+  CAPDEC_RETURN_IF(gemm(c.precision, l, EPI_LSTM, s));
+  // fc(h)  (:171; dropout is the identity in eval)
+  CAPDEC_RETURN_IF(linear(h, S.hnew[0], H, "fc", logits, ld_logits, rows, EPI_STORE, s));
+  (void)V;
+  return CAPDEC_OK;
+}
+
+int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
+              int64_t ld_alpha, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, layers = c.num_layers;
+  const int rows = S.R;
+  const bool adaptive = c.attention == CAPDEC_ATT_ADAPTIVE;
+  // nn.LSTM single step (decoders.py:281): stacked cells, layer l+1 input = new h of layer l
+  for (int l = 0; l < layers; ++l) {
+    const int in = l == 0 ? E + H : H;
+    const bool top = l == layers - 1;
+    GemmArgs g{};
+    g.A = S.X[l]; g.lda = S.ldX[l]; g.W = h->w_gates[l]; g.ldw = in + H; g.bias = h->b_gates[l];
+    g.C = S.hnew[l]; g.ldc = (top && adaptive) ? 2 * H : H; g.M = rows; g.N = 4 * H; g.K = in + H;
+    g.c_in = S.c[l]; g.ldcin = H; g.c_out = S.cnew[l]; g.ldcout = H;
+    if (!top) { g.C2 = S.X[l + 1]; g.ldc2 = S.ldX[l + 1]; }
+    else if (adaptive) { g.C2 = S.hnew[l] + H; g.ldc2 = 2 * H; }  // [q | memory_state] with memory_state == q
+    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_LSTM, s));
+  }
+  const float* q = S.hnew[layers - 1];
+  const int64_t ld_q = adaptive ? 2 * H : H;
+  if (adaptive) {
+    // run_attention expects [q|mem] in S.qq: alias it onto the top layer's output
+    float* saved = S.qq;
+    S.qq = S.hnew[layers - 1];
+    const int st = run_attention(h, S, feats, mask, q, ld_q, q + H, ld_q, S.cnew[layers - 1], H, S.B, S.ctx, alpha,
+                                 ld_alpha, s);
+    S.qq = saved;
+    CAPDEC_RETURN_IF(st);
+  } else {
+    CAPDEC_RETURN_IF(run_attention(h, S, feats, mask, q, ld_q, nullptr, 0, nullptr, 0, S.B, S.ctx, alpha, ld_alpha, s));
+  }
+  // logits = output_layer(context)  (decoders.py:303)
+  CAPDEC_RETURN_IF(linear(h, S.ctx, H, "output_layer", S.logits, c.vocab_size, rows, EPI_STORE, s));
+  return CAPDEC_OK;
+}
+
+int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
+             int64_t ld_alpha, cudaStream_t s) {
+  if (is_legacy(h)) return step_legacy(h, S, feats, S.B, S.logits, h->cfg.vocab_size, alpha, ld_alpha, s);
+  return step_lstm(h, S, feats, mask, alpha, ld_alpha, s);
+}
+
+// commit the step: reorder state by back-pointer, embed the chosen tokens, optionally record them
+int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
+           bool with_state, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim;
+  GatherArgs g{};
+  g.rows = S.R; g.tok = S.next_tok; g.src = src;
+  g.embedding = h->W("embedding.weight"); g.E = E; g.x_emb = S.X[0]; g.ld_x = S.ldX[0];
+  g.tok_out = (tok_out && pos >= 0 && pos < S.T) ? tok_out : nullptr; g.ld_tok = ld_tok; g.pos = pos;
+  int n = 0;
+  if (with_state) {
+    for (int l = 0; l < c.num_layers; ++l) {
+      const int in = l == 0 ? (is_legacy(h) ? E + D : E + H) : H;
+      const bool wide = !is_legacy(h) && c.attention == CAPDEC_ATT_ADAPTIVE && l == c.num_layers - 1;
+      g.state_src[n] = S.hnew[l]; g.ld_src[n] = wide ? 2 * H : H; g.state_dst[n] = S.X[l] + in; g.ld_dst[n] = S.ldX[l]; g.width[n] = H; ++n;
+      g.state_src[n] = S.cnew[l]; g.ld_src[n] = H; g.state_dst[n] = S.c[l]; g.ld_dst[n] = H; g.width[n] = H; ++n;
+    }
+    if (!is_legacy(h)) {  // prev_ctx (decoders.py:297)
+      g.state_src[n] = S.ctx; g.ld_src[n] = H; g.state_dst[n] = S.X[0] + E; g.ld_dst[n] = S.ldX[0]; g.width[n] = H; ++n;
+    }
+  }
+  g.n_state = n;
+  return gather_rows(g, s);
+}
+
+int check_common(const capdec_handle* h, const float* feats, const float* pooled, int B, int L, int k, int T) {
+  CAPDEC_REQUIRE(h != nullptr, CAPDEC_ERR_INVALID, "null handle");
+  CAPDEC_REQUIRE(h->finalized, CAPDEC_ERR_STATE, "capdec_finalize has not been called");
+  CAPDEC_REQUIRE(feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
+  CAPDEC_REQUIRE(is_legacy(h) || pooled != nullptr, CAPDEC_ERR_INVALID, "pooled_features pointer is null");
+  CAPDEC_REQUIRE(B >= 0 && L >= 1 && T >= 2, CAPDEC_ERR_INVALID, "bad sizes B=%d L=%d max_length=%d", B, L, T);
+  CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "rows per image %d not in [1,%d]", k,
+                 kMaxRowsPerImage);
+  return CAPDEC_OK;
+}
+
+static int need(const capdec_handle* h, const std::string& n, std::vector<int64_t> shape) {
+  const DevTensor* t = h->find(n);
+  CAPDEC_REQUIRE(t != nullptr, CAPDEC_ERR_STATE, "missing parameter '%s'", n.c_str());
+  bool ok = t->shape.size() == shape.size();
+  for (size_t i = 0; ok && i < shape.size(); ++i) ok = t->shape[i] == shape[i];
+  if (!ok) {
+    std::string got, want;
+    for (auto v : t->shape) got += std::to_string(v) + ",";
+    for (auto v : shape) want += std::to_string(v) + ",";
+    set_error("parameter '%s' has shape [%s] but the config implies [%s]", n.c_str(), got.c_str(), want.c_str());
+    return CAPDEC_ERR_INVALID;
+  }
+  return CAPDEC_OK;
+}
+
+template <typename T>
+static int dev_alloc(capdec_handle* h, T** p, size_t n) {
+  CAPDEC_CHECK_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  h->owned.push_back(*p);
+  return CAPDEC_OK;
+}
+
+static int pack_gates(capdec_handle* h, const std::string& wih, const std::string& whh, const std::string& bih,
+                      const std::string& bhh, int in, cudaStream_t s) {
+  const int H = h->cfg.hidden_dim;
+  float *w = nullptr, *b = nullptr;
+  CAPDEC_RETURN_IF(dev_alloc(h, &w, (size_t)4 * H * (in + H)));
+  CAPDEC_RETURN_IF(dev_alloc(h, &b, (size_t)4 * H));
+  for (int g = 0; g < 4; ++g) {
+    CAPDEC_RETURN_IF(scatter_rows(w, in + H, 4, g, 0, h->W(wih) + (size_t)g * H * in, in, H, in, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(w, in + H, 4, g, in, h->W(whh) + (size_t)g * H * H, H, H, H, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(b, 1, 4, g, 0, h->W(bih) + (size_t)g * H, 1, H, 1, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(b, 1, 4, g, 0, h->W(bhh) + (size_t)g * H, 1, H, 1, true, s));
+  }
+  h->w_gates.push_back(w);
+  h->b_gates.push_back(b);
+  h->gate_in.push_back(in);
+  return CAPDEC_OK;
+}
+
+}  // namespace
+}  // namespace capdec
+
+using namespace capdec;
+
+// ================================================ C ABI =================================================
+extern "C" {
+
+const char* capdec_last_error(void) { return g_err; }
+int capdec_version(void) { return CAPDEC_VERSION; }
+int64_t capdec_launch_count(void) { return g_launch_count; }
+
+int capdec_create(const capdec_config* cfg, capdec_handle** out) {
+  CAPDEC_REQUIRE(cfg && out, CAPDEC_ERR_INVALID, "capdec_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  CAPDEC_REQUIRE(e == cudaSuccess && ndev > 0, CAPDEC_ERR_CUDA,
+                 "capdec_create: no CUDA device (%s); libcapdec has no CPU fallback", cudaGetErrorString(e));
+  CAPDEC_REQUIRE(cfg->arch == CAPDEC_ARCH_LEGACY_SAT || cfg->arch == CAPDEC_ARCH_LSTM, CAPDEC_ERR_UNSUPPORTED,
+                 "unsupported decoder arch %d", cfg->arch);
+  CAPDEC_REQUIRE(cfg->attention >= CAPDEC_ATT_SOFT && cfg->attention <= CAPDEC_ATT_AOA, CAPDEC_ERR_UNSUPPORTED,
+                 "Unsupported attention type: %d", cfg->attention);
+  CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_BF16, CAPDEC_ERR_UNSUPPORTED,
+                 "unsupported precision %d", cfg->precision);
+  CAPDEC_REQUIRE(cfg->vocab_size > 0 && cfg->hidden_dim > 0 && cfg->embed_dim > 0 && cfg->num_layers >= 1 &&
+                     cfg->num_layers <= 7,
+                 CAPDEC_ERR_INVALID, "bad dimensions in config");
+  CAPDEC_REQUIRE(cfg->hidden_dim % 4 == 0 && cfg->embed_dim % 4 == 0 && cfg->feature_dim % 4 == 0 &&
+                     cfg->attention_dim % 4 == 0,
+                 CAPDEC_ERR_UNSUPPORTED, "hidden/embed/feature/attention dims must be multiples of 4");
+  if (cfg->arch == CAPDEC_ARCH_LSTM) {
+    CAPDEC_REQUIRE(cfg->feature_dim == cfg->hidden_dim && cfg->attention_dim == cfg->hidden_dim, CAPDEC_ERR_INVALID,
+                   "LSTM arch requires feature_dim == attention_dim == hidden_dim (attention.py:45-51)");
+    CAPDEC_REQUIRE(cfg->num_heads >= 1 && cfg->hidden_dim % cfg->num_heads == 0, CAPDEC_ERR_INVALID,
+                   "Hidden dim must be divisible by num heads");
+  } else {
+    CAPDEC_REQUIRE(cfg->num_layers == 1, CAPDEC_ERR_INVALID, "legacy decoder has a single LSTMCell");
+  }
+  capdec_handle* h = new capdec_handle();
+  h->cfg = *cfg;
+  *out = h;
+  return CAPDEC_OK;
+}
+
+void capdec_destroy(capdec_handle* h) {
+  if (!h) return;
+  for (auto& kv : h->w) cudaFree(kv.second.p);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->stream_compute) cudaStreamDestroy(h->stream_compute);
+  if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
+  delete h;
+}
+
+int capdec_set_weight(capdec_handle* h, const char* name, const float* data_dev, const int64_t* shape, int32_t rank,
+                      void* stream) {
+  CAPDEC_REQUIRE(h && name && data_dev && shape && rank >= 1 && rank <= 4, CAPDEC_ERR_INVALID,
+                 "capdec_set_weight: bad argument");
+  DevTensor t;
+  t.numel = 1;
+  for (int i = 0; i < rank; ++i) { t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+  CAPDEC_REQUIRE(t.numel > 0, CAPDEC_ERR_INVALID, "capdec_set_weight(%s): empty tensor", name);
+  auto it = h->w.find(name);
+  if (it != h->w.end()) { cudaFree(it->second.p); h->w.erase(it); }
+  CAPDEC_CHECK_CUDA(cudaMalloc((void**)&t.p, (size_t)t.numel * sizeof(float)));
+  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(t.p, data_dev, (size_t)t.numel * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+  h->w[name] = t;
+  h->finalized = false;
+  return CAPDEC_OK;
+}
+
+int capdec_finalize(capdec_handle* h, void* stream) {
+  CAPDEC_REQUIRE(h, CAPDEC_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  const capdec_config& c = h->cfg;
+  const int64_t H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim, V = c.vocab_size;
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear(); h->w_gates.clear(); h->b_gates.clear(); h->gate_in.clear();
+  h->w_hproj = h->b_hproj = h->w_init = h->b_init = h->w_aoa = h->b_aoa = nullptr;
+
+  if (is_legacy(h)) {
+    // models/decoder.py:33-54
+    CAPDEC_RETURN_IF(need(h, "enc_att.weight", {A, D})); CAPDEC_RETURN_IF(need(h, "enc_att.bias", {A}));
+    CAPDEC_RETURN_IF(need(h, "dec_att.weight", {A, H})); CAPDEC_RETURN_IF(need(h, "dec_att.bias", {A}));
+    CAPDEC_RETURN_IF(need(h, "att.weight", {1, A}));     CAPDEC_RETURN_IF(need(h, "att.bias", {1}));
+    CAPDEC_RETURN_IF(need(h, "decode_step.weight_ih", {4 * H, E + D}));
+    CAPDEC_RETURN_IF(need(h, "decode_step.weight_hh", {4 * H, H}));
+    CAPDEC_RETURN_IF(need(h, "decode_step.bias_ih", {4 * H})); CAPDEC_RETURN_IF(need(h, "decode_step.bias_hh", {4 * H}));
+    CAPDEC_RETURN_IF(need(h, "h_lin.weight", {H, D})); CAPDEC_RETURN_IF(need(h, "h_lin.bias", {H}));
+    CAPDEC_RETURN_IF(need(h, "c_lin.weight", {H, D})); CAPDEC_RETURN_IF(need(h, "c_lin.bias", {H}));
+    CAPDEC_RETURN_IF(need(h, "f_beta.weight", {D, H})); CAPDEC_RETURN_IF(need(h, "f_beta.bias", {D}));
+    CAPDEC_RETURN_IF(need(h, "fc.weight", {V, H})); CAPDEC_RETURN_IF(need(h, "fc.bias", {V}));
+    CAPDEC_RETURN_IF(need(h, "embedding.weight", {V, E}));
+    CAPDEC_RETURN_IF(pack_gates(h, "decode_step.weight_ih", "decode_step.weight_hh", "decode_step.bias_ih",
+                                "decode_step.bias_hh", (int)(E + D), s));
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->w_hproj, (size_t)(A + D) * H));
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->b_hproj, (size_t)(A + D)));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_hproj, H, 1, 0, 0, h->W("dec_att.weight"), H, (int)A, (int)H, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_hproj + A * H, H, 1, 0, 0, h->W("f_beta.weight"), H, (int)D, (int)H, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_hproj, 1, 1, 0, 0, h->W("dec_att.bias"), 1, (int)A, 1, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_hproj + A, 1, 1, 0, 0, h->W("f_beta.bias"), 1, (int)D, 1, false, s));
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->w_init, (size_t)2 * H * D));
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->b_init, (size_t)2 * H));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_init, D, 1, 0, 0, h->W("h_lin.weight"), D, (int)H, (int)D, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_init + H * D, D, 1, 0, 0, h->W("c_lin.weight"), D, (int)H, (int)D, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_init, 1, 1, 0, 0, h->W("h_lin.bias"), 1, (int)H, 1, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_init + H, 1, 1, 0, 0, h->W("c_lin.bias"), 1, (int)H, 1, false, s));
+    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(&h->energy_bias, h->W("att.bias"), sizeof(float), cudaMemcpyDeviceToHost, s));
+  } else {
+    // src/models/decoders.py:92-117
+    const int64_t Ln = c.num_layers;
+    CAPDEC_RETURN_IF(need(h, "embedding.weight", {V, E}));
+    CAPDEC_RETURN_IF(need(h, "output_layer.weight", {V, H})); CAPDEC_RETURN_IF(need(h, "output_layer.bias", {V}));
+    CAPDEC_RETURN_IF(need(h, "init_h.weight", {H * Ln, H})); CAPDEC_RETURN_IF(need(h, "init_h.bias", {H * Ln}));
+    CAPDEC_RETURN_IF(need(h, "init_c.weight", {H * Ln, H})); CAPDEC_RETURN_IF(need(h, "init_c.bias", {H * Ln}));
+    for (int l = 0; l < Ln; ++l) {
+      const int64_t in = l == 0 ? E + H : H;
+      const std::string sfx = "_l" + std::to_string(l);
+      CAPDEC_RETURN_IF(need(h, "lstm.weight_ih" + sfx, {4 * H, in}));
+      CAPDEC_RETURN_IF(need(h, "lstm.weight_hh" + sfx, {4 * H, H}));
+      CAPDEC_RETURN_IF(need(h, "lstm.bias_ih" + sfx, {4 * H}));
+      CAPDEC_RETURN_IF(need(h, "lstm.bias_hh" + sfx, {4 * H}));
+      CAPDEC_RETURN_IF(pack_gates(h, "lstm.weight_ih" + sfx, "lstm.weight_hh" + sfx, "lstm.bias_ih" + sfx,
+                                  "lstm.bias_hh" + sfx, (int)in, s));
+    }
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->w_init, (size_t)2 * Ln * H * H));
+    CAPDEC_RETURN_IF(dev_alloc(h, &h->b_init, (size_t)2 * Ln * H));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_init, H, 1, 0, 0, h->W("init_h.weight"), H, (int)(Ln * H), (int)H, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->w_init + Ln * H * H, H, 1, 0, 0, h->W("init_c.weight"), H, (int)(Ln * H), (int)H, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_init, 1, 1, 0, 0, h->W("init_h.bias"), 1, (int)(Ln * H), 1, false, s));
+    CAPDEC_RETURN_IF(scatter_rows(h->b_init + Ln * H, 1, 1, 0, 0, h->W("init_c.bias"), 1, (int)(Ln * H), 1, false, s));
+    // attention parameters (src/models/attention.py:48-52,133-137,232-239,311-320)
+    const std::string p = base_prefix(h);
+    CAPDEC_RETURN_IF(need(h, p + "query_proj.weight", {H, H})); CAPDEC_RETURN_IF(need(h, p + "query_proj.bias", {H}));
+    CAPDEC_RETURN_IF(need(h, p + "key_proj.weight", {H, H}));   CAPDEC_RETURN_IF(need(h, p + "key_proj.bias", {H}));
+    if (base_is_mha(h)) {
+      CAPDEC_RETURN_IF(need(h, p + "value_proj.weight", {H, H}));  CAPDEC_RETURN_IF(need(h, p + "value_proj.bias", {H}));
+      CAPDEC_RETURN_IF(need(h, p + "output_proj.weight", {H, H})); CAPDEC_RETURN_IF(need(h, p + "output_proj.bias", {H}));
+    } else {
+      CAPDEC_RETURN_IF(need(h, p + "energy.weight", {1, H})); CAPDEC_RETURN_IF(need(h, p + "energy.bias", {1}));
+      CAPDEC_CHECK_CUDA(cudaMemcpyAsync(&h->energy_bias, h->W(p + "energy.bias"), sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (c.attention == CAPDEC_ATT_AOA) {
+      CAPDEC_RETURN_IF(need(h, "attention.query_proj.weight", {H, H})); CAPDEC_RETURN_IF(need(h, "attention.query_proj.bias", {H}));
+      CAPDEC_RETURN_IF(need(h, "attention.info_vector_proj.0.weight", {H, 2 * H}));
+      CAPDEC_RETURN_IF(need(h, "attention.info_vector_proj.0.bias", {H}));
+      CAPDEC_RETURN_IF(need(h, "attention.info_gate_proj.0.weight", {H, 2 * H}));
+      CAPDEC_RETURN_IF(need(h, "attention.info_gate_proj.0.bias", {H}));
+      CAPDEC_RETURN_IF(dev_alloc(h, &h->w_aoa, (size_t)2 * H * 2 * H));
+      CAPDEC_RETURN_IF(dev_alloc(h, &h->b_aoa, (size_t)2 * H));
+      CAPDEC_RETURN_IF(scatter_rows(h->w_aoa, 2 * H, 2, 0, 0, h->W("attention.info_vector_proj.0.weight"), 2 * H, (int)H, (int)(2 * H), false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->w_aoa, 2 * H, 2, 1, 0, h->W("attention.info_gate_proj.0.weight"), 2 * H, (int)H, (int)(2 * H), false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->b_aoa, 1, 2, 0, 0, h->W("attention.info_vector_proj.0.bias"), 1, (int)H, 1, false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->b_aoa, 1, 2, 1, 0, h->W("attention.info_gate_proj.0.bias"), 1, (int)H, 1, false, s));
+    }
+    if (c.attention == CAPDEC_ATT_ADAPTIVE) {
+      CAPDEC_RETURN_IF(need(h, "attention.sentinel_gate.weight", {H, 2 * H})); CAPDEC_RETURN_IF(need(h, "attention.sentinel_gate.bias", {H}));
+      CAPDEC_RETURN_IF(need(h, "attention.sentinel_proj.weight", {H, H}));     CAPDEC_RETURN_IF(need(h, "attention.sentinel_proj.bias", {H}));
+      CAPDEC_RETURN_IF(need(h, "attention.adaptive_weight.weight", {1, 2 * H})); CAPDEC_RETURN_IF(need(h, "attention.adaptive_weight.bias", {1}));
+      CAPDEC_CHECK_CUDA(cudaMemcpyAsync(&h->adaptive_bias, h->W("attention.adaptive_weight.bias"), sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CAPDEC_RETURN_IF(gemm_tc_prepare(h, s));
+  CAPDEC_CHECK_CUDA(cudaStreamSynchronize(s));
+  h->finalized = true;
+  return CAPDEC_OK;
+}
+
+size_t capdec_workspace_bytes(const capdec_handle* h, int32_t B, int32_t L, int32_t k, int32_t T) {
+  if (!h) return 0;
+  Arena ar(nullptr, 0);
+  Session S;
+  carve(h, ar, S, B, L, k, T, MODE_BEAM);
+  size_t beam = ar.off;
+  Arena ar2(nullptr, 0);
+  Session S2;
+  carve(h, ar2, S2, B, L, k, T, MODE_TEACHER);
+  return align_up((beam > ar2.off ? beam : ar2.off) + 4096, 4096);
+}
+
+int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
+                       int32_t L, int32_t k, int32_t T, float length_penalty, int32_t* out_tok, int32_t* out_len,
+                       float* out_score, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes,
+                       void* stream) {
+  CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, k, T));
+  CAPDEC_REQUIRE(out_tok && out_len && out_score, CAPDEC_ERR_INVALID, "output pointers must not be null");
+  CAPDEC_REQUIRE(is_legacy(h) ? mask == nullptr : true, CAPDEC_ERR_UNSUPPORTED, "legacy decoder takes no padding mask");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, k, T, MODE_BEAM);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
+  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  // HF: output_fill_value = pad_token_id or eos_token_id  (generation/utils.py:3187)
+  const int fill = c.pad_token_id ? c.pad_token_id : c.eos_token_id;
+  CAPDEC_RETURN_IF(beam_init(S.beam, B, k, T, c.bos_token_id, fill, s));
+  CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, c.bos_token_id, s));
+  CAPDEC_RETURN_IF(commit(h, S, nullptr, nullptr, 0, -1, false, s));
+  const int k2 = 2 * k;
+  for (int cur_len = 1; cur_len < T; ++cur_len) {
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
+    CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, k2, S.cand_lp, S.cand_idx, nullptr, s));
+    // prompt length is 1 (BOS): finished score / (cur_len+1-1)^lp ; heuristic uses ((cur_len+1)-1)^lp
+    const float div_fin = (float)pow((double)cur_len, (double)length_penalty);
+    const float div_heur = div_fin;
+    const size_t o = (size_t)(cur_len - 1) * B * k2;
+    CAPDEC_RETURN_IF(beam_step(S.beam, B, k, T, c.vocab_size, cur_len, c.eos_token_id, div_fin, div_heur, S.cand_lp,
+                               S.cand_idx, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
+                               dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, s));
+    if (cur_len + 1 < T) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s));
+  }
+  CAPDEC_RETURN_IF(beam_finalize(S.beam, (T - 1) & 1, B, k, T, out_tok, out_len, out_score, s));
+  return CAPDEC_OK;
+}
+
+int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
+                         int32_t L, int32_t T, int32_t start_token_id, int32_t* out_tok, float* out_alpha, void* ws,
+                         size_t ws_bytes, void* stream) {
+  CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, 1, T));
+  CAPDEC_REQUIRE(out_tok, CAPDEC_ERR_INVALID, "output pointer must not be null");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, 1, T, MODE_GREEDY);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
+  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, start_token_id, s));
+  CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));  // out[:,0] = start (decoders.py:271)
+  for (int t = 0; t < T; ++t) {
+    float* alpha = out_alpha ? out_alpha + (size_t)t * L : nullptr;
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, s));
+    if (t + 1 == T) break;  // the last argmax is discarded (decoders.py:306 after the final store at :271)
+    CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, 1, S.cand_lp, S.next_tok, nullptr, s));
+    CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, t + 1, true, s));
+  }
+  return CAPDEC_OK;
+}
+
+int capdec_decode_sample(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
+                         int32_t L, int32_t num_samples, int32_t with_greedy, int32_t T, const float* uniforms,
+                         int32_t* out_tok, float* out_lp, void* ws, size_t ws_bytes, void* stream) {
+  const int k = num_samples + (with_greedy ? 1 : 0);
+  CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, k, T));
+  CAPDEC_REQUIRE(num_samples >= 0 && out_tok && (num_samples == 0 || uniforms), CAPDEC_ERR_INVALID, "bad sampling arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, k, T, MODE_SAMPLE);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
+  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, c.bos_token_id, s));
+  CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));
+  for (int t = 0; t + 1 < T; ++t) {  // trainer.py:413
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
+    CAPDEC_RETURN_IF(sample_rows(S.logits, c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
+                                 with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s));
+    if (out_lp) {
+      // out_lp[r, t] = step_lp[r]
+      CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(out_lp + t, (size_t)(T - 1) * sizeof(float), S.step_lp, sizeof(float),
+                                          sizeof(float), S.R, cudaMemcpyDeviceToDevice, s));
+    }
+    CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, t + 1, t + 2 < T, s));
+  }
+  return CAPDEC_OK;
+}
+
+int capdec_forward_teacher(capdec_handle* h, const float* feats, int32_t B, int32_t L, const int32_t* captions,
+                           int32_t cap_stride, const int32_t* dec_len, float* preds, float* alphas, void* ws,
+                           size_t ws_bytes, void* stream) {
+  CAPDEC_RETURN_IF(check_common(h, feats, feats, B, L, 1, 2));
+  CAPDEC_REQUIRE(is_legacy(h), CAPDEC_ERR_UNSUPPORTED, "capdec_forward_teacher mirrors models/decoder.py::Decoder.forward only");
+  CAPDEC_REQUIRE(captions && dec_len && preds, CAPDEC_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int T = 0;
+  for (int b = 0; b < B; ++b) {
+    CAPDEC_REQUIRE(b == 0 || dec_len[b] <= dec_len[b - 1], CAPDEC_ERR_INVALID,
+                   "captions must be sorted by decreasing length (data_loader.py:65 collate_fn)");
+    T = dec_len[b] > T ? dec_len[b] : T;
+  }
+  CAPDEC_REQUIRE(T >= 1 && T <= cap_stride, CAPDEC_ERR_INVALID, "bad caption lengths");
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, 1, T, MODE_TEACHER);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, V = c.vocab_size;
+  CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
+  for (int t = 0; t < T; ++t) {
+    int bt = 0;
+    for (int b = 0; b < B; ++b) bt += dec_len[b] > t ? 1 : 0;  // models/decoder.py:149
+    // next_tok[r] = captions[r, t]
+    CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(S.next_tok, sizeof(int32_t), captions + t, (size_t)cap_stride * sizeof(int32_t),
+                                        sizeof(int32_t), bt, cudaMemcpyDeviceToDevice, s));
+    GatherArgs g{};
+    g.rows = bt; g.tok = S.next_tok; g.src = nullptr; g.embedding = h->W("embedding.weight"); g.E = E;
+    g.x_emb = S.X[0]; g.ld_x = S.ldX[0]; g.pos = -1; g.n_state = 0;
+    if (t > 0) {
+      g.state_src[0] = S.hnew[0]; g.ld_src[0] = H; g.state_dst[0] = S.X[0] + E + D; g.ld_dst[0] = S.ldX[0]; g.width[0] = H;
+      g.state_src[1] = S.cnew[0]; g.ld_src[1] = H; g.state_dst[1] = S.c[0]; g.ld_dst[1] = H; g.width[1] = H;
+      g.n_state = 2;
+    }
+    CAPDEC_RETURN_IF(gather_rows(g, s));
+    CAPDEC_RETURN_IF(step_legacy(h, S, feats, bt, preds + (size_t)t * V, (int64_t)T * V,
+                                 alphas ? alphas + (size_t)t * L : nullptr, (int64_t)T * L, s));
+  }
+  return CAPDEC_OK;
+}
+
+int capdec_attention_forward(capdec_handle* h, const float* query, const float* feats, const uint8_t* mask,
+                             const float* memory, const float* cell, int32_t B, int32_t L, int32_t k, float* context,
+                             float* weights, void* ws, size_t ws_bytes, void* stream) {
+  CAPDEC_RETURN_IF(check_common(h, feats, feats, B, L, k, 2));
+  CAPDEC_REQUIRE(!is_legacy(h), CAPDEC_ERR_UNSUPPORTED, "capdec_attention_forward mirrors src/models/attention.py");
+  CAPDEC_REQUIRE(query && context, CAPDEC_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, k, 2, MODE_ATTENTION);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const int H = h->cfg.hidden_dim;
+  CAPDEC_RETURN_IF(prologue_attention(h, S, feats, s));
+  return run_attention(h, S, feats, mask, query, H, memory, H, cell, H, B, context, weights, L, s);
+}
+
+int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const float* pooled_host, int32_t B, int32_t L,
+                            int32_t k, int32_t T, float length_penalty, int32_t chunk, int32_t* out_tok_host,
+                            int32_t* out_len_host, float* out_score_host) {
+  CAPDEC_RETURN_IF(check_common(h, feats_host, pooled_host, B, L, k, T));
+  CAPDEC_REQUIRE(out_tok_host && out_len_host && out_score_host, CAPDEC_ERR_INVALID, "output pointers must not be null");
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  if (chunk <= 0) chunk = 512;
+  if (chunk > B) chunk = B;
+  const size_t feat_chunk = align_up((size_t)chunk * L * c.feature_dim * sizeof(float), 256);
+  const size_t pool_chunk = align_up((size_t)chunk * c.hidden_dim * sizeof(float), 256);
+  const size_t ws_bytes = capdec_workspace_bytes(h, chunk, L, k, T);
+  const size_t out_bytes = align_up((size_t)B * T * 4, 256) + 2 * align_up((size_t)B * 4, 256);
+  const size_t total = 2 * feat_chunk + 2 * pool_chunk + ws_bytes + out_bytes;
+  if (h->stage_bytes < total) {
+    if (h->stage_dev) CAPDEC_CHECK_CUDA(cudaFree(h->stage_dev));
+    h->stage_dev = nullptr; h->stage_bytes = 0;
+    CAPDEC_CHECK_CUDA(cudaMalloc(&h->stage_dev, total));
+    h->stage_bytes = total;
+  }
+  if (!h->stream_compute) {
+    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_compute, cudaStreamNonBlocking));
+    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  char* base = (char*)h->stage_dev;
+  float* d_feat[2] = {(float*)base, (float*)(base + feat_chunk)};
+  float* d_pool[2] = {(float*)(base + 2 * feat_chunk), (float*)(base + 2 * feat_chunk + pool_chunk)};
+  void* d_ws = base + 2 * feat_chunk + 2 * pool_chunk;
+  int32_t* d_tok = (int32_t*)((char*)d_ws + ws_bytes);
+  int32_t* d_len = (int32_t*)((char*)d_tok + align_up((size_t)B * T * 4, 256));
+  float* d_score = (float*)((char*)d_len + align_up((size_t)B * 4, 256));
+  const size_t img_floats = (size_t)L * c.feature_dim;
+  int idx = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++idx) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    const int buf = idx & 1;
+    if (idx >= 2) CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_done[buf], 0));
+    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_feat[buf], feats_host + (size_t)b0 * img_floats, (size_t)nb * img_floats * sizeof(float),
+                                      cudaMemcpyHostToDevice, h->stream_copy));
+    if (pooled_host)
+      CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_pool[buf], pooled_host + (size_t)b0 * c.hidden_dim,
+                                        (size_t)nb * c.hidden_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream_copy));
+    CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_copied[buf], h->stream_copy));
+    CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_compute, h->ev_copied[buf], 0));
+    CAPDEC_RETURN_IF(capdec_decode_beam(h, d_feat[buf], pooled_host ? d_pool[buf] : nullptr, nullptr, nb, L, k, T,
+                                        length_penalty, d_tok + (size_t)b0 * T, d_len + b0, d_score + b0, nullptr,
+                                        nullptr, nullptr, d_ws, ws_bytes, h->stream_compute));
+    CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_done[buf], h->stream_compute));
+  }
+  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_tok_host, d_tok, (size_t)B * T * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_score_host, d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+  CAPDEC_CHECK_CUDA(cudaStreamSynchronize(h->stream_compute));
+  return CAPDEC_OK;
+}
+
+int capdec_linear(int32_t precision, const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,
+                  float* c, int64_t ldc, int32_t m, int32_t n, int32_t k, void* stream) {
+  GemmArgs g{};
+  g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.C = c; g.ldc = ldc; g.M = m; g.N = n; g.K = k;
+  return gemm(precision, g, EPI_STORE, (cudaStream_t)stream);
+}
+
+int capdec_lse_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t topk, float* out_lp,
+                    int32_t* out_idx, float* out_lse, void* stream) {
+  return lse_topk(logits, ld, rows, vocab, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared helpers for libcapdec (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+
+#include "../../include/capdec.h"
+
+namespace capdec {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_launch_count;
+
+#define CAPDEC_CHECK_CUDA(expr)                                                          \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      capdec::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CAPDEC_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define CAPDEC_RETURN_IF(expr)          \
+  do {                                  \
+    int _s = (expr);                    \
+    if (_s != CAPDEC_OK) return _s;     \
+  } while (0)
+
+#define CAPDEC_REQUIRE(cond, code, ...)     \
+  do {                                      \
+    if (!(cond)) {                          \
+      capdec::set_error(__VA_ARGS__);       \
+      return (code);                        \
+    }                                       \
+  } while (0)
+
+// every kernel launch in the library goes through this so launches can be counted and checked
+#define CAPDEC_LAUNCH_CHECK()                                                            \
+  do {                                                                                   \
+    ++capdec::g_launch_count;                                                            \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      capdec::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CAPDEC_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (tiles are read once per CTA)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// ---- GEMM front door (gemm_ffma.cu / gemm_tc.cu) ---------------------------------------------------
+enum Epilogue : int {
+  EPI_STORE = 0,         // C = acc + bias
+  EPI_SIGMOID_TAIL = 1,  // columns >= n_split get sigmoid(acc + bias)   (legacy [dec_att | f_beta] GEMM)
+  EPI_LSTM = 2,          // N = 4*H gate-interleaved (n = 4*j + {i,f,g,o}); fused cell update
+  EPI_TANH = 3,          // tanh(acc + bias)
+  EPI_AOA = 4            // N = 2*H interleaved (n = 2*j + {info, gate}); out = tanh(info)*sigmoid(gate)
+};
+
+struct GemmArgs {
+  const float* A; int64_t lda;      // [M,K]
+  const float* W; int64_t ldw;      // [N,K]  (nn.Linear weight layout)
+  const float* bias;                // [N] or nullptr
+  float* C; int64_t ldc;            // EPI_STORE/SIGMOID_TAIL/TANH: [M,N]; EPI_LSTM: h_out [M,H]; EPI_AOA: out [M,H]
+  int M, N, K;
+  int n_split;                      // EPI_SIGMOID_TAIL
+  const float* c_in; int64_t ldcin; // EPI_LSTM: previous cell state [M,H]
+  float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
+  float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
+};
+
+int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s);
+int gemm(int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
+
+}  // namespace capdec

@@ -1,0 +1,476 @@
+// Token selection (log-softmax + top-k / argmax / inverse-CDF sampling), HF-static beam
+// bookkeeping, and the in-place index gathers that reorder decoder state by back-pointer.
+#include "select.cuh"
+#include "attention.cuh"
+#include <limits.h>
+
+namespace capdec {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kNeg = -1.0e9f;
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better(ov, oi, v, i)) { v = ov; i = oi; }
+  }
+}
+
+__device__ __forceinline__ float block_max(float v, float* s_tmp) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_tmp[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w) r = fmaxf(r, s_tmp[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* s_tmp) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) r += s_tmp[w];
+  __syncthreads();
+  return r;
+}
+
+// One CTA per row.  The row is staged in shared memory; element i is owned by thread i % 256, which
+// caches its best remaining (value, index); each of the K rounds is a block arg-max after which only
+// the winner's owner rescans its elements.
+__global__ void __launch_bounds__(kThreads) lse_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, int K,
+                                                            float* __restrict__ out_lp, int32_t* __restrict__ out_idx,
+                                                            float* __restrict__ out_lse) {
+  extern __shared__ float row[];
+  __shared__ float s_tmp[kThreads / 32];
+  __shared__ float s_v[kThreads / 32];
+  __shared__ int s_i[kThreads / 32];
+  __shared__ int s_win;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = logits + (int64_t)blockIdx.x * ld;
+
+  float bv = -INFINITY;
+  int bi = INT_MAX;
+  for (int i = tid; i < V; i += kThreads) {
+    const float v = x[i];
+    row[i] = v;
+    if (v > bv) { bv = v; bi = i; }
+  }
+  const float M = block_max(bv, s_tmp);
+  float sum = 0.f;
+  for (int i = tid; i < V; i += kThreads) sum += expf(row[i] - M);
+  const float S = block_sum(sum, s_tmp);
+  const float logS = logf(S);
+  if (tid == 0 && out_lse) out_lse[blockIdx.x] = M + logS;
+
+  for (int r = 0; r < K; ++r) {
+    float v = bv;
+    int i = bi;
+    warp_argmax(v, i);
+    if (lane == 0) { s_v[warp] = v; s_i[warp] = i; }
+    __syncthreads();
+    if (tid == 0) {
+      float wv = s_v[0];
+      int wi = s_i[0];
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; ++w)
+        if (better(s_v[w], s_i[w], wv, wi)) { wv = s_v[w]; wi = s_i[w]; }
+      const bool valid = wi != INT_MAX;
+      out_lp[(int64_t)blockIdx.x * K + r] = valid ? (wv - M) - logS : -INFINITY;
+      out_idx[(int64_t)blockIdx.x * K + r] = valid ? wi : -1;
+      s_win = valid ? wi : -1;
+    }
+    __syncthreads();
+    const int w = s_win;
+    if (w >= 0 && (w % kThreads) == tid) {
+      row[w] = -INFINITY;
+      bv = -INFINITY;
+      bi = INT_MAX;
+      for (int j = tid; j < V; j += kThreads) {
+        const float t = row[j];
+        if (t > bv) { bv = t; bi = j; }
+      }
+      if (bv == -INFINITY) bi = INT_MAX;  // exhausted
+    }
+  }
+}
+
+// One CTA per row: inverse-CDF draw in vocabulary index order (double prefix sums), or argmax for the greedy slot.
+__global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restrict__ logits, int64_t ld, int V,
+                                                          const float* __restrict__ uniforms, int64_t ld_u, int step,
+                                                          int rows_per_image, int greedy_slot,
+                                                          int32_t* __restrict__ out_tok, float* __restrict__ out_lp) {
+  extern __shared__ float row[];
+  __shared__ float s_tmp[kThreads / 32];
+  __shared__ float s_v[kThreads / 32];
+  __shared__ int s_i[kThreads / 32];
+  __shared__ double s_part[kThreads];
+  __shared__ double s_total;
+  __shared__ int s_cnt[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.x;
+  const float* x = logits + (int64_t)r * ld;
+
+  float bv = -INFINITY;
+  int bi = INT_MAX;
+  for (int i = tid; i < V; i += kThreads) {
+    const float v = x[i];
+    row[i] = v;
+    if (v > bv) { bv = v; bi = i; }
+  }
+  const float M = block_max(bv, s_tmp);  // includes the barrier that publishes row[]
+  const bool greedy = greedy_slot >= 0 && (r % rows_per_image) == greedy_slot;
+
+  // contiguous chunk per thread so prefix sums follow index order
+  const int chunk = (V + kThreads - 1) / kThreads;
+  const int beg = min(V, tid * chunk), end = min(V, beg + chunk);
+  double local = 0.0;
+  for (int i = beg; i < end; ++i) local += (double)expf(row[i] - M);
+  s_part[tid] = local;
+  __syncthreads();
+  if (tid == 0) {  // serial exclusive scan over 256 partials (tiny)
+    double run = 0.0;
+    for (int t = 0; t < kThreads; ++t) { const double v = s_part[t]; s_part[t] = run; run += v; }
+    s_total = run;
+  }
+  __syncthreads();
+  const double S = s_total;
+  int tok;
+  if (greedy) {  // block-uniform branch
+    float v = bv; int i = bi;
+    warp_argmax(v, i);
+    if (lane == 0) { s_v[warp] = v; s_i[warp] = i; }
+    __syncthreads();
+    float wv = s_v[0]; int wi = s_i[0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w)
+      if (better(s_v[w], s_i[w], wv, wi)) { wv = s_v[w]; wi = s_i[w]; }
+    tok = wi;
+  } else {
+    const double target = (double)uniforms[(int64_t)r * ld_u + step] * S;
+    double run = s_part[tid];
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) {
+      run += (double)expf(row[i] - M);
+      cnt += (run <= target) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) total += s_cnt[w];
+    tok = min(total, V - 1);
+  }
+  if (tid == 0) {
+    out_tok[r] = tok;
+    if (out_lp) out_lp[r] = (row[tok] - M) - logf((float)S);
+  }
+}
+
+// ---- beam bookkeeping: one thread per image -------------------------------------------------------
+__global__ void beam_init_kernel(BeamState st, int B, int k, int T, int bos, int fill) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= B) return;
+  for (int b = 0; b < k; ++b) {
+    const int64_t o = ((int64_t)img * k + b) * T;
+    for (int t = 0; t < T; ++t) {
+      const int v = t == 0 ? bos : fill;
+      st.run_seq[0][o + t] = v; st.run_seq[1][o + t] = v;
+      st.fin_seq[0][o + t] = v; st.fin_seq[1][o + t] = v;
+    }
+    st.run_score[img * k + b] = b == 0 ? 0.f : kNeg;
+    st.fin_score[img * k + b] = kNeg;
+    st.fin_len[img * k + b] = 1;
+    st.fin_flag[img * k + b] = 0;
+  }
+  st.unsatisfied[img] = 1;
+}
+
+__global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int cur_len, int eos, float div_fin,
+                                 float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
+                                 int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
+                                 int32_t* dbg_tok, int32_t* dbg_beam) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= B) return;
+  constexpr int KM = kMaxRowsPerImage, K2 = kMaxTopK;
+  const int k2 = 2 * k;
+  const int par = (cur_len - 1) & 1;  // read buffers [par], write [par ^ 1]
+  const int32_t* run_old = st.run_seq[par] + (int64_t)img * k * T;
+  int32_t* run_new = st.run_seq[par ^ 1] + (int64_t)img * k * T;
+  const int32_t* fin_old = st.fin_seq[par] + (int64_t)img * k * T;
+  int32_t* fin_new = st.fin_seq[par ^ 1] + (int64_t)img * k * T;
+
+  // (c) top-2k continuations over the k*V accumulated log-probs: k-way merge of the per-row sorted lists
+  float score[KM];
+  int ptr[KM];
+  for (int b = 0; b < k; ++b) { score[b] = st.run_score[img * k + b]; ptr[b] = 0; }
+  float top_lp[K2];
+  int top_tok[K2], top_beam[K2];
+  for (int j = 0; j < k2; ++j) {
+    float bv = -INFINITY;
+    int bb = -1, bt = 0;
+    for (int b = 0; b < k; ++b) {
+      if (ptr[b] >= k2) continue;
+      const int64_t o = ((int64_t)img * k + b) * k2 + ptr[b];
+      const int tok = cand_idx[o];
+      if (tok < 0) continue;
+      const float v = cand_lp[o] + score[b];
+      if (bb < 0 || v > bv) { bv = v; bb = b; bt = tok; }  // ties keep the lower flat index (lower beam first)
+    }
+    top_lp[j] = bv; top_tok[j] = bt; top_beam[j] = bb < 0 ? 0 : bb;
+    if (bb >= 0) ptr[bb]++;
+    if (dbg_lp) {
+      const int64_t o = (int64_t)img * k2 + j;
+      dbg_lp[o] = bv; dbg_tok[o] = bt; dbg_beam[o] = top_beam[j];
+    }
+  }
+
+  // (d) stopping criteria on the extended sequences: MaxLength | Eos
+  const bool at_max = cur_len + 1 >= T;
+  bool hits[K2];
+  float run_lp[K2];
+  for (int j = 0; j < k2; ++j) {
+    hits[j] = at_max || top_tok[j] == eos;
+    run_lp[j] = top_lp[j] + (hits[j] ? kNeg : 0.f);
+  }
+
+  // (e) next running beams: top-k of run_lp (stable)
+  bool used[K2];
+  for (int j = 0; j < k2; ++j) used[j] = false;
+  float new_score[KM];
+  for (int i = 0; i < k; ++i) {
+    int bj = -1;
+    for (int j = 0; j < k2; ++j)
+      if (!used[j] && (bj < 0 || run_lp[j] > run_lp[bj])) bj = j;
+    used[bj] = true;
+    new_score[i] = run_lp[bj];
+    const int32_t* srcp = run_old + (int64_t)top_beam[bj] * T;
+    int32_t* dstp = run_new + (int64_t)i * T;
+    for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
+    dstp[cur_len] = top_tok[bj];
+    next_tok[img * k + i] = top_tok[bj];
+    src_row[img * k + i] = img * k + top_beam[bj];
+  }
+
+  // (f) finished beams: merge the k finished with the 2k candidates, keep the best k (stable)
+  const bool unsat = st.unsatisfied[img] != 0;
+  float m_sc[KM + K2];
+  for (int b = 0; b < k; ++b) m_sc[b] = st.fin_score[img * k + b];
+  for (int j = 0; j < k2; ++j) {
+    const bool just_fin = hits[j] && j < k;
+    float v = top_lp[j] / div_fin;
+    v += unsat ? 0.f : kNeg;
+    v += just_fin ? 0.f : kNeg;
+    m_sc[k + j] = v;
+  }
+  bool m_used[KM + K2];
+  for (int j = 0; j < k + k2; ++j) m_used[j] = false;
+  float f_sc[KM];
+  int f_len[KM];
+  uint8_t f_flag[KM];
+  for (int i = 0; i < k; ++i) {
+    int bj = -1;
+    for (int j = 0; j < k + k2; ++j)
+      if (!m_used[j] && (bj < 0 || m_sc[j] > m_sc[bj])) bj = j;
+    m_used[bj] = true;
+    f_sc[i] = m_sc[bj];
+    int32_t* dstp = fin_new + (int64_t)i * T;
+    if (bj < k) {
+      const int32_t* srcp = fin_old + (int64_t)bj * T;
+      for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
+      f_len[i] = st.fin_len[img * k + bj];
+      f_flag[i] = st.fin_flag[img * k + bj];
+    } else {
+      const int j = bj - k;
+      const int32_t* srcp = run_old + (int64_t)top_beam[j] * T;
+      for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
+      dstp[cur_len] = top_tok[j];
+      f_len[i] = cur_len + 1;
+      f_flag[i] = (hits[j] && j < k) ? 1 : 0;
+    }
+  }
+  float fmin = f_sc[0];
+  for (int i = 0; i < k; ++i) {
+    st.fin_score[img * k + i] = f_sc[i];
+    st.fin_len[img * k + i] = f_len[i];
+    st.fin_flag[img * k + i] = f_flag[i];
+    st.run_score[img * k + i] = new_score[i];
+    fmin = fminf(fmin, f_sc[i]);
+  }
+
+  // (g) early-stop heuristic (early_stopping=False): can the best running beam still beat the worst finished?
+  const float best_possible = new_score[0] / div_heur;
+  bool any = false;
+  for (int i = 0; i < k; ++i) any = any || (best_possible > (f_flag[i] ? fmin : kNeg));
+  st.unsatisfied[img] = (unsat && any) ? 1 : 0;
+}
+
+__global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
+                                     float* out_score) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T) return;
+  const int img = i / T, t = i - img * T;
+  out_tok[i] = st.fin_seq[parity][((int64_t)img * k) * T + t];
+  if (t == 0) {
+    out_len[img] = st.fin_len[img * k];
+    out_score[img] = st.fin_score[img * k];
+  }
+}
+
+// ---- gathers ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int src = a.src ? a.src[r] : r;
+  if (a.tok) {
+    const int tok = a.tok[r];
+    if (a.tok_out && tid == 0 && a.pos >= 0) a.tok_out[(int64_t)r * a.ld_tok + a.pos] = tok;
+    if (a.embedding) {
+      const float4* e = reinterpret_cast<const float4*>(a.embedding + (int64_t)tok * a.E);
+      float4* d = reinterpret_cast<float4*>(a.x_emb + (int64_t)r * a.ld_x);
+      for (int i = tid; i < a.E / 4; i += blockDim.x) d[i] = e[i];
+    }
+  }
+  for (int sidx = 0; sidx < a.n_state; ++sidx) {
+    const float4* sp = reinterpret_cast<const float4*>(a.state_src[sidx] + (int64_t)src * a.ld_src[sidx]);
+    float4* dp = reinterpret_cast<float4*>(a.state_dst[sidx] + (int64_t)r * a.ld_dst[sidx]);
+    for (int i = tid; i < a.width[sidx] / 4; i += blockDim.x) dp[i] = sp[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restrict__ feats, int L, int D,
+                                                           float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
+  if (c >= D / 4) return;
+  const float4* p = reinterpret_cast<const float4*>(feats + (int64_t)b * L * D) + c;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const float4 v = ldg_stream(p + (int64_t)l * (D / 4));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float fl = (float)L;
+  reinterpret_cast<float4*>(out + (int64_t)b * D)[c] = make_float4(acc.x / fl, acc.y / fl, acc.z / fl, acc.w / fl);
+}
+
+__global__ void __launch_bounds__(128) expand_rows_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                          float* __restrict__ dst, int64_t ld_dst, int k, int width) {
+  const int r = blockIdx.x;
+  const float4* sp = reinterpret_cast<const float4*>(src + (int64_t)(r / k) * ld_src);
+  float4* dp = reinterpret_cast<float4*>(dst + (int64_t)r * ld_dst);
+  for (int i = threadIdx.x; i < width / 4; i += blockDim.x) dp[i] = sp[i];
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, float* out_lp, int32_t* out_idx,
+             float* out_lse, cudaStream_t s) {
+  CAPDEC_REQUIRE(topk >= 1 && topk <= kMaxTopK, CAPDEC_ERR_UNSUPPORTED, "lse_topk: topk %d not in [1,%d]", topk, kMaxTopK);
+  CAPDEC_REQUIRE(vocab >= 1 && (size_t)vocab * 4 <= 220 * 1024, CAPDEC_ERR_UNSUPPORTED,
+                 "lse_topk: vocab %d does not fit a shared-memory row", vocab);
+  if (rows == 0) return CAPDEC_OK;
+  const size_t smem = (size_t)vocab * sizeof(float);
+  if (smem > 48 * 1024)
+    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(lse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lse_topk_kernel<<<rows, kThreads, smem, s>>>(logits, ld, vocab, topk, out_lp, out_idx, out_lse);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const float* uniforms, int64_t ld_u, int step,
+                int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s) {
+  CAPDEC_REQUIRE(vocab >= 1 && (size_t)vocab * 4 <= 200 * 1024, CAPDEC_ERR_UNSUPPORTED,
+                 "sample_rows: vocab %d does not fit a shared-memory row", vocab);
+  if (rows == 0) return CAPDEC_OK;
+  const size_t smem = (size_t)vocab * sizeof(float);
+  if (smem > 48 * 1024)
+    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_kernel<<<rows, kThreads, smem, s>>>(logits, ld, vocab, uniforms, ld_u, step, rows_per_image, greedy_slot,
+                                             out_tok, out_lp);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int beam_init(const BeamState& st, int B, int k, int T, int bos, int fill, cudaStream_t s) {
+  if (B == 0) return CAPDEC_OK;
+  beam_init_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, k, T, bos, fill);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int beam_step(const BeamState& st, int B, int k, int T, int V, int cur_len, int eos, float len_div_finished,
+              float len_div_heuristic, const float* cand_lp, const int32_t* cand_idx, int32_t* next_tok,
+              int32_t* src_row, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, cudaStream_t s) {
+  CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "beam_step: num_beams %d not in [1,%d]", k,
+                 kMaxRowsPerImage);
+  if (B == 0) return CAPDEC_OK;
+  beam_step_kernel<<<ceil_div(B, 64), 64, 0, s>>>(st, B, k, T, V, cur_len, eos, len_div_finished, len_div_heuristic,
+                                                  cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int beam_finalize(const BeamState& st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
+                  float* out_score, cudaStream_t s) {
+  if (B == 0) return CAPDEC_OK;
+  beam_finalize_kernel<<<ceil_div(B * T, 256), 256, 0, s>>>(st, parity, B, k, T, out_tok, out_len, out_score);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int gather_rows(const GatherArgs& a, cudaStream_t s) {
+  CAPDEC_REQUIRE(a.n_state <= 16, CAPDEC_ERR_INVALID, "gather_rows: too many state tensors");
+  if (a.rows == 0) return CAPDEC_OK;
+  gather_rows_kernel<<<a.rows, 128, 0, s>>>(a);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int mean_regions(const float* feats, int B, int L, int D, float* out, cudaStream_t s) {
+  CAPDEC_REQUIRE(D % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "mean_regions: D must be a multiple of 4");
+  if (B == 0) return CAPDEC_OK;
+  dim3 grid(ceil_div(D / 4, 256), B);
+  mean_regions_kernel<<<grid, 256, 0, s>>>(feats, L, D, out);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int expand_rows(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int k, int width, cudaStream_t s) {
+  CAPDEC_REQUIRE(width % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0, CAPDEC_ERR_INVALID, "expand_rows: widths must be multiples of 4");
+  if (rows == 0) return CAPDEC_OK;
+  expand_rows_kernel<<<rows, 128, 0, s>>>(src, ld_src, dst, ld_dst, k, width);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s) {
+  if (n == 0) return CAPDEC_OK;
+  fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+int fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
+  if (n == 0) return CAPDEC_OK;
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+}  // namespace capdec

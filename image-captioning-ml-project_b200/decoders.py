@@ -1,0 +1,139 @@
+"""Drop-in caption decoders (mirror of /root/reference/src/models/decoders.py, LSTM family).
+
+`LSTMDecoder` keeps the reference's constructor signature, parameter names (state_dict-compatible
+with src/models/decoders.py:92-117) and `generate(encoder_features, max_length, start_token_id=1,
+**kwargs) -> (LongTensor, info)` contract; `generate` runs in libcapdec.  Extra keyword arguments
+select the decode entry points the north star adds on the same step kernels:
+
+    num_beams=k            HF-static beam search (the algorithm GPT2Decoder.generate reaches at
+                           decoders.py:645); returns HF-cropped sequences, info["scores"], info["lengths"]
+    do_sample=True         ancestral sampling rollout (trainer.py:383-438): num_samples rows per image
+                           (+ with_greedy=True for the SCST baseline row), uniforms=... to fix the draws
+
+The teacher-forced `forward(captions=...)` is the training path (out of scope per SURVEY.md section 8) and raises.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+from .attention import build_attention
+from .config import AttentionConfig, DecoderConfig, DecoderType, attention_kind, decoder_kind
+from .engine import Engine
+
+
+class CaptionDecoder(nn.Module, ABC):
+    """Base class for all caption decoders (decoders.py:20-69)."""
+
+    @abstractmethod
+    def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs) -> Dict[str, torch.Tensor]:
+        ...
+
+    @abstractmethod
+    def generate(self, encoder_features, max_length: int, **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        ...
+
+
+def _padding_mask(encoder_features):
+    """decoders.py:291 passes key_padding_mask = ~attention_mask.  The reference encoders emit a float
+    mask (encoders.py:84) on which `~` raises; here any dtype is accepted, non-zero = valid region."""
+    m = encoder_features.get("attention_mask", None)
+    if m is None:
+        return None
+    return ~(m.bool())
+
+
+class LSTMDecoder(CaptionDecoder):
+    """LSTM decoder with attention (decoders.py:72-314)."""
+
+    def __init__(self, config: DecoderConfig, attention_config: AttentionConfig, vocab_size: int, pad_token_id: int,
+                 embedding_dim: int = None, bos_token_id: int = 1, eos_token_id: int = 2, precision: str = "fp32"):
+        super().__init__()
+        self.hidden_dim = config.hidden_dim
+        self.embedding_dim = embedding_dim or config.hidden_dim
+        self.num_layers = config.num_layers
+        self.vocab_size = vocab_size
+        self.dropout_p = config.dropout
+        self.pad_token_id = pad_token_id
+        self.bos_token_id, self.eos_token_id = bos_token_id, eos_token_id
+        self.max_length = config.max_length
+        self.precision = precision
+        self._attention_kind = attention_kind(attention_config)
+        self._attention_heads = attention_config.num_heads
+        self._attention_temperature = attention_config.temperature
+        # same construction order as the reference => identical random init under the same seed
+        self.embedding = nn.Embedding(vocab_size, self.embedding_dim, padding_idx=pad_token_id)
+        self.lstm = nn.LSTM(input_size=self.embedding_dim + self.hidden_dim, hidden_size=self.hidden_dim,
+                            num_layers=self.num_layers, batch_first=True,
+                            dropout=self.dropout_p if self.num_layers > 1 else 0)
+        self.attention = build_attention(attention_config)
+        self.output_layer = nn.Linear(self.hidden_dim, vocab_size)
+        self.init_h = nn.Linear(self.hidden_dim, self.hidden_dim * self.num_layers)
+        self.init_c = nn.Linear(self.hidden_dim, self.hidden_dim * self.num_layers)
+        self.dropout = nn.Dropout(self.dropout_p)
+
+    # ---- engine lifecycle: re-bind when parameters, device or precision change
+    def _engine(self, device) -> Engine:
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(device), self.precision)
+        if getattr(self, "_eng_sig", None) != sig:
+            H = self.hidden_dim
+            cfg = _capi.Config(arch=_capi.ARCH_LSTM, attention=_capi.ATT[self._attention_kind],
+                               precision=_capi.PREC[self.precision], vocab_size=self.vocab_size, hidden_dim=H,
+                               embed_dim=self.embedding_dim, feature_dim=H, attention_dim=H,
+                               num_layers=self.num_layers, num_heads=int(self._attention_heads),
+                               temperature=float(self._attention_temperature), pad_token_id=int(self.pad_token_id),
+                               bos_token_id=int(self.bos_token_id), eos_token_id=int(self.eos_token_id))
+            object.__setattr__(self, "_eng", Engine(cfg, self.state_dict(), device))
+            object.__setattr__(self, "_eng_sig", sig)
+        return self._eng
+
+    def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
+        """decoders.py:137-234.  Only the inference branch (captions is None) is on the decode path."""
+        if captions is None:
+            return self.generate(encoder_features, self.max_length)   # reference hits a NameError here (:148)
+        raise NotImplementedError(
+            "teacher-forced training forward is outside the accelerated decode path (SURVEY.md section 8: the trainer is "
+            "out of scope); train with the reference module and load its state_dict here for decoding. "
+            "For the SCST rollout (trainer.py:383-438) call generate(..., do_sample=True).")
+
+    def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, start_token_id: int = 1,
+                 num_beams: int = 1, do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
+                 uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
+                 **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        feats = encoder_features["features"]
+        pooled = encoder_features["pooled_features"]
+        mask = _padding_mask(encoder_features)
+        eng = self._engine(feats.device)
+        if do_sample:
+            B = feats.shape[0]
+            k = num_samples + (1 if with_greedy else 0)
+            if uniforms is None:
+                uniforms = torch.rand(B * k, max_length - 1, device=feats.device)
+            tok, lp = eng.decode_sample(feats, pooled, mask, num_samples, with_greedy, max_length, uniforms)
+            return tok.long(), {"log_probs": lp}
+        if num_beams > 1:
+            out = eng.decode_beam(feats, pooled, mask, num_beams, max_length, length_penalty, trace=trace)
+            seq = out["tokens"].long()
+            seq = seq[:, : int(out["lengths"].max().item())]     # HF crops to the longest hypothesis
+            info = {"scores": out["scores"], "lengths": out["lengths"].long()}
+            if trace:
+                info.update({k: out[k] for k in ("top_logprob", "top_token", "top_beam")})
+            return seq, info
+        tok, alpha = eng.decode_greedy(feats, pooled, mask, max_length, start_token_id)
+        return tok.long(), {"attention_weights": alpha}
+
+
+def build_decoder(config: DecoderConfig, attention_config: AttentionConfig, vocab_size: int, pad_token_id: int,
+                  bos_token_id: int, eos_token_id: int) -> CaptionDecoder:
+    """Factory (decoders.py:659-692).  Only the LSTM family is accelerated so far; other types raise."""
+    kind = decoder_kind(config)
+    if kind == DecoderType.LSTM.value:
+        return LSTMDecoder(config=config, attention_config=attention_config, vocab_size=vocab_size,
+                           pad_token_id=pad_token_id, bos_token_id=bos_token_id, eos_token_id=eos_token_id)
+    if kind in (DecoderType.TRANSFORMER.value, DecoderType.GPT2.value):
+        raise NotImplementedError(f"decoder type {kind!r} has no capdec kernels yet (SURVEY.md section 8 rows a7/a8)")
+    raise ValueError(f"Unsupported decoder type: {config.decoder_type}")

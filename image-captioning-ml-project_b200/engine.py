@@ -1,0 +1,204 @@
+"""Host-side session over a libcapdec handle.
+
+PyTorch is plumbing here: it owns device memory (features, outputs, workspace) and the CUDA
+stream; every computation happens in libcapdec's kernels behind the C ABI (include/capdec.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _capi
+from ._capi import Config, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """One capdec_handle bound to a module's parameters on one CUDA device."""
+
+    def __init__(self, cfg: Config, state_dict: Dict[str, torch.Tensor], device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("capdec runs on CUDA devices only (no CPU fallback); move the module to cuda")
+        self.device = device
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.capdec_create(C.byref(cfg), C.byref(self._h)))
+            s = _stream(device)
+            for name, t in state_dict.items():
+                t = _f32(t, device)
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                check(lib.capdec_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), s))
+            check(lib.capdec_finalize(self._h, s))
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.capdec_destroy(h)
+            self._h = None
+
+    # -- workspace ------------------------------------------------------------------------------
+    def _workspace(self, B: int, L: int, k: int, T: int) -> torch.Tensor:
+        need = int(lib.capdec_workspace_bytes(self._h, B, L, k, T))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _mask(self, key_padding_mask, B, L):
+        if key_padding_mask is None:
+            return None
+        m = key_padding_mask.to(device=self.device)
+        if m.shape != (B, L):
+            raise ValueError(f"key_padding_mask must be [B,L]=({B},{L}), got {tuple(m.shape)}")
+        return m.to(torch.uint8).contiguous()
+
+    # -- decode ---------------------------------------------------------------------------------
+    def decode_beam(self, features, pooled, key_padding_mask, num_beams, max_length, length_penalty=1.0,
+                    trace=False):
+        feats = _f32(features, self.device)
+        B, L = feats.shape[0], feats.shape[1]
+        pooled = None if pooled is None else _f32(pooled, self.device)
+        mask = self._mask(key_padding_mask, B, L)
+        dev = self.device
+        tok = torch.empty(B, max_length, dtype=torch.int32, device=dev)
+        length = torch.empty(B, dtype=torch.int32, device=dev)
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        steps, k2 = max_length - 1, 2 * num_beams
+        dlp = torch.empty(steps, B, k2, dtype=torch.float32, device=dev) if trace else None
+        dtok = torch.empty(steps, B, k2, dtype=torch.int32, device=dev) if trace else None
+        dbeam = torch.empty(steps, B, k2, dtype=torch.int32, device=dev) if trace else None
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, L, num_beams, max_length)
+            check(lib.capdec_decode_beam(self._h, _ptr(feats), _ptr(pooled), _ptr(mask), B, L, num_beams, max_length,
+                                         float(length_penalty), _ptr(tok), _ptr(length), _ptr(score), _ptr(dlp),
+                                         _ptr(dtok), _ptr(dbeam), _ptr(ws), ws.numel(), _stream(dev)))
+        out = {"tokens": tok, "lengths": length, "scores": score}
+        if trace:
+            out.update(top_logprob=dlp, top_token=dtok, top_beam=dbeam)
+        return out
+
+    def decode_greedy(self, features, pooled, key_padding_mask, max_length, start_token_id=1, want_alpha=True):
+        feats = _f32(features, self.device)
+        B, L = feats.shape[0], feats.shape[1]
+        pooled = None if pooled is None else _f32(pooled, self.device)
+        mask = self._mask(key_padding_mask, B, L)
+        dev = self.device
+        tok = torch.empty(B, max_length, dtype=torch.int32, device=dev)
+        alpha = torch.empty(B, max_length, L, dtype=torch.float32, device=dev) if want_alpha else None
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, L, 1, max_length)
+            check(lib.capdec_decode_greedy(self._h, _ptr(feats), _ptr(pooled), _ptr(mask), B, L, max_length,
+                                           int(start_token_id), _ptr(tok), _ptr(alpha), _ptr(ws), ws.numel(),
+                                           _stream(dev)))
+        return tok, alpha
+
+    def decode_sample(self, features, pooled, key_padding_mask, num_samples, with_greedy, max_length, uniforms):
+        feats = _f32(features, self.device)
+        B, L = feats.shape[0], feats.shape[1]
+        pooled = None if pooled is None else _f32(pooled, self.device)
+        mask = self._mask(key_padding_mask, B, L)
+        dev = self.device
+        k = num_samples + (1 if with_greedy else 0)
+        R = B * k
+        u = _f32(uniforms, dev)
+        if u.shape != (R, max_length - 1):
+            raise ValueError(f"uniforms must be [{R},{max_length - 1}], got {tuple(u.shape)}")
+        tok = torch.empty(R, max_length, dtype=torch.int32, device=dev)
+        lp = torch.empty(R, max_length - 1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, L, k, max_length)
+            check(lib.capdec_decode_sample(self._h, _ptr(feats), _ptr(pooled), _ptr(mask), B, L, num_samples,
+                                           1 if with_greedy else 0, max_length, _ptr(u), _ptr(tok), _ptr(lp),
+                                           _ptr(ws), ws.numel(), _stream(dev)))
+        return tok, lp
+
+    def forward_teacher(self, features, captions, dec_len):
+        feats = _f32(features, self.device)
+        B, L = feats.shape[0], feats.shape[1]
+        dev = self.device
+        T = max(dec_len)
+        V = self.cfg.vocab_size
+        caps = captions.to(device=dev, dtype=torch.int32).contiguous()
+        preds = torch.zeros(B, T, V, dtype=torch.float32, device=dev)
+        alphas = torch.zeros(B, T, L, dtype=torch.float32, device=dev)
+        dl = (C.c_int32 * B)(*[int(x) for x in dec_len])
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, L, 1, T + 1)
+            check(lib.capdec_forward_teacher(self._h, _ptr(feats), B, L, _ptr(caps), caps.shape[1], dl, _ptr(preds),
+                                             _ptr(alphas), _ptr(ws), ws.numel(), _stream(dev)))
+        return preds, alphas
+
+    def attention_forward(self, query, features, key_padding_mask, memory_state, cell_state, rows_per_image=1):
+        feats = _f32(features, self.device)
+        B, L = feats.shape[0], feats.shape[1]
+        q = _f32(query, self.device)
+        R, H = q.shape
+        if R != B * rows_per_image:
+            raise ValueError(f"query rows {R} != images {B} * rows_per_image {rows_per_image}")
+        mask = self._mask(key_padding_mask, B, L)
+        mem = None if memory_state is None else _f32(memory_state, self.device)
+        cell = None if cell_state is None else _f32(cell_state, self.device)
+        ctx = torch.empty(R, H, dtype=torch.float32, device=self.device)
+        w = torch.empty(R, L, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, L, rows_per_image, 2)
+            check(lib.capdec_attention_forward(self._h, _ptr(q), _ptr(feats), _ptr(mask), _ptr(mem), _ptr(cell), B, L,
+                                               rows_per_image, _ptr(ctx), _ptr(w), _ptr(ws), ws.numel(),
+                                               _stream(self.device)))
+        return ctx, w
+
+    def decode_beam_host(self, features_host, pooled_host, num_beams, max_length, length_penalty=1.0,
+                         chunk_images=512, out=None):
+        """End-to-end path: host (pinned) buffers in, host buffers out, copies inside the call."""
+        assert features_host.device.type == "cpu" and features_host.dtype == torch.float32 and features_host.is_contiguous()
+        B, L = features_host.shape[0], features_host.shape[1]
+        if out is None:
+            out = {"tokens": torch.empty(B, max_length, dtype=torch.int32).pin_memory(),
+                   "lengths": torch.empty(B, dtype=torch.int32).pin_memory(),
+                   "scores": torch.empty(B, dtype=torch.float32).pin_memory()}
+        with torch.cuda.device(self.device):
+            check(lib.capdec_decode_beam_host(self._h, _ptr(features_host), _ptr(pooled_host), B, L, num_beams,
+                                              max_length, float(length_penalty), int(chunk_images),
+                                              _ptr(out["tokens"]), _ptr(out["lengths"]), _ptr(out["scores"])))
+        return out
+
+
+def launch_count() -> int:
+    return int(lib.capdec_launch_count())
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], precision: str = "fp32") -> torch.Tensor:
+    """Stage-level entry (unit tests): nn.Linear through libcapdec's GEMM."""
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.capdec_linear(_capi.PREC[precision], _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(c),
+                                c.stride(0), M, N, K, _stream(a.device)))
+    return c
+
+
+def lse_topk(logits: torch.Tensor, topk: int):
+    R, V = logits.shape
+    lp = torch.empty(R, topk, dtype=torch.float32, device=logits.device)
+    idx = torch.empty(R, topk, dtype=torch.int32, device=logits.device)
+    lse = torch.empty(R, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        check(lib.capdec_lse_topk(_ptr(logits), logits.stride(0), R, V, topk, _ptr(lp), _ptr(idx), _ptr(lse),
+                                  _stream(logits.device)))
+    return lp, idx, lse

@@ -1,0 +1,199 @@
+"""CPU suite: pin the oracle (a) against the reference's own modules when /root/reference is present
+(the build container), (b) against the committed golden vectors those modules produced, (c) the beam
+driver against transformers' own generate(num_beams=k)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, refshim, sample as osample
+from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs
+
+needs_ref = pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present on this box")
+torch.set_grad_enabled(False)
+
+
+# ---------------------------------------------------------------- (a) against the reference itself
+@needs_ref
+def test_dropin_init_equals_reference_init():
+    ns = refshim.load_reference()
+    torch.manual_seed(0)
+    ref = ns.legacy.Decoder(300, False, "cpu")
+    _, sd = legacy_weights(300, 0)
+    assert set(sd) == set(ref.state_dict())
+    assert all(torch.equal(sd[k], v) for k, v in ref.state_dict().items())
+    C = ns.config
+    for kind in ("soft", "multi_head", "adaptive", "aoa"):
+        for heads in (1, 4):
+            torch.manual_seed(0)
+            r = ns.decoders.LSTMDecoder(
+                C.DecoderConfig(decoder_type=C.DecoderType.LSTM, hidden_dim=32, num_layers=2),
+                C.AttentionConfig(attention_type=C.AttentionType(kind), num_heads=heads, hidden_dim=32),
+                vocab_size=50, pad_token_id=0)
+            _, sd2 = lstm_decoder(kind, H=32, layers=2, heads=heads, V=50)
+            assert set(sd2) == set(r.state_dict())
+            assert all(torch.equal(sd2[k], v) for k, v in r.state_dict().items())
+
+
+@needs_ref
+def test_legacy_restatement_matches_reference_forward():
+    ns = refshim.load_reference()
+    torch.manual_seed(3)
+    ref = ns.legacy.Decoder(400, False, "cpu").eval()
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    enc = legacy_features(4, seed=5)
+    g = torch.Generator().manual_seed(9)
+    lens = [7, 7, 4, 2]
+    caps = torch.randint(0, 400, (4, 7), generator=g)
+    preds, _, dec_len, alphas = ref(enc, caps, lens)
+    p2, a2, d2 = olegacy.forward_teacher_forced(sd, enc, caps, lens)
+    assert dec_len == d2
+    assert torch.equal(preds, p2) and torch.equal(alphas, a2)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,heads", [("soft", 8), ("multi_head", 4), ("aoa", 4), ("aoa", 1), ("adaptive", 4), ("adaptive", 1)])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_lstm_restatement_matches_reference_generate(kind, heads, ragged):
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(1)
+    H, layers, V, L, B, T = 64, 2, 300, 21, 5, 10
+    ref = ns.decoders.LSTMDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.LSTM, hidden_dim=H, num_layers=layers),
+        C.AttentionConfig(attention_type=C.AttentionType(kind), num_heads=heads, hidden_dim=H),
+        vocab_size=V, pad_token_id=0).eval()
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    feats, pooled, mask = lstm_inputs(B, L, H, seed=2, ragged=ragged)
+    ef = {"features": feats, "pooled_features": pooled}
+    if mask is not None:
+        ef["attention_mask"] = mask
+    ids, info = ref.generate(ef, T)
+    ids2, al2 = olstm.generate_greedy(sd, feats, pooled, kind, layers, T, num_heads=heads,
+                                      mask=None if mask is None else ~mask)
+    assert torch.equal(ids, ids2)
+    assert torch.allclose(info["attention_weights"], al2, atol=1e-6)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,heads", [("soft", 1), ("multi_head", 8), ("aoa", 8), ("adaptive", 8)])
+def test_attention_restatement_matches_reference_module(kind, heads):
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(4)
+    H, L, B = 64, 17, 6
+    mod = ns.attention.build_attention(C.AttentionConfig(attention_type=C.AttentionType(kind), num_heads=heads,
+                                                         hidden_dim=H, temperature=1.7)).eval()
+    sd = {"attention." + k: v.detach() for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    q, feats = torch.randn(B, H, generator=g), torch.randn(B, L, H, generator=g)
+    mem, cell = torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
+    pad = torch.zeros(B, L, dtype=torch.bool)
+    pad[2, 9:] = True
+    ctx, w = mod(q, feats, feats, pad, memory_state=mem, cell_state=cell)
+    ctx2, w2 = oatt.attend(kind, sd, "attention.", q, feats, heads, None, pad, 1.7, mem, cell)
+    assert torch.allclose(ctx, ctx2, atol=1e-6) and torch.allclose(w, w2, atol=1e-6)
+
+
+# ---------------------------------------------------------------- (b) against the committed goldens
+def test_golden_legacy_teacher_forced():
+    gd = torch.load(os.path.join(GOLDEN, "legacy_teacher.pt"))
+    _, sd = legacy_weights(gd["vocab"], gd["seed"])
+    enc = legacy_features(gd["B"], gd["feat_seed"])
+    preds, alphas, _ = olegacy.forward_teacher_forced(sd, enc, gd["caps"], gd["lens"])
+    assert torch.allclose(preds[:, :, ::97], gd["preds_sub"], atol=1e-5)
+    assert torch.equal(preds.argmax(-1), gd["argmax"])
+    assert torch.allclose(alphas, gd["alphas"], atol=1e-6)
+
+
+def test_golden_legacy_beam3():
+    gd = torch.load(os.path.join(GOLDEN, "legacy_beam3.pt"))
+    _, sd = legacy_weights(gd["vocab"], gd["seed"])
+    B = 3  # first images only: keeps the CPU suite short; the GPU suite checks all of them
+    enc = legacy_features(gd["B"], gd["feat_seed"])[:B]
+    out = obeam.beam_search(olegacy.LegacyStepper(sd, enc, gd["k"]), B, gd["k"], gd["T"], record_steps=True)
+    assert torch.equal(out["sequences"], gd["sequences"][:B])
+    assert torch.allclose(out["scores"], gd["scores"][:B], atol=1e-4)
+    lp = torch.stack([s["top_lp"] for s in out["steps"]])
+    live = gd["top_lp"][:, :B] > -1e8
+    assert torch.allclose(lp[live], gd["top_lp"][:, :B][live], atol=1e-4)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "lstm_greedy_*_H256_*.pt"))))
+def test_golden_lstm_greedy(path):
+    gd = torch.load(path)
+    _, sd = lstm_decoder(gd["kind"], H=gd["H"], layers=gd["layers"], heads=gd["heads"], V=gd["vocab"], seed=gd["seed"])
+    feats, pooled, mask = lstm_inputs(gd["B"], gd["L"], gd["H"], gd["feat_seed"], gd["ragged"])
+    ids, al = olstm.generate_greedy(sd, feats, pooled, gd["kind"], gd["layers"], gd["T"], num_heads=gd["heads"],
+                                    mask=None if mask is None else ~mask)
+    assert torch.equal(ids, gd["ids"])
+    assert torch.allclose(al, gd["attention_weights"], atol=1e-6)
+
+
+# ---------------------------------------------------------------- (c) beam driver against transformers
+class _HFStepper:
+    """prefix-recompute stepper over a real HF GPT-2 (logits sharpened / EOS-biased to exercise finishing)."""
+
+    def __init__(self, model, first_tokens, scale, eos_bias):
+        self.m, self.first, self.scale, self.eos_bias = model, first_tokens, scale, eos_bias
+        self.state = None
+        self.vocab_size = model.config.vocab_size
+
+    def reorder(self, idx):
+        self.state = self.state[idx]
+
+    def __call__(self, tokens):
+        if self.state is None:
+            tokens = self.first
+        seqs = tokens[:, None] if self.state is None else torch.cat([self.state, tokens[:, None]], 1)
+        self.state = seqs
+        logits = self.m(input_ids=seqs).logits[:, -1] * self.scale
+        logits[..., 2] += self.eos_bias
+        return logits
+
+
+@pytest.mark.parametrize("k", [3, 5])
+@pytest.mark.parametrize("scale,eos_bias", [(1.0, 0.0), (1.0, 4.0), (30.0, 12.0)])
+@pytest.mark.parametrize("lp", [1.0, 0.8, 0.0])
+def test_beam_driver_matches_hf(k, scale, eos_bias, lp):
+    from transformers import GPT2Config, GPT2LMHeadModel
+    torch.manual_seed(0)
+    V, B, T = 97, 6, 12
+    m = GPT2LMHeadModel(GPT2Config(vocab_size=V, n_positions=32, n_embd=32, n_layer=2, n_head=2, bos_token_id=1,
+                                   eos_token_id=2, pad_token_id=0)).eval()
+    ids = torch.arange(3, 3 + B)[:, None]
+    orig = m.forward
+
+    def fwd(*a, **kw):
+        out = orig(*a, **kw)
+        out.logits = out.logits * scale
+        out.logits[..., 2] += eos_bias
+        return out
+
+    m.forward = fwd
+    hf = m.generate(input_ids=ids, max_length=T, num_beams=k, do_sample=False, pad_token_id=0, bos_token_id=1,
+                    eos_token_id=2, length_penalty=lp, use_cache=False, return_dict_in_generate=True,
+                    output_scores=True, early_stopping=False)
+    m.forward = orig
+    out = obeam.beam_search(_HFStepper(m, ids.repeat_interleave(k, 0)[:, 0], scale, eos_bias), B, k, T,
+                            bos_token_id=1, eos_token_id=2, pad_token_id=0, length_penalty=lp)
+    seq = out["sequences"].clone()
+    seq[:, 0] = ids[:, 0]
+    seq = obeam.crop_like_hf(seq, out["lengths"])
+    assert hf.sequences.shape == seq.shape and torch.equal(hf.sequences, seq)
+    assert torch.allclose(hf.sequences_scores, out["scores"], atol=1e-5)
+
+
+def test_sample_rollout_inverse_cdf():
+    _, sd = lstm_decoder("soft", H=32, layers=1, V=50)
+    feats, pooled, _ = lstm_inputs(3, 7, 32)
+    u = torch.rand(6, 9, generator=torch.Generator().manual_seed(3))
+    st = olstm.LSTMStepper(sd, feats, pooled, "soft", 1, rows_per_image=2)
+    ids, lps, edges = osample.sample_rollout(st, 6, 10, u)
+    assert ids.shape[0] == 6 and ids[:, 0].eq(1).all() and lps.shape == (6, ids.shape[1] - 1)
+    assert (lps <= 0).all() and (ids >= 0).all() and (ids < 50).all()
+    # same uniforms => same draw; different uniforms => (almost surely) different draw
+    st2 = olstm.LSTMStepper(sd, feats, pooled, "soft", 1, rows_per_image=2)
+    ids2, _, _ = osample.sample_rollout(st2, 6, 10, u)
+    assert torch.equal(ids, ids2)
