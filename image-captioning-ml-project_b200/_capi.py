@@ -67,6 +67,8 @@ def _load() -> C.CDLL:
     lib.capdec_forward_teacher.argtypes = [p, p, i32, i32, p, i32, C.POINTER(i32), p, p, p, sz, p]
     lib.capdec_attention_forward.argtypes = [p, p, p, p, p, p, i32, i32, i32, p, p, p, sz, p]
     lib.capdec_decode_beam_host.argtypes = [p, p, p, i32, i32, i32, i32, f32, i32, p, p, p]
+    lib.capdec_stage_timing.argtypes = [p, i32]
+    lib.capdec_stage_times.argtypes = [p, C.POINTER(f32), C.POINTER(i32)]
     lib.capdec_linear.argtypes = [i32, p, i64, p, i64, p, p, i64, i32, i32, i32, p]
     lib.capdec_lse_topk.argtypes = [p, i64, i32, i32, i32, p, p, p, p]
     return lib

@@ -184,6 +184,7 @@ int linear(const capdec_handle* h, const float* A, int64_t lda, const std::strin
 }
 
 int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool expand, cudaStream_t s) {
+  StageScope sc(h, STAGE_PROLOGUE, s);
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
   // att1 = enc_att(enc)  (models/decoder.py:152, hoisted)
@@ -210,6 +211,7 @@ int prologue_attention(const capdec_handle* h, Session& S, const float* feats, c
 }
 
 int prologue_lstm(const capdec_handle* h, Session& S, const float* feats, const float* pooled, cudaStream_t s) {
+  StageScope sc(h, STAGE_PROLOGUE, s);
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, layers = c.num_layers;
   CAPDEC_RETURN_IF(prologue_attention(h, S, feats, s));
@@ -241,6 +243,7 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
   const int64_t ld_base = c.attention == CAPDEC_ATT_AOA ? 2 * H : H;
 
   if (c.attention == CAPDEC_ATT_ADAPTIVE) {
+    StageScope sc(h, STAGE_SMALL_GEMM, s);
     // sentinel (attention.py:266-272): s = sentinel_proj(sigmoid(W[q;mem]) * tanh(cell))
     CAPDEC_REQUIRE(memory && cell, CAPDEC_ERR_INVALID, "AdaptiveAttention requires memory_state and cell_state");
     GatherArgs ga{};
@@ -259,24 +262,25 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
     CAPDEC_RETURN_IF(linear(h, S.spre, H, "attention.sentinel_proj", S.sent, H, rows, EPI_STORE, s));
   }
 
-  CAPDEC_RETURN_IF(linear(h, q, ld_q, p + "query_proj", S.qproj, H, rows, EPI_STORE, s));
+  { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(linear(h, q, ld_q, p + "query_proj", S.qproj, H, rows, EPI_STORE, s)); }
   if (base_is_mha(h)) {
     MhaArgs m{};
     m.q = S.qproj; m.ld_q = H; m.kproj = S.keyp; m.vproj = S.valp; m.mask = mask;
     m.denom = (float)((double)c.temperature * sqrt((double)(H / c.num_heads)));
     m.out = S.att_out; m.ld_out = H; m.alpha = alpha; m.ld_alpha = ld_alpha;
     m.B = images; m.L = S.L; m.H = H; m.heads = c.num_heads; m.k = k;
-    CAPDEC_RETURN_IF(mha_attention(m, s));
-    CAPDEC_RETURN_IF(linear(h, S.att_out, H, p + "output_proj", base_dst, ld_base, rows, EPI_STORE, s));
+    { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(mha_attention(m, s)); }
+    { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(linear(h, S.att_out, H, p + "output_proj", base_dst, ld_base, rows, EPI_STORE, s)); }
   } else {
     AddAttnArgs a{};
     a.att1 = S.keyp; a.att2 = S.qproj; a.ld_att2 = H; a.w = h->W(p + "energy.weight");
     a.w_bias = h->energy_bias; a.temperature = c.temperature; a.mask = mask; a.feats = feats;
     a.gate = nullptr; a.ctx = base_dst; a.ld_ctx = ld_base; a.alpha = alpha; a.ld_alpha = ld_alpha;
     a.B = images; a.L = S.L; a.A = H; a.D = H; a.k = k;
-    CAPDEC_RETURN_IF(additive_attention(a, ACT_TANH, s));
+    { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, ACT_TANH, s)); }
   }
 
+  StageScope sc_tail(h, STAGE_SMALL_GEMM, s);
   if (c.attention == CAPDEC_ATT_AOA) {
     // attention.py:343-353: cat = [ctx ; query_proj(q)];  out = tanh(W_i cat) * sigmoid(W_g cat)
     CAPDEC_RETURN_IF(linear(h, q, ld_q, "attention.query_proj", S.cat + H, 2 * H, rows, EPI_STORE, s));
@@ -302,22 +306,22 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   GemmArgs g{};
   g.A = S.X[0] + E + D; g.lda = S.ldX[0]; g.W = h->w_hproj; g.ldw = H; g.bias = h->b_hproj;
   g.C = S.hproj; g.ldc = A + D; g.M = rows; g.N = A + D; g.K = H; g.n_split = A;
-  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s));
+  { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s)); }
   // scores -> softmax -> gated context, written straight into the LSTM operand (:154-161)
   AddAttnArgs a{};
   a.att1 = S.att1; a.att2 = S.hproj; a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
   a.temperature = 1.f; a.mask = nullptr; a.feats = feats; a.gate = S.hproj + A; a.ld_gate = A + D;
   a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;
   a.B = images; a.L = S.L; a.A = A; a.D = D; a.k = S.k;
-  CAPDEC_RETURN_IF(additive_attention(a, ACT_RELU, s));
+  { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, ACT_RELU, s)); }
   // LSTMCell([emb ; ctx], (h, c)) with the cell update fused into the gate GEMM (:168)
   GemmArgs l{};
   l.A = S.X[0]; l.lda = S.ldX[0]; l.W = h->w_gates[0]; l.ldw = E + D + H; l.bias = h->b_gates[0];
   l.C = S.hnew[0]; l.ldc = H; l.M = rows; l.N = 4 * H; l.K = E + D + H;
   l.c_in = S.c[0]; l.ldcin = H; l.c_out = S.cnew[0]; l.ldcout = H;
-  CAPDEC_RETURN_IF(gemm(c.precision, l, EPI_LSTM, s));
+  { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(c.precision, l, EPI_LSTM, s)); }
   // fc(h)  (:171; dropout is the identity in eval)
-  CAPDEC_RETURN_IF(linear(h, S.hnew[0], H, "fc", logits, ld_logits, rows, EPI_STORE, s));
+  { StageScope sc(h, STAGE_VOCAB_GEMM, s); CAPDEC_RETURN_IF(linear(h, S.hnew[0], H, "fc", logits, ld_logits, rows, EPI_STORE, s)); }
   (void)V;
   return CAPDEC_OK;
 }
@@ -338,6 +342,7 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
     g.c_in = S.c[l]; g.ldcin = H; g.c_out = S.cnew[l]; g.ldcout = H;
     if (!top) { g.C2 = S.X[l + 1]; g.ldc2 = S.ldX[l + 1]; }
     else if (adaptive) { g.C2 = S.hnew[l] + H; g.ldc2 = 2 * H; }  // [q | memory_state] with memory_state == q
+    StageScope sc(h, STAGE_GATE_GEMM, s);
     CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_LSTM, s));
   }
   const float* q = S.hnew[layers - 1];
@@ -354,6 +359,7 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
     CAPDEC_RETURN_IF(run_attention(h, S, feats, mask, q, ld_q, nullptr, 0, nullptr, 0, S.B, S.ctx, alpha, ld_alpha, s));
   }
   // logits = output_layer(context)  (decoders.py:303)
+  StageScope sc(h, STAGE_VOCAB_GEMM, s);
   CAPDEC_RETURN_IF(linear(h, S.ctx, H, "output_layer", S.logits, c.vocab_size, rows, EPI_STORE, s));
   return CAPDEC_OK;
 }
@@ -386,6 +392,7 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
     }
   }
   g.n_state = n;
+  StageScope sc(h, STAGE_GATHER, s);
   return gather_rows(g, s);
 }
 
@@ -493,6 +500,7 @@ void capdec_destroy(capdec_handle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->stream_compute) cudaStreamDestroy(h->stream_compute);
   if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
   delete h;
@@ -649,14 +657,16 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
   const int k2 = 2 * k;
   for (int cur_len = 1; cur_len < T; ++cur_len) {
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
-    CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, k2, S.cand_lp, S.cand_idx, nullptr, s));
+    { StageScope sc(h, STAGE_SELECT, s);
+      CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, k2, S.cand_lp, S.cand_idx, nullptr, s)); }
     // prompt length is 1 (BOS): finished score / (cur_len+1-1)^lp ; heuristic uses ((cur_len+1)-1)^lp
     const float div_fin = (float)pow((double)cur_len, (double)length_penalty);
     const float div_heur = div_fin;
     const size_t o = (size_t)(cur_len - 1) * B * k2;
-    CAPDEC_RETURN_IF(beam_step(S.beam, B, k, T, c.vocab_size, cur_len, c.eos_token_id, div_fin, div_heur, S.cand_lp,
-                               S.cand_idx, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
-                               dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, s));
+    { StageScope sc(h, STAGE_BEAM, s);
+      CAPDEC_RETURN_IF(beam_step(S.beam, B, k, T, c.vocab_size, cur_len, c.eos_token_id, div_fin, div_heur, S.cand_lp,
+                                 S.cand_idx, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
+                                 dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, s)); }
     if (cur_len + 1 < T) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s));
   }
   CAPDEC_RETURN_IF(beam_finalize(S.beam, (T - 1) & 1, B, k, T, out_tok, out_len, out_score, s));
@@ -683,7 +693,8 @@ int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pool
     float* alpha = out_alpha ? out_alpha + (size_t)t * L : nullptr;
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, s));
     if (t + 1 == T) break;  // the last argmax is discarded (decoders.py:306 after the final store at :271)
-    CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, 1, S.cand_lp, S.next_tok, nullptr, s));
+    { StageScope sc(h, STAGE_SELECT, s);
+      CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, 1, S.cand_lp, S.next_tok, nullptr, s)); }
     CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, t + 1, true, s));
   }
   return CAPDEC_OK;
@@ -708,8 +719,9 @@ int capdec_decode_sample(capdec_handle* h, const float* feats, const float* pool
   CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));
   for (int t = 0; t + 1 < T; ++t) {  // trainer.py:413
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
-    CAPDEC_RETURN_IF(sample_rows(S.logits, c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
-                                 with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s));
+    { StageScope sc(h, STAGE_SELECT, s);
+      CAPDEC_RETURN_IF(sample_rows(S.logits, c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
+                                   with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s)); }
     if (out_lp) {
       // out_lp[r, t] = step_lp[r]
       CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(out_lp + t, (size_t)(T - 1) * sizeof(float), S.step_lp, sizeof(float),
@@ -837,6 +849,27 @@ int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const flo
   CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
   CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_score_host, d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
   CAPDEC_CHECK_CUDA(cudaStreamSynchronize(h->stream_compute));
+  return CAPDEC_OK;
+}
+
+int capdec_stage_timing(capdec_handle* h, int32_t enable) {
+  CAPDEC_REQUIRE(h, CAPDEC_ERR_INVALID, "null handle");
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return CAPDEC_OK;
+}
+
+int capdec_stage_times(capdec_handle* h, float* ms_out, int32_t* count_out) {
+  CAPDEC_REQUIRE(h && ms_out && count_out, CAPDEC_ERR_INVALID, "null argument");
+  for (int i = 0; i < STAGE_COUNT; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    CAPDEC_CHECK_CUDA(cudaEventSynchronize(h->ev_pool[2 * i + 1]));
+    float ms = 0.f;
+    CAPDEC_CHECK_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    ms_out[h->ev_stage[i]] += ms;
+    count_out[h->ev_stage[i]] += 1;
+  }
+  h->ev_used = 0;
   return CAPDEC_OK;
 }
 

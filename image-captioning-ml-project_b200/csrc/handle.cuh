@@ -37,6 +37,12 @@ struct capdec_handle {
   cudaStream_t stream_compute = nullptr, stream_copy = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 
+  // ---- optional per-stage device timing (capdec_stage_timing): cudaEvent pairs around every stage launch
+  mutable bool timing = false;
+  mutable std::vector<cudaEvent_t> ev_pool;      // [2*i] start, [2*i+1] stop
+  mutable std::vector<int> ev_stage;             // stage id of pair i
+  mutable size_t ev_used = 0;
+
   const DevTensor* find(const std::string& n) const {
     auto it = w.find(n);
     return it == w.end() ? nullptr : &it->second;
@@ -58,6 +64,37 @@ struct Arena {
     return r;
   }
   bool ok() const { return dry || off <= cap; }
+};
+
+enum Stage : int {
+  STAGE_PROLOGUE = 0,   // hoisted region projections + init state
+  STAGE_SMALL_GEMM = 1, // per-step query-side projections (dec_att|f_beta, query_proj, output_proj, AoA ...)
+  STAGE_ATTENTION = 2,  // scores + softmax + context over the region tiles
+  STAGE_GATE_GEMM = 3,  // LSTM gate GEMM with fused cell update
+  STAGE_VOCAB_GEMM = 4, // vocabulary projection
+  STAGE_SELECT = 5,     // log-softmax + top-k / argmax / sampling
+  STAGE_BEAM = 6,       // per-image beam bookkeeping
+  STAGE_GATHER = 7,     // back-pointer reorder + embedding gather
+  STAGE_COUNT = 8
+};
+
+// RAII: record an event pair around the launches issued while in scope (no-op unless timing is enabled)
+struct StageScope {
+  const capdec_handle* h; cudaStream_t s; cudaEvent_t stop = nullptr;
+  StageScope(const capdec_handle* h_, int stage, cudaStream_t s_) : h(h_), s(s_) {
+    if (!h->timing) return;
+    if (h->ev_used * 2 + 2 > h->ev_pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+      h->ev_stage.push_back(stage);
+    }
+    h->ev_stage[h->ev_used] = stage;
+    cudaEventRecord(h->ev_pool[h->ev_used * 2], s);
+    stop = h->ev_pool[h->ev_used * 2 + 1];
+    h->ev_used++;
+  }
+  ~StageScope() { if (stop) cudaEventRecord(stop, s); }
 };
 
 // tensor-core GEMM modes (gemm_tc.cu)

@@ -178,6 +178,25 @@ class Engine:
         return out
 
 
+STAGES = ("prologue", "small_gemm", "attention", "gate_gemm", "vocab_gemm", "select", "beam", "gather")
+
+
+def _stage_timing(self, enable: bool) -> None:
+    check(lib.capdec_stage_timing(self._h, 1 if enable else 0))
+
+
+def _stage_times(self):
+    """-> {stage: (milliseconds, launches)} since the last call (waits for the recorded events)."""
+    ms = (C.c_float * 8)()
+    n = (C.c_int32 * 8)()
+    check(lib.capdec_stage_times(self._h, ms, n))
+    return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(STAGES)}
+
+
+Engine.stage_timing = _stage_timing
+Engine.stage_times = _stage_times
+
+
 def launch_count() -> int:
     return int(lib.capdec_launch_count())
 

@@ -161,6 +161,16 @@ int capdec_decode_beam_host(capdec_handle* h, const float* features_host, const 
                             int32_t max_length, float length_penalty, int32_t chunk_images,
                             int32_t* out_tokens_host, int32_t* out_lengths_host, float* out_scores_host);
 
+/* ---- per-stage device timing ---------------------------------------------------------------------
+ * When enabled, every stage launch of subsequent decode calls is bracketed by a cudaEvent pair on the
+ * caller's stream.  capdec_stage_times waits for them, returns the summed milliseconds and the number of
+ * launches per stage (arrays of CAPDEC_STAGE_COUNT) and resets the log.  Stage ids: 0 prologue, 1 small
+ * per-step GEMMs, 2 attention, 3 LSTM gate GEMM, 4 vocab GEMM, 5 top-k/argmax/sampling, 6 beam bookkeeping,
+ * 7 reorder gathers. */
+#define CAPDEC_STAGE_COUNT 8
+int capdec_stage_timing(capdec_handle* h, int32_t enable);
+int capdec_stage_times(capdec_handle* h, float* ms_out, int32_t* count_out);
+
 /* ---- stage-level entry points (unit tests / profiling of single kernels) -------------------- */
 /* C[M,N] = A[M,K] * W[N,K]^T + bias[N]   (nn.Linear), lda/ldw/ldc in elements. */
 int capdec_linear(int32_t precision, const float* a_dev, int64_t lda, const float* w_dev, int64_t ldw,
