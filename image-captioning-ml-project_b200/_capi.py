@@ -15,7 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "capdec.h")
 
 ARCH_LEGACY_SAT, ARCH_LSTM = 0, 1
 ATT = {"soft": 0, "multi_head": 1, "adaptive": 2, "aoa": 3}
-PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "tf32": 3}
 
 
 class CapdecError(RuntimeError):

@@ -13,5 +13,5 @@ for f in capdec gemm_ffma gemm_tc attn_additive attn_mha select; do
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libcapdec.so _build/*.o -lcudart -lcuda
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libcapdec.so _build/*.o -lcudart
 echo "built $(pwd)/libcapdec.so"

@@ -23,9 +23,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int gemm(int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
+int gemm(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
   if (precision == CAPDEC_PREC_FP32) return gemm_ffma(a, epilogue, s);
-  return gemm_tc(precision, a, epilogue, s);
+  return gemm_tc(h, precision, a, epilogue, s);
 }
 
 namespace {
@@ -180,7 +180,7 @@ int linear(const capdec_handle* h, const float* A, int64_t lda, const std::strin
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = w->p; g.ldw = w->shape[1]; g.bias = b ? b->p : nullptr;
   g.C = C; g.ldc = ldc; g.M = M; g.N = (int)w->shape[0]; g.K = (int)w->shape[1]; g.C2 = C2; g.ldc2 = ldc2;
-  return gemm(h->cfg.precision, g, epi, s);
+  return gemm(h, h->cfg.precision, g, epi, s);
 }
 
 int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool expand, cudaStream_t s) {
@@ -194,7 +194,7 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
   GemmArgs g{};
   g.A = S.meanb; g.lda = D; g.W = h->w_init; g.ldw = D; g.bias = h->b_init; g.C = S.init; g.ldc = 2 * H;
   g.M = S.B; g.N = 2 * H; g.K = D;
-  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_STORE, s));
+  CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_STORE, s));
   if (expand) {
     CAPDEC_RETURN_IF(expand_rows(S.init, 2 * H, S.X[0] + E + D, S.ldX[0], S.R, S.k, H, s));
     CAPDEC_RETURN_IF(expand_rows(S.init + H, 2 * H, S.c[0], H, S.R, S.k, H, s));
@@ -219,7 +219,7 @@ int prologue_lstm(const capdec_handle* h, Session& S, const float* feats, const 
   GemmArgs g{};
   g.A = pooled; g.lda = H; g.W = h->w_init; g.ldw = H; g.bias = h->b_init; g.C = S.init; g.ldc = 2 * layers * H;
   g.M = S.B; g.N = 2 * layers * H; g.K = H;
-  CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_STORE, s));
+  CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_STORE, s));
   for (int l = 0; l < layers; ++l) {
     const int in = l == 0 ? E + H : H;
     CAPDEC_RETURN_IF(expand_rows(S.init + (size_t)l * H, 2 * layers * H, S.X[l] + in, S.ldX[l], S.R, S.k, H, s));
@@ -255,7 +255,7 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
     GemmArgs g{};
     g.A = S.qq; g.lda = 2 * H; g.W = w->p; g.ldw = 2 * H; g.bias = h->W("attention.sentinel_gate.bias");
     g.C = S.sgate; g.ldc = H; g.M = rows; g.N = H; g.K = 2 * H; g.n_split = 0;
-    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s));
+    CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_SIGMOID_TAIL, s));
     const int64_t n = (int64_t)rows * H;
     sentinel_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(S.sgate, H, cell, ld_cell, S.spre, H, rows, H);
     CAPDEC_LAUNCH_CHECK();
@@ -287,7 +287,7 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
     GemmArgs g{};
     g.A = S.cat; g.lda = 2 * H; g.W = h->w_aoa; g.ldw = 2 * H; g.bias = h->b_aoa; g.C = ctx_out; g.ldc = H;
     g.M = rows; g.N = 2 * H; g.K = 2 * H;
-    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_AOA, s));
+    CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_AOA, s));
   } else if (c.attention == CAPDEC_ATT_ADAPTIVE) {
     adaptive_mix_kernel<<<rows, 128, 0, s>>>(S.base_ctx, S.sent, h->W("attention.adaptive_weight.weight"),
                                              h->adaptive_bias, ctx_out, H, H);
@@ -306,7 +306,7 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   GemmArgs g{};
   g.A = S.X[0] + E + D; g.lda = S.ldX[0]; g.W = h->w_hproj; g.ldw = H; g.bias = h->b_hproj;
   g.C = S.hproj; g.ldc = A + D; g.M = rows; g.N = A + D; g.K = H; g.n_split = A;
-  { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_SIGMOID_TAIL, s)); }
+  { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_SIGMOID_TAIL, s)); }
   // scores -> softmax -> gated context, written straight into the LSTM operand (:154-161)
   AddAttnArgs a{};
   a.att1 = S.att1; a.att2 = S.hproj; a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
@@ -319,7 +319,7 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   l.A = S.X[0]; l.lda = S.ldX[0]; l.W = h->w_gates[0]; l.ldw = E + D + H; l.bias = h->b_gates[0];
   l.C = S.hnew[0]; l.ldc = H; l.M = rows; l.N = 4 * H; l.K = E + D + H;
   l.c_in = S.c[0]; l.ldcin = H; l.c_out = S.cnew[0]; l.ldcout = H;
-  { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(c.precision, l, EPI_LSTM, s)); }
+  { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, l, EPI_LSTM, s)); }
   // fc(h)  (:171; dropout is the identity in eval)
   { StageScope sc(h, STAGE_VOCAB_GEMM, s); CAPDEC_RETURN_IF(linear(h, S.hnew[0], H, "fc", logits, ld_logits, rows, EPI_STORE, s)); }
   (void)V;
@@ -343,7 +343,7 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
     if (!top) { g.C2 = S.X[l + 1]; g.ldc2 = S.ldX[l + 1]; }
     else if (adaptive) { g.C2 = S.hnew[l] + H; g.ldc2 = 2 * H; }  // [q | memory_state] with memory_state == q
     StageScope sc(h, STAGE_GATE_GEMM, s);
-    CAPDEC_RETURN_IF(gemm(c.precision, g, EPI_LSTM, s));
+    CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_LSTM, s));
   }
   const float* q = S.hnew[layers - 1];
   const int64_t ld_q = adaptive ? 2 * H : H;
@@ -399,8 +399,8 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
 int check_common(const capdec_handle* h, const float* feats, const float* pooled, int B, int L, int k, int T) {
   CAPDEC_REQUIRE(h != nullptr, CAPDEC_ERR_INVALID, "null handle");
   CAPDEC_REQUIRE(h->finalized, CAPDEC_ERR_STATE, "capdec_finalize has not been called");
-  CAPDEC_REQUIRE(feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
-  CAPDEC_REQUIRE(is_legacy(h) || pooled != nullptr, CAPDEC_ERR_INVALID, "pooled_features pointer is null");
+  CAPDEC_REQUIRE(B == 0 || feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
+  CAPDEC_REQUIRE(B == 0 || is_legacy(h) || pooled != nullptr, CAPDEC_ERR_INVALID, "pooled_features pointer is null");
   CAPDEC_REQUIRE(B >= 0 && L >= 1 && T >= 2, CAPDEC_ERR_INVALID, "bad sizes B=%d L=%d max_length=%d", B, L, T);
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "rows per image %d not in [1,%d]", k,
                  kMaxRowsPerImage);
@@ -469,7 +469,7 @@ int capdec_create(const capdec_config* cfg, capdec_handle** out) {
                  "unsupported decoder arch %d", cfg->arch);
   CAPDEC_REQUIRE(cfg->attention >= CAPDEC_ATT_SOFT && cfg->attention <= CAPDEC_ATT_AOA, CAPDEC_ERR_UNSUPPORTED,
                  "Unsupported attention type: %d", cfg->attention);
-  CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_BF16, CAPDEC_ERR_UNSUPPORTED,
+  CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
                  "unsupported precision %d", cfg->precision);
   CAPDEC_REQUIRE(cfg->vocab_size > 0 && cfg->hidden_dim > 0 && cfg->embed_dim > 0 && cfg->num_layers >= 1 &&
                      cfg->num_layers <= 7,
@@ -495,6 +495,7 @@ void capdec_destroy(capdec_handle* h) {
   if (!h) return;
   for (auto& kv : h->w) cudaFree(kv.second.p);
   for (void* p : h->owned) cudaFree(p);
+  gemm_tc_release(h);
   if (h->stage_dev) cudaFree(h->stage_dev);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -638,7 +639,7 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
                        float* out_score, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes,
                        void* stream) {
   CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, k, T));
-  CAPDEC_REQUIRE(out_tok && out_len && out_score, CAPDEC_ERR_INVALID, "output pointers must not be null");
+  CAPDEC_REQUIRE(B == 0 || (out_tok && out_len && out_score), CAPDEC_ERR_INVALID, "output pointers must not be null");
   CAPDEC_REQUIRE(is_legacy(h) ? mask == nullptr : true, CAPDEC_ERR_UNSUPPORTED, "legacy decoder takes no padding mask");
   cudaStream_t s = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
@@ -877,7 +878,7 @@ int capdec_linear(int32_t precision, const float* a, int64_t lda, const float* w
                   float* c, int64_t ldc, int32_t m, int32_t n, int32_t k, void* stream) {
   GemmArgs g{};
   g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.C = c; g.ldc = ldc; g.M = m; g.N = n; g.K = k;
-  return gemm(precision, g, EPI_STORE, (cudaStream_t)stream);
+  return gemm(nullptr, precision, g, EPI_STORE, (cudaStream_t)stream);
 }
 
 int capdec_lse_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t topk, float* out_lp,

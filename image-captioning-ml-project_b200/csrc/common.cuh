@@ -94,6 +94,5 @@ struct GemmArgs {
 };
 
 int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s);
-int gemm(int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
 
 }  // namespace capdec

@@ -1,0 +1,55 @@
+// Fused GEMM epilogues shared by the CUDA-core (gemm_ffma.cu) and tcgen05 (gemm_tc.cu) kernels.
+#pragma once
+#include "common.cuh"
+
+namespace capdec {
+
+template <int EPI>
+__device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float v0, float v1, float v2, float v3) {
+  // (m, n..n+3) with n % 4 == 0.  Fused epilogues require N % 4 == 0 (checked by the launcher); the plain
+  // store family also handles a ragged last group and unaligned C rows (e.g. V = 50257 logits).
+  if (m >= p.M || n >= p.N) return;
+  if (EPI == EPI_STORE || EPI == EPI_SIGMOID_TAIL || EPI == EPI_TANH) {
+    const bool vec_ok = (n + 3 < p.N) && ((p.ldc & 3) == 0) && (!p.C2 || (p.ldc2 & 3) == 0);
+    if (!vec_ok) {
+      float v[4] = {v0, v1, v2, v3};
+      for (int j = 0; j < 4 && n + j < p.N; ++j) {
+        float t = v[j] + (p.bias ? p.bias[n + j] : 0.f);
+        if (EPI == EPI_SIGMOID_TAIL && n + j >= p.n_split) t = sigmoidf_(t);
+        if (EPI == EPI_TANH) t = tanhf(t);
+        p.C[(int64_t)m * p.ldc + n + j] = t;
+        if (p.C2) p.C2[(int64_t)m * p.ldc2 + n + j] = t;
+      }
+      return;
+    }
+  }
+  if (p.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
+    v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+  }
+  if (EPI == EPI_STORE || EPI == EPI_SIGMOID_TAIL || EPI == EPI_TANH) {
+    if (EPI == EPI_SIGMOID_TAIL && n >= p.n_split) {
+      v0 = sigmoidf_(v0); v1 = sigmoidf_(v1); v2 = sigmoidf_(v2); v3 = sigmoidf_(v3);
+    }
+    if (EPI == EPI_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); v2 = tanhf(v2); v3 = tanhf(v3); }
+    *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v0, v1, v2, v3);
+    if (p.C2) *reinterpret_cast<float4*>(p.C2 + (int64_t)m * p.ldc2 + n) = make_float4(v0, v1, v2, v3);
+  } else if (EPI == EPI_LSTM) {
+    // torch.nn.LSTMCell: c' = sigmoid(f)*c + sigmoid(i)*tanh(g);  h' = sigmoid(o)*tanh(c')
+    const int j = n >> 2;
+    const float cp = p.c_in[(int64_t)m * p.ldcin + j];
+    const float c2 = sigmoidf_(v1) * cp + sigmoidf_(v0) * tanhf(v2);
+    const float h2 = sigmoidf_(v3) * tanhf(c2);
+    p.c_out[(int64_t)m * p.ldcout + j] = c2;
+    p.C[(int64_t)m * p.ldc + j] = h2;
+    if (p.C2) p.C2[(int64_t)m * p.ldc2 + j] = h2;
+  } else if (EPI == EPI_AOA) {
+    const int j = n >> 1;
+    const float o0 = tanhf(v0) * sigmoidf_(v1);
+    const float o1 = tanhf(v2) * sigmoidf_(v3);
+    *reinterpret_cast<float2*>(p.C + (int64_t)m * p.ldc + j) = make_float2(o0, o1);
+    if (p.C2) *reinterpret_cast<float2*>(p.C2 + (int64_t)m * p.ldc2 + j) = make_float2(o0, o1);
+  }
+}
+
+}  // namespace capdec

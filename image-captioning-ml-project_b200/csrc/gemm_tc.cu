@@ -1,14 +1,390 @@
-// Tensor-core GEMM modes (tcgen05).  Placeholder until the tcgen05 path lands: the modes report
-// CAPDEC_ERR_UNSUPPORTED instead of silently falling back to the fp32 kernel.
+// tcgen05 GEMM for the dense contractions of the decode step (CAPDEC_PREC_TF32X3):
+//     C[M,N] = A[M,K] * W[N,K]^T + bias,  fused epilogues as in gemm_epilogue.cuh
+// fp32-equivalent accuracy on the 5th-gen tensor cores by the 3-term TF32 split
+//     a = a_hi + a_lo,  w = w_hi + w_lo   (hi = cvt.rna.tf32(x), lo = x - hi, exact in fp32)
+//     a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi       (the dropped lo*lo term is ~2^-22 relative)
+// accumulated in fp32 in TMEM.  tcgen05 has no IEEE-fp32 MMA; this is the split-accumulate form
+// SURVEY.md section 7 names for the fp32 mode.
+//
+// Kernel: one 128 x BN output tile per CTA, K streamed in 32-float (128-byte, SWIZZLE_128B) blocks.
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A_hi/A_lo/W_hi/W_lo tiles, mbarrier tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8),
+//               tcgen05.commit releases shared-memory stages and publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+#include <cuda.h>
+
+#include "gemm_epilogue.cuh"
 #include "handle.cuh"
 
 namespace capdec {
+namespace {
 
-int gemm_tc(int precision, const GemmArgs&, int, cudaStream_t) {
-  set_error("precision mode %d is not built into this libcapdec", precision);
-  return CAPDEC_ERR_UNSUPPORTED;
+constexpr int BM = 128, BK = 32;
+constexpr int kStages = 2;
+constexpr int kThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2.  cute/arch/mma_sm100_desc.hpp::SmemDescriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute/arch/mma_sm100_desc.hpp::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major A and B,
+// n_dim = N>>3 @17, m_dim = M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-int gemm_tc_prepare(capdec_handle*, cudaStream_t) { return CAPDEC_OK; }
+template <int BN>
+struct SmemLayout {
+  static constexpr uint32_t kABytes = BM * BK * 4;
+  static constexpr uint32_t kWBytes = BN * BK * 4;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
+};
+
+template <int BN, int EPI, int TERMS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                    const GemmArgs p) {
+  using SL = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * SL::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes);
+        tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m_tile * BM);
+        tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, n_tile * BN);
+        if (TERMS == 3) {
+          tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, m_tile * BM);
+          tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * SL::kStageBytes);
+        const uint32_t a_lo = a_hi + SL::kABytes;
+        const uint32_t w_hi = a_hi + 2 * SL::kABytes;
+        const uint32_t w_lo = w_hi + SL::kWBytes;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span
+          const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+          if (TERMS == 3) {
+            mma_tf32(tmem_base, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), idesc, first);
+            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), idesc, 1u);
+            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, 1u);
+          } else {
+            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, first);
+          }
+        }
+        tcgen05_commit(&empty_bar[s]);                      // frees this shared-memory stage when the MMAs retire
+        if (kb == num_kb - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int m = m_tile * BM + q * 32 + lane;   // accumulator row == TMEM lane
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n0 = n_tile * BN + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// hi = round-to-nearest TF32 of x (exactly representable, so the tensor core's own fp32->tf32 conversion is the
+// identity whatever its rounding), lo = x - hi (exact).  Output is dense [rows, cols].
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const int c4 = cols >> 2;
+  if (i >= (int64_t)rows * c4) return;
+  const int r = (int)(i / c4), c = (int)(i - (int64_t)r * c4);
+  const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ld + c * 4);
+  float4 h, l;
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+int split_tf32(const float* x, int64_t ld, int rows, int cols, float* hi, float* lo, cudaStream_t s) {
+  const int64_t n = (int64_t)rows * (cols / 4);
+  if (n == 0) return CAPDEC_OK;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, hi, lo);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CAPDEC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+    CAPDEC_REQUIRE(ptr != nullptr && q == cudaDriverEntryPointSuccess, CAPDEC_ERR_CUDA,
+                   "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (EncodeTiledFn)ptr;
+  }
+  *out = fn;
+  return CAPDEC_OK;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [box_rows, BK]; 128-byte swizzle; OOB -> 0
+int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn;
+  CAPDEC_RETURN_IF(get_encode_fn(&fn));
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CAPDEC_REQUIRE(r == CUDA_SUCCESS, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)",
+                 (int)r, (long long)rows, (long long)cols, (long long)ld);
+  return CAPDEC_OK;
+}
+
+template <int BN, int TERMS>
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+              const GemmArgs& g, int epi, cudaStream_t s) {
+  constexpr int smem = SmemLayout<BN>::kTotal;
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+#define CAPDEC_TC_CASE(E)                                                                                         \
+  case E: {                                                                                                       \
+    auto kern = gemm_tcgen05_kernel<BN, E, TERMS>;                                                                \
+    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
+    kern<<<grid, kThreads, smem, s>>>(a_hi, a_lo, w_hi, w_lo, g);                                                 \
+    break;                                                                                                        \
+  }
+  switch (epi) {
+    CAPDEC_TC_CASE(EPI_STORE)
+    CAPDEC_TC_CASE(EPI_SIGMOID_TAIL)
+    CAPDEC_TC_CASE(EPI_LSTM)
+    CAPDEC_TC_CASE(EPI_TANH)
+    CAPDEC_TC_CASE(EPI_AOA)
+    default: CAPDEC_REQUIRE(false, CAPDEC_ERR_INVALID, "gemm_tc: unknown epilogue %d", epi);
+  }
+#undef CAPDEC_TC_CASE
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+struct Scratch {
+  float* p = nullptr;
+  size_t bytes = 0;
+};
+Scratch g_scratch;  // handle-less path (capdec_linear): grow-only, process lifetime
+
+int ensure(float** p, size_t* have, size_t need) {
+  if (*have >= need) return CAPDEC_OK;
+  if (*p) CAPDEC_CHECK_CUDA(cudaFree(*p));
+  *p = nullptr; *have = 0;
+  CAPDEC_CHECK_CUDA(cudaMalloc((void**)p, need));
+  *have = need;
+  return CAPDEC_OK;
+}
+
+}  // namespace
+
+int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
+  CAPDEC_REQUIRE(precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
+                 "precision mode %d has no kernel in this build", precision);
+  CAPDEC_REQUIRE(a.M >= 0 && a.N > 0 && a.K > 0, CAPDEC_ERR_INVALID, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  if (a.M == 0) return CAPDEC_OK;
+  CAPDEC_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0, CAPDEC_ERR_UNSUPPORTED,
+                 "gemm: K, lda, ldw must be multiples of 4 (K=%d lda=%lld ldw=%lld)", a.K, (long long)a.lda, (long long)a.ldw);
+  if (epilogue == EPI_LSTM || epilogue == EPI_AOA)
+    CAPDEC_REQUIRE(a.N % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "gemm: fused epilogue needs N %% 4 == 0 (N=%d)", a.N);
+  CAPDEC_REQUIRE((((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.bias | (uintptr_t)a.C) & 15) == 0, CAPDEC_ERR_INVALID,
+                 "gemm: A/W/bias/C must be 16-byte aligned");
+  const int terms = precision == CAPDEC_PREC_TF32X3 ? 3 : 1;
+  const int K = a.K;
+
+  // ---- weight split: cached per handle (weights are immutable after capdec_finalize)
+  float *w_hi = nullptr, *w_lo = nullptr;
+  const size_t w_elems = (size_t)a.N * K;
+  if (h) {
+    auto it = h->tc_weights.find(a.W);
+    if (it == h->tc_weights.end()) {
+      float* buf = nullptr;
+      CAPDEC_CHECK_CUDA(cudaMalloc((void**)&buf, 2 * w_elems * sizeof(float)));
+      CAPDEC_RETURN_IF(split_tf32(a.W, a.ldw, a.N, K, buf, buf + w_elems, s));
+      h->tc_weights[a.W] = buf;
+      it = h->tc_weights.find(a.W);
+    }
+    w_hi = it->second; w_lo = w_hi + w_elems;
+  }
+  // ---- activation split scratch, M chunked so the scratch stays <= ~1 GiB
+  const size_t cap_bytes = (size_t)1 << 30;
+  int m_chunk = (int)((cap_bytes / (2 * (size_t)K * sizeof(float))) / BM * BM);
+  if (m_chunk < BM) m_chunk = BM;
+  if (m_chunk > a.M) m_chunk = a.M;
+  const size_t a_elems = (size_t)m_chunk * K;
+  float* scratch = nullptr;
+  if (h) {
+    CAPDEC_RETURN_IF(ensure(&h->tc_scratch, &h->tc_scratch_bytes, 2 * a_elems * sizeof(float)));
+    scratch = h->tc_scratch;
+  } else {
+    CAPDEC_RETURN_IF(ensure(&g_scratch.p, &g_scratch.bytes, (2 * a_elems + 2 * w_elems) * sizeof(float)));
+    scratch = g_scratch.p;
+    w_hi = scratch + 2 * a_elems; w_lo = w_hi + w_elems;
+    CAPDEC_RETURN_IF(split_tf32(a.W, a.ldw, a.N, K, w_hi, w_lo, s));
+  }
+  float* a_hi = scratch;
+  float* a_lo = scratch + a_elems;
+
+  const int bn = a.N <= 128 ? 128 : 256;
+  CUtensorMap map_w_hi, map_w_lo;
+  CAPDEC_RETURN_IF(make_map(&map_w_hi, w_hi, a.N, K, K, bn));
+  CAPDEC_RETURN_IF(make_map(&map_w_lo, w_lo, a.N, K, K, bn));
+
+  for (int m0 = 0; m0 < a.M; m0 += m_chunk) {
+    const int mc = a.M - m0 < m_chunk ? a.M - m0 : m_chunk;
+    CAPDEC_RETURN_IF(split_tf32(a.A + (int64_t)m0 * a.lda, a.lda, mc, K, a_hi, a_lo, s));
+    CUtensorMap map_a_hi, map_a_lo;
+    CAPDEC_RETURN_IF(make_map(&map_a_hi, a_hi, mc, K, K, BM));
+    CAPDEC_RETURN_IF(make_map(&map_a_lo, a_lo, mc, K, K, BM));
+    GemmArgs g = a;
+    g.M = mc;
+    g.C = a.C + (int64_t)m0 * a.ldc;
+    if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
+    if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
+    if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
+    int st;
+    if (bn == 128) st = terms == 3 ? launch_tc<128, 3>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+                                   : launch_tc<128, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+    else           st = terms == 3 ? launch_tc<256, 3>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+                                   : launch_tc<256, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+    CAPDEC_RETURN_IF(st);
+  }
+  return CAPDEC_OK;
+}
+
+int gemm_tc_prepare(capdec_handle* h, cudaStream_t) {
+  for (auto& kv : h->tc_weights) cudaFree(kv.second);
+  h->tc_weights.clear();
+  return CAPDEC_OK;
+}
+
+void gemm_tc_release(capdec_handle* h) {
+  for (auto& kv : h->tc_weights) cudaFree(kv.second);
+  h->tc_weights.clear();
+  if (h->tc_scratch) cudaFree(h->tc_scratch);
+  h->tc_scratch = nullptr; h->tc_scratch_bytes = 0;
+}
 
 }  // namespace capdec

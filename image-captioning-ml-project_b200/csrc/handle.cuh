@@ -43,6 +43,11 @@ struct capdec_handle {
   mutable std::vector<int> ev_stage;             // stage id of pair i
   mutable size_t ev_used = 0;
 
+  // ---- tensor-core GEMM state (gemm_tc.cu): split weight copies keyed by weight pointer, activation scratch
+  mutable std::map<const float*, float*> tc_weights;
+  mutable float* tc_scratch = nullptr;
+  mutable size_t tc_scratch_bytes = 0;
+
   const DevTensor* find(const std::string& n) const {
     auto it = w.find(n);
     return it == w.end() ? nullptr : &it->second;
@@ -98,7 +103,9 @@ struct StageScope {
 };
 
 // tensor-core GEMM modes (gemm_tc.cu)
-int gemm_tc(int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
+int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
 int gemm_tc_prepare(capdec_handle* h, cudaStream_t s);
+void gemm_tc_release(capdec_handle* h);
+int gemm(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
 
 }  // namespace capdec

@@ -55,7 +55,8 @@ typedef enum {
 typedef enum {
   CAPDEC_PREC_FP32 = 0,    /* CUDA-core FFMA, IEEE fp32 accumulate: the exact mode            */
   CAPDEC_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
-  CAPDEC_PREC_BF16 = 2     /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate             */
+  CAPDEC_PREC_BF16 = 2,    /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate (not built yet: UNSUPPORTED) */
+  CAPDEC_PREC_TF32 = 3     /* tcgen05 kind::tf32 single pass on round-to-nearest TF32 operands, fp32 accumulate */
 } capdec_precision;
 
 typedef struct {

@@ -93,7 +93,7 @@ def generate_greedy(sd, feats, pooled, kind, num_layers, max_length, num_heads=8
         logits = st(cur)
         alphas.append(st.last_alpha)
         top2 = logits.topk(2, dim=1).values
-        margins.append(top2[:, 0] - top2[:, 1])
+        margins.append((top2[:, 0] - top2[:, 1]) / logits.std(dim=1))   # top-1/top-2 gap in units of the logit spread
         cur = logits.argmax(dim=1)
     res = (out, torch.stack(alphas, dim=1))
     if return_margins:

@@ -27,9 +27,22 @@ def greedy_rollout(stepper, num_rows, max_length, start_token_id=1):
         out[:, t] = cur
         logits = stepper(cur)
         top2 = logits.topk(2, dim=1).values
-        margins.append(top2[:, 0] - top2[:, 1])
+        margins.append((top2[:, 0] - top2[:, 1]) / logits.std(dim=1))   # gap in units of the logit spread
         cur = logits.argmax(dim=1)
     return out, torch.stack(margins, dim=1)
+
+
+@torch.no_grad()
+def rescore(stepper, sequences, lengths, length_penalty=1.0):
+    """Oracle score of given hypotheses (one row per image): sum of log p(token) over the generated tokens
+    divided by generated_length ** length_penalty -- what HF's finished-beam score is for that sequence."""
+    R, T = sequences.shape
+    total = torch.zeros(R)
+    for t in range(T - 1):
+        logp = torch.log_softmax(stepper(sequences[:, t]).float(), dim=-1)
+        step_lp = logp.gather(1, sequences[:, t + 1:t + 2].clamp(min=0)).squeeze(1)
+        total += torch.where(t + 1 < lengths, step_lp, torch.zeros(R))
+    return total / ((lengths - 1).float() ** length_penalty)
 
 
 @torch.no_grad()
