@@ -225,8 +225,9 @@ int prologue_lstm(const capdec_handle* h, Session& S, const float* feats, const 
     CAPDEC_RETURN_IF(expand_rows(S.init + (size_t)l * H, 2 * layers * H, S.X[l] + in, S.ldX[l], S.R, S.k, H, s));
     CAPDEC_RETURN_IF(expand_rows(S.init + (size_t)(layers + l) * H, 2 * layers * H, S.c[l], H, S.R, S.k, H, s));
   }
-  // prev_ctx = 0 (decoders.py:265-266)
+  // prev_ctx = 0 (decoders.py:265-266): both the attention output buffer and its slot in the LSTM operand
   CAPDEC_CHECK_CUDA(cudaMemsetAsync(S.ctx, 0, (size_t)S.R * H * sizeof(float), s));
+  CAPDEC_CHECK_CUDA(cudaMemset2DAsync(S.X[0] + E, S.ldX[0] * sizeof(float), 0, (size_t)H * sizeof(float), S.R, s));
   return CAPDEC_OK;
 }
 

@@ -6,6 +6,7 @@ stream; every computation happens in libcapdec's kernels behind the C ABI (inclu
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -47,7 +48,7 @@ class Engine:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:      # `lib` is already None during interpreter shutdown
             lib.capdec_destroy(h)
             self._h = None
 
@@ -57,6 +58,8 @@ class Engine:
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if os.environ.get("CAPDEC_POISON_WORKSPACE"):     # tests: every call starts from NaN-filled scratch
+            self._ws.fill_(0xFF)
         return self._ws
 
     def _mask(self, key_padding_mask, B, L):

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+os.environ.setdefault("CAPDEC_POISON_WORKSPACE", "1")   # catch reads of uninitialised workspace
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # the product library must exist before the package can be imported (no fallback): build it if absent
