@@ -35,8 +35,9 @@ int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s);
 // src/models/attention.py:161-211 (the output_proj GEMM follows outside).
 struct MhaArgs {
   const float* q; int64_t ld_q;         // [R,H] projected query
-  const float* kproj;                   // [B,L,H] hoisted key_proj(key)
-  const float* vproj;                   // [B,L,H] hoisted value_proj(value)
+  const float* kproj;                   // [B,L,H] hoisted key_proj(key), row stride ld_kv
+  const float* vproj;                   // [B,L,H] hoisted value_proj(value), row stride ld_kv
+  int64_t ld_kv;
   const uint8_t* mask;                  // [B,L] or nullptr
   float denom;                          // temperature * sqrt(head_dim)
   float* out; int64_t ld_out;           // [R,H] concatenated heads

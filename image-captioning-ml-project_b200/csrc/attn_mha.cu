@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kThreads) mha_attention_kernel(const MhaArgs p
   __syncthreads();
 
   // ---- scores
-  const float* K = p.kproj + (int64_t)img * L * H;
+  const float* K = p.kproj + (int64_t)img * L * p.ld_kv;
   for (int l0 = warp * kRowsPerIter; l0 < L; l0 += kWarps * kRowsPerIter) {
     for (int hd = 0; hd < heads; ++hd) {
       float acc[kRowsPerIter][KB];
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) mha_attention_kernel(const MhaArgs p
 #pragma unroll
         for (int r = 0; r < kRowsPerIter; ++r) {
           const int l = min(l0 + r, L - 1);
-          x[r] = ldg_stream(reinterpret_cast<const float4*>(K + (int64_t)l * H + hd * d) + c);
+          x[r] = ldg_stream(reinterpret_cast<const float4*>(K + (int64_t)l * p.ld_kv + hd * d) + c);
         }
 #pragma unroll
         for (int b = 0; b < KB; ++b) {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) mha_attention_kernel(const MhaArgs p
   }
 
   // ---- attended values, heads concatenated
-  const float* V = p.vproj + (int64_t)img * L * H;
+  const float* V = p.vproj + (int64_t)img * L * p.ld_kv;
   int G = 1;
   while (H4 * G * 2 <= kThreads) G *= 2;
 
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) mha_attention_kernel(const MhaArgs p
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int ll = min(l + u, L - 1);
-        x[u] = ldg_stream(reinterpret_cast<const float4*>(V + (int64_t)ll * H) + c);
+        x[u] = ldg_stream(reinterpret_cast<const float4*>(V + (int64_t)ll * p.ld_kv) + c);
       }
 #pragma unroll
       for (int b = 0; b < KB; ++b) {
@@ -194,7 +194,7 @@ int mha_attention(const MhaArgs& a, cudaStream_t s) {
                  "mha_attention: rows per image %d not in [1,%d]", a.k, kMaxRowsPerImage);
   CAPDEC_REQUIRE(a.heads >= 1 && a.H % a.heads == 0 && (a.H / a.heads) % 4 == 0, CAPDEC_ERR_UNSUPPORTED,
                  "mha_attention: head_dim must be a multiple of 4 (H=%d heads=%d)", a.H, a.heads);
-  CAPDEC_REQUIRE(a.ld_q % 4 == 0 && a.ld_out % 4 == 0, CAPDEC_ERR_INVALID, "mha_attention: strides must be multiples of 4");
+  CAPDEC_REQUIRE(a.ld_q % 4 == 0 && a.ld_out % 4 == 0 && a.ld_kv % 4 == 0 && a.ld_kv >= a.H, CAPDEC_ERR_INVALID, "mha_attention: strides must be multiples of 4");
   if (a.B == 0) return CAPDEC_OK;
   switch (a.k) {
     case 1: return launch_kb<1>(a, s);

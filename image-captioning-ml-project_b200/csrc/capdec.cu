@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include "handle.cuh"
+#include "transformer.cuh"
 
 namespace capdec {
 
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(128) adaptive_mix_kernel(const float* ctx, con
 }
 
 bool is_legacy(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_LEGACY_SAT; }
+bool is_transformer(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_TRANSFORMER; }
 bool base_is_mha(const capdec_handle* h) {
   const int a = h->cfg.attention;
   if (a == CAPDEC_ATT_MULTI_HEAD) return true;
@@ -104,6 +106,12 @@ struct Session {
   float* keyp = nullptr; float* valp = nullptr; float* qproj = nullptr; float* att_out = nullptr;
   float* ctx = nullptr; float* cat = nullptr; float* qq = nullptr; float* sgate = nullptr; float* spre = nullptr;
   float* sent = nullptr; float* base_ctx = nullptr;
+  // transformer arch
+  float* tx = nullptr; float* tqkv = nullptr; float* tsa = nullptr; float* ty = nullptr; float* tqc = nullptr;
+  float* tca = nullptr; float* tff = nullptr; float* tmem = nullptr;
+  std::vector<float*> tckv, tcache_k, tcache_v;
+  int32_t* anc[2] = {nullptr, nullptr};
+  int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
@@ -114,6 +122,30 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   S.B = B; S.L = L; S.k = k; S.R = B * k; S.T = T;
   const size_t R = (size_t)S.R;
   const int layers = c.num_layers;
+  if (is_transformer(h)) {
+    const DevTensor* f1 = h->find("transformer_decoder.layers.0.linear1.weight");
+    const size_t F = f1 ? (size_t)f1->shape[0] : (size_t)4 * H;
+    S.tx = ar.take<float>(R * H); S.tqkv = ar.take<float>(R * 3 * H); S.tsa = ar.take<float>(R * H);
+    S.ty = ar.take<float>(R * H); S.tqc = ar.take<float>(R * H); S.tca = ar.take<float>(R * H);
+    S.tff = ar.take<float>(R * F);
+    S.tmem = ar.take<float>((size_t)B * L * H);
+    S.tckv.resize(layers); S.tcache_k.resize(layers); S.tcache_v.resize(layers);
+    for (int l = 0; l < layers; ++l) {
+      S.tckv[l] = ar.take<float>((size_t)B * L * 2 * H);
+      S.tcache_k[l] = ar.take<float>(R * T * H);
+      S.tcache_v[l] = ar.take<float>(R * T * H);
+    }
+    S.anc[0] = ar.take<int32_t>(R * T); S.anc[1] = ar.take<int32_t>(R * T);
+    S.logits = ar.take<float>(R * V);
+    S.next_tok = ar.take<int32_t>(R); S.src_row = ar.take<int32_t>(R); S.step_lp = ar.take<float>(R);
+    S.cand_lp = ar.take<float>(R * 2 * k); S.cand_idx = ar.take<int32_t>(R * 2 * k);
+    if (mode == MODE_BEAM) {
+      for (int i = 0; i < 2; ++i) { S.beam.run_seq[i] = ar.take<int32_t>(R * T); S.beam.fin_seq[i] = ar.take<int32_t>(R * T); }
+      S.beam.run_score = ar.take<float>(R); S.beam.fin_score = ar.take<float>(R); S.beam.fin_len = ar.take<int32_t>(R);
+      S.beam.fin_flag = ar.take<uint8_t>(R); S.beam.unsatisfied = ar.take<uint8_t>(B);
+    }
+    return CAPDEC_OK;
+  }
   if (mode != MODE_ATTENTION) {
     S.X.resize(layers); S.c.resize(layers); S.cnew.resize(layers); S.hnew.resize(layers); S.ldX.resize(layers);
     for (int l = 0; l < layers; ++l) {
@@ -266,7 +298,7 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
   { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(linear(h, q, ld_q, p + "query_proj", S.qproj, H, rows, EPI_STORE, s)); }
   if (base_is_mha(h)) {
     MhaArgs m{};
-    m.q = S.qproj; m.ld_q = H; m.kproj = S.keyp; m.vproj = S.valp; m.mask = mask;
+    m.q = S.qproj; m.ld_q = H; m.kproj = S.keyp; m.vproj = S.valp; m.ld_kv = H; m.mask = mask;
     m.denom = (float)((double)c.temperature * sqrt((double)(H / c.num_heads)));
     m.out = S.att_out; m.ld_out = H; m.alpha = alpha; m.ld_alpha = ld_alpha;
     m.B = images; m.L = S.L; m.H = H; m.heads = c.num_heads; m.k = k;
@@ -365,15 +397,110 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
   return CAPDEC_OK;
 }
 
+
+// ---- transformer arch (src/models/decoders.py:317-493) ----------------------------------------------------------
+std::string tl(int l, const char* name) { return "transformer_decoder.layers." + std::to_string(l) + "." + name; }
+
+int gemm_w(const capdec_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+           int64_t ldc, int M, int N, int K, int epi, cudaStream_t s) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  return gemm(h, h->cfg.precision, g, epi, s);
+}
+
+int prologue_transformer(const capdec_handle* h, Session& S, const float* feats, cudaStream_t s) {
+  StageScope sc(h, STAGE_PROLOGUE, s);
+  const int H = h->cfg.hidden_dim, rows = S.B * S.L;
+  // memory = visual_projection(features)  (decoders.py:453), then every layer's cross-attention K|V projection of
+  // it, hoisted out of the step loop (nn.MultiheadAttention in_proj rows [H:3H) are the packed k and v projections)
+  CAPDEC_RETURN_IF(linear(h, feats, H, "visual_projection", S.tmem, H, rows, EPI_STORE, s));
+  for (int l = 0; l < h->cfg.num_layers; ++l) {
+    const float* w = h->W(tl(l, "multihead_attn.in_proj_weight"));
+    const float* b = h->W(tl(l, "multihead_attn.in_proj_bias"));
+    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)H * H, H, b + H, S.tckv[l], 2 * H, rows, 2 * H, H, EPI_STORE, s));
+  }
+  S.anc_cur = -1;
+  return CAPDEC_OK;
+}
+
+// one KV-cached decode step at position t: tokens S.next_tok -> S.logits
+int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, rows = S.R, heads = c.num_heads;
+  const DevTensor* pos = h->find("position_encoding.weight");
+  CAPDEC_REQUIRE(t < pos->shape[0], CAPDEC_ERR_INVALID, "position %d exceeds position_encoding rows %lld", t, (long long)pos->shape[0]);
+  const int F = (int)h->find(tl(0, "linear1.weight"))->shape[0];
+  { StageScope sc(h, STAGE_GATHER, s);
+    CAPDEC_RETURN_IF(embed_pos(S.next_tok, h->W("embedding.weight"), pos->p + (size_t)t * H, S.tx, rows, H, s)); }
+  const float eps = 1e-5f;
+  for (int l = 0; l < c.num_layers; ++l) {
+    // self-attention block: x = norm1(x + out_proj(attn(in_proj(x))))   (post-LN, norm_first=False)
+    { StageScope sc(h, STAGE_SMALL_GEMM, s);
+      CAPDEC_RETURN_IF(gemm_w(h, S.tx, H, h->W(tl(l, "self_attn.in_proj_weight")), H, h->W(tl(l, "self_attn.in_proj_bias")),
+                              S.tqkv, 3 * H, rows, 3 * H, H, EPI_STORE, s)); }
+    { StageScope sc(h, STAGE_ATTENTION, s);
+      SelfAttnArgs a{};
+      a.qkv = S.tqkv; a.ld_qkv = 3 * H; a.cache_k = S.tcache_k[l]; a.cache_v = S.tcache_v[l];
+      a.anc = S.anc_cur >= 0 ? S.anc[S.anc_cur] : nullptr; a.n_prefix = 0; a.rows_per_image = S.k;
+      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H;
+      a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
+      CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
+    { StageScope sc(h, STAGE_SMALL_GEMM, s);
+      CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm1.weight")), h->W(tl(l, "norm1.bias")), nullptr, S.tx, rows, H, eps, s));
+      // cross-attention block over the hoisted K|V of the image regions: x = norm2(x + out_proj(attn(q(x), K, V)))
+      CAPDEC_RETURN_IF(gemm_w(h, S.tx, H, h->W(tl(l, "multihead_attn.in_proj_weight")), H, h->W(tl(l, "multihead_attn.in_proj_bias")),
+                              S.tqc, H, rows, H, H, EPI_STORE, s)); }
+    { StageScope sc(h, STAGE_ATTENTION, s);
+      MhaArgs m{};
+      m.q = S.tqc; m.ld_q = H; m.kproj = S.tckv[l]; m.vproj = S.tckv[l] + H; m.ld_kv = 2 * H; m.mask = nullptr;
+      m.denom = (float)sqrt((double)(H / heads)); m.out = S.tca; m.ld_out = H; m.alpha = nullptr; m.ld_alpha = 0;
+      m.B = S.B; m.L = S.L; m.H = H; m.heads = heads; m.k = S.k;
+      CAPDEC_RETURN_IF(mha_attention(m, s)); }
+    { StageScope sc(h, STAGE_SMALL_GEMM, s);
+      CAPDEC_RETURN_IF(linear(h, S.tca, H, tl(l, "multihead_attn.out_proj"), S.ty, H, rows, EPI_STORE, s));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm2.weight")), h->W(tl(l, "norm2.bias")), nullptr, S.tx, rows, H, eps, s)); }
+    // feed-forward block: x = norm3(x + linear2(gelu(linear1(x))))
+    { StageScope sc(h, STAGE_GATE_GEMM, s);
+      CAPDEC_RETURN_IF(linear(h, S.tx, H, tl(l, "linear1"), S.tff, F, rows, EPI_GELU, s));
+      CAPDEC_RETURN_IF(linear(h, S.tff, F, tl(l, "linear2"), S.ty, H, rows, EPI_STORE, s));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm3.weight")), h->W(tl(l, "norm3.bias")), nullptr, S.tx, rows, H, eps, s)); }
+  }
+  StageScope sc(h, STAGE_VOCAB_GEMM, s);
+  return linear(h, S.tx, H, "output_layer", S.logits, c.vocab_size, rows, EPI_STORE, s);
+}
+
+// after position t_done: record tokens, and (beam) re-point every row's earlier cache positions at its parent's
+int commit_transformer(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
+                       int t_done, cudaStream_t s) {
+  StageScope sc(h, STAGE_GATHER, s);
+  if (tok_out && pos >= 0 && pos < S.T) {
+    GatherArgs g{};
+    g.rows = S.R; g.tok = S.next_tok; g.src = nullptr; g.embedding = nullptr; g.tok_out = tok_out; g.ld_tok = ld_tok;
+    g.pos = pos; g.n_state = 0;
+    CAPDEC_RETURN_IF(gather_rows(g, s));
+  }
+  if (src && t_done >= 0) {
+    const int nxt = S.anc_cur < 0 ? 0 : (S.anc_cur ^ 1);
+    // first reorder: the old table is the identity; build it lazily by pointing anc_old at a table never read (p == t_done only)
+    CAPDEC_REQUIRE(S.anc_cur >= 0 || t_done == 0, CAPDEC_ERR_STATE, "ancestor table must start at position 0");
+    CAPDEC_RETURN_IF(reorder_ancestors(src, S.anc_cur >= 0 ? S.anc[S.anc_cur] : S.anc[1], S.anc[nxt], S.R, S.T, t_done, s));
+    S.anc_cur = nxt;
+  }
+  return CAPDEC_OK;
+}
+
 int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
-             int64_t ld_alpha, cudaStream_t s) {
+             int64_t ld_alpha, int t, cudaStream_t s) {
+  if (is_transformer(h)) return step_transformer(h, S, t, s);
   if (is_legacy(h)) return step_legacy(h, S, feats, S.B, S.logits, h->cfg.vocab_size, alpha, ld_alpha, s);
   return step_lstm(h, S, feats, mask, alpha, ld_alpha, s);
 }
 
 // commit the step: reorder state by back-pointer, embed the chosen tokens, optionally record them
 int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
-           bool with_state, cudaStream_t s) {
+           bool with_state, cudaStream_t s, int t_done = -1) {
+  if (is_transformer(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim;
   GatherArgs g{};
@@ -397,11 +524,18 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
   return gather_rows(g, s);
 }
 
+int prologue_any(const capdec_handle* h, Session& S, const float* feats, const float* pooled, cudaStream_t s) {
+  if (is_transformer(h)) return prologue_transformer(h, S, feats, s);
+  if (is_legacy(h)) return prologue_legacy(h, S, feats, true, s);
+  return prologue_lstm(h, S, feats, pooled, s);
+}
+
 int check_common(const capdec_handle* h, const float* feats, const float* pooled, int B, int L, int k, int T) {
   CAPDEC_REQUIRE(h != nullptr, CAPDEC_ERR_INVALID, "null handle");
   CAPDEC_REQUIRE(h->finalized, CAPDEC_ERR_STATE, "capdec_finalize has not been called");
   CAPDEC_REQUIRE(B == 0 || feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
-  CAPDEC_REQUIRE(B == 0 || is_legacy(h) || pooled != nullptr, CAPDEC_ERR_INVALID, "pooled_features pointer is null");
+  CAPDEC_REQUIRE(B == 0 || h->cfg.arch != CAPDEC_ARCH_LSTM || pooled != nullptr, CAPDEC_ERR_INVALID,
+                 "pooled_features pointer is null");
   CAPDEC_REQUIRE(B >= 0 && L >= 1 && T >= 2, CAPDEC_ERR_INVALID, "bad sizes B=%d L=%d max_length=%d", B, L, T);
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "rows per image %d not in [1,%d]", k,
                  kMaxRowsPerImage);
@@ -466,19 +600,26 @@ int capdec_create(const capdec_config* cfg, capdec_handle** out) {
   cudaError_t e = cudaGetDeviceCount(&ndev);
   CAPDEC_REQUIRE(e == cudaSuccess && ndev > 0, CAPDEC_ERR_CUDA,
                  "capdec_create: no CUDA device (%s); libcapdec has no CPU fallback", cudaGetErrorString(e));
-  CAPDEC_REQUIRE(cfg->arch == CAPDEC_ARCH_LEGACY_SAT || cfg->arch == CAPDEC_ARCH_LSTM, CAPDEC_ERR_UNSUPPORTED,
-                 "unsupported decoder arch %d", cfg->arch);
+  CAPDEC_REQUIRE(cfg->arch == CAPDEC_ARCH_LEGACY_SAT || cfg->arch == CAPDEC_ARCH_LSTM ||
+                     cfg->arch == CAPDEC_ARCH_TRANSFORMER,
+                 CAPDEC_ERR_UNSUPPORTED, "unsupported decoder arch %d", cfg->arch);
   CAPDEC_REQUIRE(cfg->attention >= CAPDEC_ATT_SOFT && cfg->attention <= CAPDEC_ATT_AOA, CAPDEC_ERR_UNSUPPORTED,
                  "Unsupported attention type: %d", cfg->attention);
   CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
                  "unsupported precision %d", cfg->precision);
   CAPDEC_REQUIRE(cfg->vocab_size > 0 && cfg->hidden_dim > 0 && cfg->embed_dim > 0 && cfg->num_layers >= 1 &&
-                     cfg->num_layers <= 7,
+                     cfg->num_layers <= (cfg->arch == CAPDEC_ARCH_TRANSFORMER ? 64 : 7),
                  CAPDEC_ERR_INVALID, "bad dimensions in config");
   CAPDEC_REQUIRE(cfg->hidden_dim % 4 == 0 && cfg->embed_dim % 4 == 0 && cfg->feature_dim % 4 == 0 &&
                      cfg->attention_dim % 4 == 0,
                  CAPDEC_ERR_UNSUPPORTED, "hidden/embed/feature/attention dims must be multiples of 4");
-  if (cfg->arch == CAPDEC_ARCH_LSTM) {
+  if (cfg->arch == CAPDEC_ARCH_TRANSFORMER) {
+    CAPDEC_REQUIRE(cfg->feature_dim == cfg->hidden_dim && cfg->embed_dim == cfg->hidden_dim, CAPDEC_ERR_INVALID,
+                   "transformer arch requires feature_dim == embed_dim == hidden_dim (decoders.py:343-375)");
+    CAPDEC_REQUIRE(cfg->num_heads >= 1 && cfg->hidden_dim % cfg->num_heads == 0 && cfg->hidden_dim / cfg->num_heads <= 128 &&
+                       (cfg->hidden_dim / cfg->num_heads) % 4 == 0,
+                   CAPDEC_ERR_UNSUPPORTED, "transformer arch needs head_dim <= 128 and a multiple of 4");
+  } else if (cfg->arch == CAPDEC_ARCH_LSTM) {
     CAPDEC_REQUIRE(cfg->feature_dim == cfg->hidden_dim && cfg->attention_dim == cfg->hidden_dim, CAPDEC_ERR_INVALID,
                    "LSTM arch requires feature_dim == attention_dim == hidden_dim (attention.py:45-51)");
     CAPDEC_REQUIRE(cfg->num_heads >= 1 && cfg->hidden_dim % cfg->num_heads == 0, CAPDEC_ERR_INVALID,
@@ -535,7 +676,32 @@ int capdec_finalize(capdec_handle* h, void* stream) {
   h->owned.clear(); h->w_gates.clear(); h->b_gates.clear(); h->gate_in.clear();
   h->w_hproj = h->b_hproj = h->w_init = h->b_init = h->w_aoa = h->b_aoa = nullptr;
 
-  if (is_legacy(h)) {
+  if (is_transformer(h)) {
+    // src/models/decoders.py:343-375 (nn.TransformerDecoderLayer parameter names)
+    CAPDEC_RETURN_IF(need(h, "embedding.weight", {V, H}));
+    const DevTensor* pos = h->find("position_encoding.weight");
+    CAPDEC_REQUIRE(pos && pos->shape.size() == 2 && pos->shape[1] == H, CAPDEC_ERR_STATE, "missing parameter 'position_encoding.weight'");
+    CAPDEC_RETURN_IF(need(h, "output_layer.weight", {V, H})); CAPDEC_RETURN_IF(need(h, "output_layer.bias", {V}));
+    CAPDEC_RETURN_IF(need(h, "visual_projection.weight", {H, H})); CAPDEC_RETURN_IF(need(h, "visual_projection.bias", {H}));
+    const DevTensor* f1 = h->find(tl(0, "linear1.weight"));
+    CAPDEC_REQUIRE(f1 && f1->shape.size() == 2, CAPDEC_ERR_STATE, "missing parameter '%s'", tl(0, "linear1.weight").c_str());
+    const int64_t F = f1->shape[0];
+    for (int l = 0; l < c.num_layers; ++l) {
+      for (const char* att : {"self_attn", "multihead_attn"}) {
+        const std::string a = att;
+        CAPDEC_RETURN_IF(need(h, tl(l, (a + ".in_proj_weight").c_str()), {3 * H, H}));
+        CAPDEC_RETURN_IF(need(h, tl(l, (a + ".in_proj_bias").c_str()), {3 * H}));
+        CAPDEC_RETURN_IF(need(h, tl(l, (a + ".out_proj.weight").c_str()), {H, H}));
+        CAPDEC_RETURN_IF(need(h, tl(l, (a + ".out_proj.bias").c_str()), {H}));
+      }
+      CAPDEC_RETURN_IF(need(h, tl(l, "linear1.weight"), {F, H})); CAPDEC_RETURN_IF(need(h, tl(l, "linear1.bias"), {F}));
+      CAPDEC_RETURN_IF(need(h, tl(l, "linear2.weight"), {H, F})); CAPDEC_RETURN_IF(need(h, tl(l, "linear2.bias"), {H}));
+      for (const char* n : {"norm1", "norm2", "norm3"}) {
+        const std::string nn = n;
+        CAPDEC_RETURN_IF(need(h, tl(l, (nn + ".weight").c_str()), {H})); CAPDEC_RETURN_IF(need(h, tl(l, (nn + ".bias").c_str()), {H}));
+      }
+    }
+  } else if (is_legacy(h)) {
     // models/decoder.py:33-54
     CAPDEC_RETURN_IF(need(h, "enc_att.weight", {A, D})); CAPDEC_RETURN_IF(need(h, "enc_att.bias", {A}));
     CAPDEC_RETURN_IF(need(h, "dec_att.weight", {A, H})); CAPDEC_RETURN_IF(need(h, "dec_att.bias", {A}));
@@ -649,8 +815,7 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
   CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
-  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
-  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
   // HF: output_fill_value = pad_token_id or eos_token_id  (generation/utils.py:3187)
   const int fill = c.pad_token_id ? c.pad_token_id : c.eos_token_id;
   CAPDEC_RETURN_IF(beam_init(S.beam, B, k, T, c.bos_token_id, fill, s));
@@ -658,7 +823,7 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
   CAPDEC_RETURN_IF(commit(h, S, nullptr, nullptr, 0, -1, false, s));
   const int k2 = 2 * k;
   for (int cur_len = 1; cur_len < T; ++cur_len) {
-    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, cur_len - 1, s));
     { StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, k2, S.cand_lp, S.cand_idx, nullptr, s)); }
     // prompt length is 1 (BOS): finished score / (cur_len+1-1)^lp ; heuristic uses ((cur_len+1)-1)^lp
@@ -669,7 +834,7 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
       CAPDEC_RETURN_IF(beam_step(S.beam, B, k, T, c.vocab_size, cur_len, c.eos_token_id, div_fin, div_heur, S.cand_lp,
                                  S.cand_idx, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
                                  dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, s)); }
-    if (cur_len + 1 < T) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s));
+    if (cur_len + 1 < T) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s, cur_len - 1));
   }
   CAPDEC_RETURN_IF(beam_finalize(S.beam, (T - 1) & 1, B, k, T, out_tok, out_len, out_score, s));
   return CAPDEC_OK;
@@ -687,13 +852,15 @@ int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pool
   CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
-  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
-  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
   CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, start_token_id, s));
   CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));  // out[:,0] = start (decoders.py:271)
-  for (int t = 0; t < T; ++t) {
+  // LSTMDecoder.generate evaluates max_length steps and discards the last argmax (decoders.py:269-306);
+  // TransformerDecoder.generate runs max_length-1 steps and keeps every token (decoders.py:461-487)
+  const int n_steps = is_transformer(h) ? T - 1 : T;
+  for (int t = 0; t < n_steps; ++t) {
     float* alpha = out_alpha ? out_alpha + (size_t)t * L : nullptr;
-    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, s));
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, t, s));
     if (t + 1 == T) break;  // the last argmax is discarded (decoders.py:306 after the final store at :271)
     { StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, 1, S.cand_lp, S.next_tok, nullptr, s)); }
@@ -715,12 +882,11 @@ int capdec_decode_sample(capdec_handle* h, const float* feats, const float* pool
   CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
-  if (is_legacy(h)) CAPDEC_RETURN_IF(prologue_legacy(h, S, feats, true, s));
-  else CAPDEC_RETURN_IF(prologue_lstm(h, S, feats, pooled, s));
+  CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
   CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, c.bos_token_id, s));
   CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));
   for (int t = 0; t + 1 < T; ++t) {  // trainer.py:413
-    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, s));
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, t, s));
     { StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(sample_rows(S.logits, c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
                                    with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s)); }

@@ -63,6 +63,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_tanh_(float x) {   // transformers.activations.NewGELUActivation
+  return 0.5f * x * (1.f + tanhf(0.79788456080286535588f * (x + 0.044715f * x * x * x)));
+}
+__host__ __device__ constexpr bool epi_is_store_family(int e) { return e == 0 || e == 1 || e == 3 || e == 5 || e == 6; }
 
 // streaming 128-bit load: read-only path, do not allocate in L1 (tiles are read once per CTA)
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
@@ -78,7 +83,9 @@ enum Epilogue : int {
   EPI_SIGMOID_TAIL = 1,  // columns >= n_split get sigmoid(acc + bias)   (legacy [dec_att | f_beta] GEMM)
   EPI_LSTM = 2,          // N = 4*H gate-interleaved (n = 4*j + {i,f,g,o}); fused cell update
   EPI_TANH = 3,          // tanh(acc + bias)
-  EPI_AOA = 4            // N = 2*H interleaved (n = 2*j + {info, gate}); out = tanh(info)*sigmoid(gate)
+  EPI_AOA = 4,           // N = 2*H interleaved (n = 2*j + {info, gate}); out = tanh(info)*sigmoid(gate)
+  EPI_GELU = 5,          // exact (erf) GELU of acc + bias        (nn.TransformerDecoderLayer activation="gelu")
+  EPI_GELU_TANH = 6      // tanh-approximated GELU ("gelu_new")    (HF GPT-2 MLP)
 };
 
 struct GemmArgs {

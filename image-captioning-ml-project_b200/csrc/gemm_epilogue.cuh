@@ -9,7 +9,7 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
   // (m, n..n+3) with n % 4 == 0.  Fused epilogues require N % 4 == 0 (checked by the launcher); the plain
   // store family also handles a ragged last group and unaligned C rows (e.g. V = 50257 logits).
   if (m >= p.M || n >= p.N) return;
-  if (EPI == EPI_STORE || EPI == EPI_SIGMOID_TAIL || EPI == EPI_TANH) {
+  if (epi_is_store_family(EPI)) {
     const bool vec_ok = (n + 3 < p.N) && ((p.ldc & 3) == 0) && (!p.C2 || (p.ldc2 & 3) == 0);
     if (!vec_ok) {
       float v[4] = {v0, v1, v2, v3};
@@ -17,6 +17,8 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
         float t = v[j] + (p.bias ? p.bias[n + j] : 0.f);
         if (EPI == EPI_SIGMOID_TAIL && n + j >= p.n_split) t = sigmoidf_(t);
         if (EPI == EPI_TANH) t = tanhf(t);
+        if (EPI == EPI_GELU) t = gelu_erf_(t);
+        if (EPI == EPI_GELU_TANH) t = gelu_tanh_(t);
         p.C[(int64_t)m * p.ldc + n + j] = t;
         if (p.C2) p.C2[(int64_t)m * p.ldc2 + n + j] = t;
       }
@@ -27,11 +29,13 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
     const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
     v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
   }
-  if (EPI == EPI_STORE || EPI == EPI_SIGMOID_TAIL || EPI == EPI_TANH) {
+  if (epi_is_store_family(EPI)) {
     if (EPI == EPI_SIGMOID_TAIL && n >= p.n_split) {
       v0 = sigmoidf_(v0); v1 = sigmoidf_(v1); v2 = sigmoidf_(v2); v3 = sigmoidf_(v3);
     }
     if (EPI == EPI_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); v2 = tanhf(v2); v3 = tanhf(v3); }
+    if (EPI == EPI_GELU) { v0 = gelu_erf_(v0); v1 = gelu_erf_(v1); v2 = gelu_erf_(v2); v3 = gelu_erf_(v3); }
+    if (EPI == EPI_GELU_TANH) { v0 = gelu_tanh_(v0); v1 = gelu_tanh_(v1); v2 = gelu_tanh_(v2); v3 = gelu_tanh_(v3); }
     *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v0, v1, v2, v3);
     if (p.C2) *reinterpret_cast<float4*>(p.C2 + (int64_t)m * p.ldc2 + n) = make_float4(v0, v1, v2, v3);
   } else if (EPI == EPI_LSTM) {

@@ -104,7 +104,7 @@ int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s) {
     CAPDEC_REQUIRE(a.N % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "gemm: fused epilogue needs N %% 4 == 0 (N=%d)", a.N);
   CAPDEC_REQUIRE((((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.bias) & 15) == 0, CAPDEC_ERR_INVALID,
                  "gemm: A/W/bias must be 16-byte aligned");
-  if (epilogue == EPI_STORE || epilogue == EPI_SIGMOID_TAIL || epilogue == EPI_TANH)
+  if (epi_is_store_family(epilogue))
     CAPDEC_REQUIRE(((uintptr_t)a.C & 15) == 0 && (!a.C2 || ((uintptr_t)a.C2 & 15) == 0), CAPDEC_ERR_INVALID,
                    "gemm: C must be 16-byte aligned");
   if (epilogue == EPI_AOA)
@@ -117,6 +117,8 @@ int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s) {
     case EPI_LSTM: gemm_ffma_kernel<EPI_LSTM><<<grid, 256, 0, s>>>(a); break;
     case EPI_TANH: gemm_ffma_kernel<EPI_TANH><<<grid, 256, 0, s>>>(a); break;
     case EPI_AOA: gemm_ffma_kernel<EPI_AOA><<<grid, 256, 0, s>>>(a); break;
+    case EPI_GELU: gemm_ffma_kernel<EPI_GELU><<<grid, 256, 0, s>>>(a); break;
+    case EPI_GELU_TANH: gemm_ffma_kernel<EPI_GELU_TANH><<<grid, 256, 0, s>>>(a); break;
     default: CAPDEC_REQUIRE(false, CAPDEC_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
   }
   CAPDEC_LAUNCH_CHECK();

@@ -276,6 +276,8 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     CAPDEC_TC_CASE(EPI_LSTM)
     CAPDEC_TC_CASE(EPI_TANH)
     CAPDEC_TC_CASE(EPI_AOA)
+    CAPDEC_TC_CASE(EPI_GELU)
+    CAPDEC_TC_CASE(EPI_GELU_TANH)
     default: CAPDEC_REQUIRE(false, CAPDEC_ERR_INVALID, "gemm_tc: unknown epilogue %d", epi);
   }
 #undef CAPDEC_TC_CASE

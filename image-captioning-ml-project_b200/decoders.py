@@ -127,6 +127,88 @@ class LSTMDecoder(CaptionDecoder):
         return tok.long(), {"attention_weights": alpha}
 
 
+class TransformerDecoder(CaptionDecoder):
+    """Transformer decoder over visual features (decoders.py:317-493), decoded with a self-attention KV cache and
+    hoisted cross-attention K/V (mathematically identical to the reference's full-prefix recompute: the stack is
+    causal).  Same constructor, parameter names and `generate` contract as the reference."""
+
+    def __init__(self, config: DecoderConfig, vocab_size: int, pad_token_id: int, bos_token_id: int, eos_token_id: int,
+                 precision: str = "fp32"):
+        super().__init__()
+        self.hidden_dim = config.hidden_dim
+        self.num_layers = config.num_layers
+        self.num_heads = config.num_heads
+        self.vocab_size = vocab_size
+        self.dropout_p = config.dropout
+        self.pad_token_id, self.bos_token_id, self.eos_token_id = pad_token_id, bos_token_id, eos_token_id
+        self.precision = precision
+        self.embedding = nn.Embedding(vocab_size, self.hidden_dim, padding_idx=pad_token_id)
+        self.position_encoding = nn.Embedding(config.max_length, self.hidden_dim)
+        decoder_layer = nn.TransformerDecoderLayer(d_model=self.hidden_dim, nhead=self.num_heads,
+                                                   dim_feedforward=self.hidden_dim * 4, dropout=self.dropout_p,
+                                                   activation="gelu", batch_first=True)
+        self.transformer_decoder = nn.TransformerDecoder(decoder_layer=decoder_layer, num_layers=self.num_layers)
+        self.output_layer = nn.Linear(self.hidden_dim, vocab_size)
+        self.visual_projection = nn.Linear(self.hidden_dim, self.hidden_dim)
+        self.dropout = nn.Dropout(self.dropout_p)
+
+    def _engine(self, device) -> Engine:
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(device), self.precision)
+        if getattr(self, "_eng_sig", None) != sig:
+            H = self.hidden_dim
+            cfg = _capi.Config(arch=_capi.ARCH_TRANSFORMER, attention=_capi.ATT["multi_head"],
+                               precision=_capi.PREC[self.precision], vocab_size=self.vocab_size, hidden_dim=H,
+                               embed_dim=H, feature_dim=H, attention_dim=H, num_layers=self.num_layers,
+                               num_heads=int(self.num_heads), temperature=1.0, pad_token_id=int(self.pad_token_id),
+                               bos_token_id=int(self.bos_token_id), eos_token_id=int(self.eos_token_id))
+            object.__setattr__(self, "_eng", Engine(cfg, self.state_dict(), device))
+            object.__setattr__(self, "_eng_sig", sig)
+        return self._eng
+
+    def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
+        if captions is None:
+            return self.generate(encoder_features, 50)      # decoders.py:385-387
+        raise NotImplementedError(
+            "teacher-forced training forward is outside the accelerated decode path; for the SCST rollout "
+            "(trainer.py:383-438) call generate(..., do_sample=True)")
+
+    def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, num_beams: int = 1,
+                 do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
+                 uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
+                 **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        feats = encoder_features["features"]
+        if max_length > self.position_encoding.num_embeddings:
+            raise IndexError("max_length exceeds the position_encoding table (index out of range in self)")
+        eng = self._engine(feats.device)
+        if do_sample:
+            B = feats.shape[0]
+            k = num_samples + (1 if with_greedy else 0)
+            if uniforms is None:
+                uniforms = torch.rand(B * k, max_length - 1, device=feats.device)
+            tok, lp = eng.decode_sample(feats, None, None, num_samples, with_greedy, max_length, uniforms)
+            tok = tok.long()
+            n = _all_eos_cut(tok, self.eos_token_id)          # trainer.py:435 batch-wide break
+            return tok[:, :n], {"log_probs": lp[:, : n - 1]}
+        if num_beams > 1:
+            out = eng.decode_beam(feats, None, None, num_beams, max_length, length_penalty, trace=trace)
+            seq = out["tokens"].long()[:, : int(out["lengths"].max().item())]
+            info = {"scores": out["scores"], "lengths": out["lengths"].long()}
+            if trace:
+                info.update({k: out[k] for k in ("top_logprob", "top_token", "top_beam")})
+            return seq, info
+        tok, _ = eng.decode_greedy(feats, None, None, max_length, self.bos_token_id, want_alpha=False)
+        tok = tok.long()
+        return tok[:, : _all_eos_cut(tok, self.eos_token_id)], {}
+
+
+def _all_eos_cut(tok: torch.Tensor, eos: int) -> int:
+    """The reference stops only when EVERY row emits EOS at the same step (decoders.py:490, trainer.py:435);
+    returns the number of columns it would have produced."""
+    hit = (tok[:, 1:] == eos).all(dim=0)
+    idx = torch.nonzero(hit).flatten()
+    return int(idx[0].item()) + 2 if idx.numel() else tok.shape[1]
+
+
 def build_decoder(config: DecoderConfig, attention_config: AttentionConfig, vocab_size: int, pad_token_id: int,
                   bos_token_id: int, eos_token_id: int) -> CaptionDecoder:
     """Factory (decoders.py:659-692).  Only the LSTM family is accelerated so far; other types raise."""
@@ -134,6 +216,9 @@ def build_decoder(config: DecoderConfig, attention_config: AttentionConfig, voca
     if kind == DecoderType.LSTM.value:
         return LSTMDecoder(config=config, attention_config=attention_config, vocab_size=vocab_size,
                            pad_token_id=pad_token_id, bos_token_id=bos_token_id, eos_token_id=eos_token_id)
-    if kind in (DecoderType.TRANSFORMER.value, DecoderType.GPT2.value):
-        raise NotImplementedError(f"decoder type {kind!r} has no capdec kernels yet (SURVEY.md section 8 rows a7/a8)")
+    if kind == DecoderType.TRANSFORMER.value:
+        return TransformerDecoder(config=config, vocab_size=vocab_size, pad_token_id=pad_token_id,
+                                  bos_token_id=bos_token_id, eos_token_id=eos_token_id)
+    if kind == DecoderType.GPT2.value:
+        raise NotImplementedError(f"decoder type {kind!r} has no capdec kernels yet (SURVEY.md section 8 row a8)")
     raise ValueError(f"Unsupported decoder type: {config.decoder_type}")

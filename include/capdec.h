@@ -40,7 +40,8 @@ typedef enum {
 /* decoder family: which reference class the handle mirrors */
 typedef enum {
   CAPDEC_ARCH_LEGACY_SAT = 0,  /* models/decoder.py::Decoder (196x2048 ResNet features, LSTMCell) */
-  CAPDEC_ARCH_LSTM = 1         /* src/models/decoders.py::LSTMDecoder + src/models/attention.py */
+  CAPDEC_ARCH_LSTM = 1,        /* src/models/decoders.py::LSTMDecoder + src/models/attention.py */
+  CAPDEC_ARCH_TRANSFORMER = 2  /* src/models/decoders.py::TransformerDecoder (6x post-LN nn.TransformerDecoderLayer), KV-cached */
 } capdec_arch;
 
 /* src/config.py::AttentionType (LSTM arch only; legacy always uses its additive-ReLU attention) */

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import beam as obeam, legacy as olegacy, refshim  # noqa: E402
-from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs  # noqa: E402
+from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder  # noqa: E402
 
 
 def main():
@@ -80,6 +80,21 @@ def main():
         name = f"lstm_greedy_{kind}_h{heads}_H{H}_l{layers}_L{L}{'_ragged' if ragged else ''}.pt"
         torch.save(dict(kind=kind, heads=heads, H=H, layers=layers, L=L, vocab=V2, ragged=ragged, B=B, T=20, seed=0,
                         feat_seed=1234, ids=ids, attention_weights=info["attention_weights"]),
+                   os.path.join(GOLDEN, name))
+        print(name, ids[0].tolist()[:8])
+
+    # ---- src TransformerDecoder.generate (greedy, full-prefix recompute) from the reference module
+    for H, layers, heads, V2, L, B, T in ((128, 2, 4, 500, 49, 5, 12), (768, 6, 8, 10000, 196, 3, 20)):
+        torch.manual_seed(0)
+        dc = C.DecoderConfig(decoder_type=C.DecoderType.TRANSFORMER, hidden_dim=H, num_layers=layers, num_heads=heads,
+                             max_length=50)
+        ref = ns.decoders.TransformerDecoder(dc, vocab_size=V2, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+        _, sd3 = transformer_decoder(H=H, layers=layers, heads=heads, V=V2, seed=0)
+        assert all(torch.equal(sd3[k_], v) for k_, v in ref.state_dict().items())
+        feats, _, _ = lstm_inputs(B, L, H)
+        ids, _ = ref.generate({"features": feats}, T)
+        name = f"transformer_greedy_H{H}_l{layers}_h{heads}_L{L}.pt"
+        torch.save(dict(H=H, layers=layers, heads=heads, vocab=V2, L=L, B=B, T=T, seed=0, feat_seed=1234, ids=ids),
                    os.path.join(GOLDEN, name))
         print(name, ids[0].tolist()[:8])
 

@@ -50,3 +50,12 @@ def lstm_inputs(B, L, H, seed=1234, ragged=False):
             keep = 1 + int(torch.randint(0, L, (1,), generator=g))
             mask[b, keep:] = False
     return feats, pooled, mask
+
+
+def transformer_decoder(H=128, layers=2, heads=4, V=500, max_length=50, seed=0):
+    import capdec_b200 as cd
+    torch.manual_seed(seed)
+    dc = cd.DecoderConfig(decoder_type=cd.DecoderType.TRANSFORMER, hidden_dim=H, num_layers=layers, num_heads=heads,
+                          max_length=max_length)
+    m = cd.TransformerDecoder(dc, vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}

@@ -12,8 +12,8 @@ import torch
 import capdec_b200 as cd
 from capdec_b200 import engine as eng_mod
 from capdec_b200._capi import CapdecError
-from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, sample as osample
-from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs
+from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, sample as osample, transformer as otr
+from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
@@ -343,6 +343,53 @@ def test_lstm_sample_rollout_vs_oracle(cuda):
     tok, info = m.to(cuda).generate(ef, T, do_sample=True, num_samples=5, with_greedy=True, uniforms=u.to(cuda))
     st = olstm.LSTMStepper(sd, feats, pooled, "aoa", 1, 8, k)
     _check_sampling(st, tok.cpu(), info["log_probs"].cpu(), u, B, k, T, greedy_slot=5)
+
+
+# ------------------------------------------------------------------------------------------------ src TransformerDecoder
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "transformer_greedy_*.pt"))), ids=os.path.basename)
+def test_transformer_generate_greedy_vs_reference_golden(cuda, path, precision):
+    """TransformerDecoder.generate (src/models/decoders.py:439-493): the KV-cached CUDA decode must reproduce the
+    reference module's full-prefix-recompute tokens."""
+    gd = torch.load(path)
+    m, sd = transformer_decoder(H=gd["H"], layers=gd["layers"], heads=gd["heads"], V=gd["vocab"], seed=gd["seed"])
+    m.precision = precision
+    feats, _, _ = lstm_inputs(gd["B"], gd["L"], gd["H"], gd["feat_seed"])
+    ids, info = m.to(cuda).generate({"features": feats.to(cuda)}, gd["T"])
+    assert info == {} and ids.dtype == torch.long and ids.shape == gd["ids"].shape
+    _, margins = otr.generate_greedy(sd, feats, gd["layers"], gd["heads"], gd["T"], return_margins=True)
+    margins = torch.cat([margins[:, :1] * 0 + 1, margins], dim=1)      # align: token at column t came from step t-1
+    _assert_tokens_match(ids.cpu(), gd["ids"], margins[:, 1:], os.path.basename(path), precision)
+
+
+def test_transformer_all_eos_break_and_beam_and_sample(cuda):
+    H, layers, heads, V, L, B, T, k = 128, 2, 4, 500, 49, 6, 10, 3
+    m, sd = transformer_decoder(H=H, layers=layers, heads=heads, V=V, seed=3)
+    feats, _, _ = lstm_inputs(B, L, H, seed=33)
+    ef = {"features": feats.to(cuda)}
+    # beam search vs the oracle driver over the reference's un-cached step
+    ref = obeam.beam_search(otr.TransformerStepper(sd, feats, layers, heads, k), B, k, T, record_steps=True)
+    seq, info = m.to(cuda).generate(ef, T, num_beams=k, trace=True)
+    out = {"tokens": torch.nn.functional.pad(seq, (0, T - seq.shape[1]), value=2).int(), "scores": info["scores"],
+           "lengths": info["lengths"], "top_logprob": info["top_logprob"], "top_token": info["top_token"],
+           "top_beam": info["top_beam"]}
+
+    def rescore(s_, lengths):
+        return osample.rescore(otr.TransformerStepper(sd, feats, layers, heads, 1), s_, lengths)
+    _compare_beam(out, ref, B, k, "transformer beam", rescore=rescore, min_identical=0.0)
+    # SCST rollout: 2 samples + greedy row, uniforms shared with the oracle replay
+    u = torch.rand(B * 3, T - 1, generator=torch.Generator().manual_seed(6))
+    tok, sinfo = m.generate(ef, T, do_sample=True, num_samples=2, with_greedy=True, uniforms=u.to(cuda))
+    assert tok.shape[1] == T            # no batch-wide EOS on random weights
+    _check_sampling(otr.TransformerStepper(sd, feats, layers, heads, 3), tok.cpu(), sinfo["log_probs"].cpu(), u, B, 3, T,
+                    greedy_slot=2)
+    # batch-wide EOS break: every row emits EOS at step 0 -> the reference returns [B, 2]
+    sd2 = {k_: v.clone() for k_, v in sd.items()}
+    sd2["output_layer.bias"][2] = 50.0
+    m.load_state_dict(sd2)
+    ids, _ = m.generate(ef, T)
+    assert ids.shape == (B, 2) and ids[:, 1].eq(2).all()
+    assert torch.equal(ids.cpu(), otr.generate_greedy(sd2, feats, layers, heads, T))
 
 
 # ------------------------------------------------------------------------------------------------ properties at size

@@ -7,8 +7,8 @@ import os
 import pytest
 import torch
 
-from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, refshim, sample as osample
-from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs
+from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, refshim, sample as osample, transformer as otr
+from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
 
 needs_ref = pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present on this box")
 torch.set_grad_enabled(False)
@@ -96,6 +96,29 @@ def test_attention_restatement_matches_reference_module(kind, heads):
     assert torch.allclose(ctx, ctx2, atol=1e-6) and torch.allclose(w, w2, atol=1e-6)
 
 
+@needs_ref
+def test_transformer_restatement_matches_reference_generate():
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(5)
+    H, layers, heads, V = 64, 2, 4, 120
+    ref = ns.decoders.TransformerDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.TRANSFORMER, hidden_dim=H, num_layers=layers, num_heads=heads,
+                        max_length=50), vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    feats, _, _ = lstm_inputs(4, 19, H, seed=8)
+    ids, info = ref.generate({"features": feats}, 11)
+    assert info == {}
+    assert torch.equal(ids, otr.generate_greedy(sd, feats, layers, heads, 11))
+    # the all-rows-EOS break (decoders.py:490): bias EOS so every row emits it at once
+    sd2 = dict(sd)
+    sd2["output_layer.bias"] = sd["output_layer.bias"].clone()
+    sd2["output_layer.bias"][2] = 50.0
+    ref.load_state_dict(sd2)
+    ids, _ = ref.generate({"features": feats}, 11)
+    assert ids.shape == (4, 2) and torch.equal(ids, otr.generate_greedy(sd2, feats, layers, heads, 11))
+
+
 # ---------------------------------------------------------------- (b) against the committed goldens
 def test_golden_legacy_teacher_forced():
     gd = torch.load(os.path.join(GOLDEN, "legacy_teacher.pt"))
@@ -129,6 +152,13 @@ def test_golden_lstm_greedy(path):
                                     mask=None if mask is None else ~mask)
     assert torch.equal(ids, gd["ids"])
     assert torch.allclose(al, gd["attention_weights"], atol=1e-6)
+
+
+def test_golden_transformer_greedy():
+    gd = torch.load(os.path.join(GOLDEN, "transformer_greedy_H128_l2_h4_L49.pt"))
+    _, sd = transformer_decoder(H=gd["H"], layers=gd["layers"], heads=gd["heads"], V=gd["vocab"], seed=gd["seed"])
+    feats, _, _ = lstm_inputs(gd["B"], gd["L"], gd["H"], gd["feat_seed"])
+    assert torch.equal(otr.generate_greedy(sd, feats, gd["layers"], gd["heads"], gd["T"]), gd["ids"])
 
 
 # ---------------------------------------------------------------- (c) beam driver against transformers
