@@ -7,10 +7,10 @@ from . import _capi                                   # noqa: F401  (loads the s
 from .config import AttentionConfig, AttentionType, DecoderConfig, DecoderType, InferenceConfig, ModelConfig  # noqa: F401
 from .attention import (AttentionMechanism, AttentionOnAttention, AdaptiveAttention, MultiHeadAttention,  # noqa: F401
                         SoftAttention, build_attention)
-from .decoders import CaptionDecoder, LSTMDecoder, TransformerDecoder, build_decoder  # noqa: F401
+from .decoders import CaptionDecoder, GPT2Decoder, LSTMDecoder, TransformerDecoder, build_decoder  # noqa: F401
 from .legacy import Decoder  # noqa: F401
 from .engine import Engine, launch_count  # noqa: F401
 
 __all__ = ["AttentionConfig", "AttentionType", "DecoderConfig", "DecoderType", "InferenceConfig", "ModelConfig",
            "AttentionMechanism", "SoftAttention", "MultiHeadAttention", "AdaptiveAttention", "AttentionOnAttention",
-           "build_attention", "CaptionDecoder", "LSTMDecoder", "TransformerDecoder", "build_decoder", "Decoder", "Engine", "launch_count"]
+           "build_attention", "CaptionDecoder", "LSTMDecoder", "TransformerDecoder", "GPT2Decoder", "build_decoder", "Decoder", "Engine", "launch_count"]

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcapdec.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "capdec.h")
 
-ARCH_LEGACY_SAT, ARCH_LSTM, ARCH_TRANSFORMER = 0, 1, 2
+ARCH_LEGACY_SAT, ARCH_LSTM, ARCH_TRANSFORMER, ARCH_GPT2 = 0, 1, 2, 3
 ATT = {"soft": 0, "multi_head": 1, "adaptive": 2, "aoa": 3}
 PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "tf32": 3}
 

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(128) adaptive_mix_kernel(const float* ctx, con
 
 bool is_legacy(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_LEGACY_SAT; }
 bool is_transformer(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_TRANSFORMER; }
+bool is_gpt2(const capdec_handle* h) { return h->cfg.arch == CAPDEC_ARCH_GPT2; }
+bool is_tf_family(const capdec_handle* h) { return is_transformer(h) || is_gpt2(h); }
 bool base_is_mha(const capdec_handle* h) {
   const int a = h->cfg.attention;
   if (a == CAPDEC_ATT_MULTI_HEAD) return true;
@@ -112,6 +114,7 @@ struct Session {
   std::vector<float*> tckv, tcache_k, tcache_v;
   int32_t* anc[2] = {nullptr, nullptr};
   int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
+  float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
@@ -122,16 +125,22 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   S.B = B; S.L = L; S.k = k; S.R = B * k; S.T = T;
   const size_t R = (size_t)S.R;
   const int layers = c.num_layers;
-  if (is_transformer(h)) {
-    const DevTensor* f1 = h->find("transformer_decoder.layers.0.linear1.weight");
+  if (is_tf_family(h)) {
+    const DevTensor* f1 = h->find(is_gpt2(h) ? "model.transformer.h.0.mlp.c_fc.weight" : "transformer_decoder.layers.0.linear1.weight");
     const size_t F = f1 ? (size_t)f1->shape[0] : (size_t)4 * H;
+    if (is_gpt2(h)) {
+      const DevTensor* ip = h->find("image_to_prefix.weight");
+      S.n_prefix = ip ? (int)(ip->shape[0] / H) : 10;
+      S.txn = ar.take<float>(R * H);
+      S.gprefix = ar.take<float>((size_t)B * S.n_prefix * H);
+    }
     S.tx = ar.take<float>(R * H); S.tqkv = ar.take<float>(R * 3 * H); S.tsa = ar.take<float>(R * H);
     S.ty = ar.take<float>(R * H); S.tqc = ar.take<float>(R * H); S.tca = ar.take<float>(R * H);
     S.tff = ar.take<float>(R * F);
-    S.tmem = ar.take<float>((size_t)B * L * H);
+    if (!is_gpt2(h)) S.tmem = ar.take<float>((size_t)B * L * H);
     S.tckv.resize(layers); S.tcache_k.resize(layers); S.tcache_v.resize(layers);
     for (int l = 0; l < layers; ++l) {
-      S.tckv[l] = ar.take<float>((size_t)B * L * 2 * H);
+      if (!is_gpt2(h)) S.tckv[l] = ar.take<float>((size_t)B * L * 2 * H);
       S.tcache_k[l] = ar.take<float>(R * T * H);
       S.tcache_v[l] = ar.take<float>(R * T * H);
     }
@@ -490,9 +499,62 @@ int commit_transformer(const capdec_handle* h, Session& S, const int32_t* src, i
   return CAPDEC_OK;
 }
 
+
+// ---- GPT-2 arch (src/models/decoders.py:496-656; block math = transformers GPT2Block, pre-LN, gelu_new) -------------
+std::string gl(int l, const char* name) { return "model.transformer.h." + std::to_string(l) + "." + name; }
+
+int prologue_gpt2(const capdec_handle* h, Session& S, const float* pooled, cudaStream_t s) {
+  StageScope sc(h, STAGE_PROLOGUE, s);
+  const capdec_config& c = h->cfg;
+  // image_prefix = image_to_prefix(pooled).view(B, P, n_embd)  (decoders.py:634-637); the SAME tensor is the past
+  // key and the past value of every layer (decoders.py:608-615)
+  CAPDEC_RETURN_IF(linear(h, pooled, c.feature_dim, "image_to_prefix", S.gprefix, (int64_t)S.n_prefix * c.hidden_dim, S.B, EPI_STORE, s));
+  S.anc_cur = -1;
+  return CAPDEC_OK;
+}
+
+int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, rows = S.R, heads = c.num_heads, P = S.n_prefix;
+  const DevTensor* wpe = h->find("model.transformer.wpe.weight");
+  CAPDEC_REQUIRE(P + t < wpe->shape[0], CAPDEC_ERR_INVALID, "position %d exceeds n_positions %lld", P + t, (long long)wpe->shape[0]);
+  const int F = (int)h->find(gl(0, "mlp.c_fc.weight"))->shape[0];
+  const float eps = 1e-5f;
+  // position ids continue after the prefix: past_len + t  (HF prepare_inputs_for_generation with a cache of length P)
+  { StageScope sc(h, STAGE_GATHER, s);
+    CAPDEC_RETURN_IF(embed_pos(S.next_tok, h->W("model.transformer.wte.weight"), wpe->p + (size_t)(P + t) * H, S.tx, rows, H, s)); }
+  const float* pending = nullptr;
+  for (int l = 0; l < c.num_layers; ++l) {
+    { StageScope sc(h, STAGE_SMALL_GEMM, s);
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W(gl(l, "ln_1.weight")), h->W(gl(l, "ln_1.bias")), pending ? S.tx : nullptr, S.txn, rows, H, eps, s));
+      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "attn.c_attn"), S.tqkv, 3 * H, rows, EPI_STORE, s)); }
+    { StageScope sc(h, STAGE_ATTENTION, s);
+      SelfAttnArgs a{};
+      a.qkv = S.tqkv; a.ld_qkv = 3 * H; a.cache_k = S.tcache_k[l]; a.cache_v = S.tcache_v[l];
+      a.anc = S.anc_cur >= 0 ? S.anc[S.anc_cur] : nullptr;
+      a.prefix_k = S.gprefix; a.prefix_v = S.gprefix; a.n_prefix = P; a.rows_per_image = S.k;
+      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H;
+      a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
+      CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
+    { StageScope sc(h, STAGE_SMALL_GEMM, s);
+      CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(gl(l, "ln_2.weight")), h->W(gl(l, "ln_2.bias")), S.tx, S.txn, rows, H, eps, s)); }
+    { StageScope sc(h, STAGE_GATE_GEMM, s);
+      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "mlp.c_fc"), S.tff, F, rows, EPI_GELU_TANH, s));
+      CAPDEC_RETURN_IF(linear(h, S.tff, F, gl(l, "mlp.c_proj"), S.ty, H, rows, EPI_STORE, s)); }
+    pending = S.ty;
+  }
+  { StageScope sc(h, STAGE_SMALL_GEMM, s);
+    CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s)); }
+  StageScope sc(h, STAGE_VOCAB_GEMM, s);
+  // lm_head is tied to wte and has no bias
+  return gemm_w(h, S.txn, H, h->W("model.lm_head.weight"), H, nullptr, S.logits, c.vocab_size, rows, c.vocab_size, H, EPI_STORE, s);
+}
+
 int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
              int64_t ld_alpha, int t, cudaStream_t s) {
   if (is_transformer(h)) return step_transformer(h, S, t, s);
+  if (is_gpt2(h)) return step_gpt2(h, S, t, s);
   if (is_legacy(h)) return step_legacy(h, S, feats, S.B, S.logits, h->cfg.vocab_size, alpha, ld_alpha, s);
   return step_lstm(h, S, feats, mask, alpha, ld_alpha, s);
 }
@@ -500,7 +562,7 @@ int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8
 // commit the step: reorder state by back-pointer, embed the chosen tokens, optionally record them
 int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
            bool with_state, cudaStream_t s, int t_done = -1) {
-  if (is_transformer(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
+  if (is_tf_family(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim;
   GatherArgs g{};
@@ -526,6 +588,7 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
 
 int prologue_any(const capdec_handle* h, Session& S, const float* feats, const float* pooled, cudaStream_t s) {
   if (is_transformer(h)) return prologue_transformer(h, S, feats, s);
+  if (is_gpt2(h)) return prologue_gpt2(h, S, pooled, s);
   if (is_legacy(h)) return prologue_legacy(h, S, feats, true, s);
   return prologue_lstm(h, S, feats, pooled, s);
 }
@@ -533,8 +596,8 @@ int prologue_any(const capdec_handle* h, Session& S, const float* feats, const f
 int check_common(const capdec_handle* h, const float* feats, const float* pooled, int B, int L, int k, int T) {
   CAPDEC_REQUIRE(h != nullptr, CAPDEC_ERR_INVALID, "null handle");
   CAPDEC_REQUIRE(h->finalized, CAPDEC_ERR_STATE, "capdec_finalize has not been called");
-  CAPDEC_REQUIRE(B == 0 || feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
-  CAPDEC_REQUIRE(B == 0 || h->cfg.arch != CAPDEC_ARCH_LSTM || pooled != nullptr, CAPDEC_ERR_INVALID,
+  CAPDEC_REQUIRE(B == 0 || is_gpt2(h) || feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
+  CAPDEC_REQUIRE(B == 0 || (h->cfg.arch != CAPDEC_ARCH_LSTM && !is_gpt2(h)) || pooled != nullptr, CAPDEC_ERR_INVALID,
                  "pooled_features pointer is null");
   CAPDEC_REQUIRE(B >= 0 && L >= 1 && T >= 2, CAPDEC_ERR_INVALID, "bad sizes B=%d L=%d max_length=%d", B, L, T);
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "rows per image %d not in [1,%d]", k,
@@ -601,21 +664,21 @@ int capdec_create(const capdec_config* cfg, capdec_handle** out) {
   CAPDEC_REQUIRE(e == cudaSuccess && ndev > 0, CAPDEC_ERR_CUDA,
                  "capdec_create: no CUDA device (%s); libcapdec has no CPU fallback", cudaGetErrorString(e));
   CAPDEC_REQUIRE(cfg->arch == CAPDEC_ARCH_LEGACY_SAT || cfg->arch == CAPDEC_ARCH_LSTM ||
-                     cfg->arch == CAPDEC_ARCH_TRANSFORMER,
+                     cfg->arch == CAPDEC_ARCH_TRANSFORMER || cfg->arch == CAPDEC_ARCH_GPT2,
                  CAPDEC_ERR_UNSUPPORTED, "unsupported decoder arch %d", cfg->arch);
   CAPDEC_REQUIRE(cfg->attention >= CAPDEC_ATT_SOFT && cfg->attention <= CAPDEC_ATT_AOA, CAPDEC_ERR_UNSUPPORTED,
                  "Unsupported attention type: %d", cfg->attention);
   CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
                  "unsupported precision %d", cfg->precision);
   CAPDEC_REQUIRE(cfg->vocab_size > 0 && cfg->hidden_dim > 0 && cfg->embed_dim > 0 && cfg->num_layers >= 1 &&
-                     cfg->num_layers <= (cfg->arch == CAPDEC_ARCH_TRANSFORMER ? 64 : 7),
+                     cfg->num_layers <= (cfg->arch >= CAPDEC_ARCH_TRANSFORMER ? 64 : 7),
                  CAPDEC_ERR_INVALID, "bad dimensions in config");
   CAPDEC_REQUIRE(cfg->hidden_dim % 4 == 0 && cfg->embed_dim % 4 == 0 && cfg->feature_dim % 4 == 0 &&
                      cfg->attention_dim % 4 == 0,
                  CAPDEC_ERR_UNSUPPORTED, "hidden/embed/feature/attention dims must be multiples of 4");
-  if (cfg->arch == CAPDEC_ARCH_TRANSFORMER) {
-    CAPDEC_REQUIRE(cfg->feature_dim == cfg->hidden_dim && cfg->embed_dim == cfg->hidden_dim, CAPDEC_ERR_INVALID,
-                   "transformer arch requires feature_dim == embed_dim == hidden_dim (decoders.py:343-375)");
+  if (cfg->arch == CAPDEC_ARCH_TRANSFORMER || cfg->arch == CAPDEC_ARCH_GPT2) {
+    CAPDEC_REQUIRE(cfg->embed_dim == cfg->hidden_dim && (cfg->arch == CAPDEC_ARCH_GPT2 || cfg->feature_dim == cfg->hidden_dim),
+                   CAPDEC_ERR_INVALID, "transformer arch requires feature_dim == embed_dim == hidden_dim (decoders.py:343-375)");
     CAPDEC_REQUIRE(cfg->num_heads >= 1 && cfg->hidden_dim % cfg->num_heads == 0 && cfg->hidden_dim / cfg->num_heads <= 128 &&
                        (cfg->hidden_dim / cfg->num_heads) % 4 == 0,
                    CAPDEC_ERR_UNSUPPORTED, "transformer arch needs head_dim <= 128 and a multiple of 4");
@@ -676,7 +739,31 @@ int capdec_finalize(capdec_handle* h, void* stream) {
   h->owned.clear(); h->w_gates.clear(); h->b_gates.clear(); h->gate_in.clear();
   h->w_hproj = h->b_hproj = h->w_init = h->b_init = h->w_aoa = h->b_aoa = nullptr;
 
-  if (is_transformer(h)) {
+  if (is_gpt2(h)) {
+    // src/models/decoders.py:513-561 + transformers GPT2LMHeadModel parameter names; Conv1D weights are bound
+    // TRANSPOSED, i.e. in nn.Linear layout [out, in] (the Python binding does the transpose)
+    const int64_t Din = c.feature_dim;
+    CAPDEC_RETURN_IF(need(h, "model.transformer.wte.weight", {V, H}));
+    CAPDEC_RETURN_IF(need(h, "model.lm_head.weight", {V, H}));
+    const DevTensor* wpe = h->find("model.transformer.wpe.weight");
+    CAPDEC_REQUIRE(wpe && wpe->shape.size() == 2 && wpe->shape[1] == H, CAPDEC_ERR_STATE, "missing parameter 'model.transformer.wpe.weight'");
+    const DevTensor* ip = h->find("image_to_prefix.weight");
+    CAPDEC_REQUIRE(ip && ip->shape.size() == 2 && ip->shape[1] == Din && ip->shape[0] % H == 0, CAPDEC_ERR_STATE,
+                   "missing or mis-shaped parameter 'image_to_prefix.weight'");
+    CAPDEC_RETURN_IF(need(h, "image_to_prefix.bias", {ip->shape[0]}));
+    CAPDEC_RETURN_IF(need(h, "model.transformer.ln_f.weight", {H})); CAPDEC_RETURN_IF(need(h, "model.transformer.ln_f.bias", {H}));
+    const DevTensor* f1 = h->find(gl(0, "mlp.c_fc.weight"));
+    CAPDEC_REQUIRE(f1 && f1->shape.size() == 2, CAPDEC_ERR_STATE, "missing parameter '%s'", gl(0, "mlp.c_fc.weight").c_str());
+    const int64_t F = f1->shape[0];
+    for (int l = 0; l < c.num_layers; ++l) {
+      CAPDEC_RETURN_IF(need(h, gl(l, "ln_1.weight"), {H})); CAPDEC_RETURN_IF(need(h, gl(l, "ln_1.bias"), {H}));
+      CAPDEC_RETURN_IF(need(h, gl(l, "ln_2.weight"), {H})); CAPDEC_RETURN_IF(need(h, gl(l, "ln_2.bias"), {H}));
+      CAPDEC_RETURN_IF(need(h, gl(l, "attn.c_attn.weight"), {3 * H, H})); CAPDEC_RETURN_IF(need(h, gl(l, "attn.c_attn.bias"), {3 * H}));
+      CAPDEC_RETURN_IF(need(h, gl(l, "attn.c_proj.weight"), {H, H})); CAPDEC_RETURN_IF(need(h, gl(l, "attn.c_proj.bias"), {H}));
+      CAPDEC_RETURN_IF(need(h, gl(l, "mlp.c_fc.weight"), {F, H})); CAPDEC_RETURN_IF(need(h, gl(l, "mlp.c_fc.bias"), {F}));
+      CAPDEC_RETURN_IF(need(h, gl(l, "mlp.c_proj.weight"), {H, F})); CAPDEC_RETURN_IF(need(h, gl(l, "mlp.c_proj.bias"), {H}));
+    }
+  } else if (is_transformer(h)) {
     // src/models/decoders.py:343-375 (nn.TransformerDecoderLayer parameter names)
     CAPDEC_RETURN_IF(need(h, "embedding.weight", {V, H}));
     const DevTensor* pos = h->find("position_encoding.weight");
@@ -857,7 +944,7 @@ int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pool
   CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));  // out[:,0] = start (decoders.py:271)
   // LSTMDecoder.generate evaluates max_length steps and discards the last argmax (decoders.py:269-306);
   // TransformerDecoder.generate runs max_length-1 steps and keeps every token (decoders.py:461-487)
-  const int n_steps = is_transformer(h) ? T - 1 : T;
+  const int n_steps = is_tf_family(h) ? T - 1 : T;
   for (int t = 0; t < n_steps; ++t) {
     float* alpha = out_alpha ? out_alpha + (size_t)t * L : nullptr;
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, t, s));

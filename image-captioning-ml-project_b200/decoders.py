@@ -201,6 +201,104 @@ class TransformerDecoder(CaptionDecoder):
         return tok[:, : _all_eos_cut(tok, self.eos_token_id)], {}
 
 
+class GPT2Decoder(CaptionDecoder):
+    """GPT-2 decoder conditioned on a 10-token image prefix (decoders.py:496-656).
+
+    Same constructor, attributes and parameter names as the reference (`self.model` IS a transformers
+    GPT2LMHeadModel, so a reference state_dict loads unchanged); `generate(encoder_features, max_length,
+    num_beams=4)` returns HF-style beam-search sequences.  As shipped the reference passes a list of
+    [B,prefix,hidden] tensors as past_key_values, which no transformers version accepts; this
+    drop-in implements the intended computation pinned in SURVEY section 8(c): the prefix, split into heads, is the past
+    key AND value of every layer, positions continue after the prefix, HF beam search with its defaults."""
+
+    def __init__(self, config: DecoderConfig, vocab_size: int = None, pad_token_id: int = None, bos_token_id: int = None,
+                 eos_token_id: int = None, precision: str = "fp32"):
+        super().__init__()
+        from transformers import GPT2Config, GPT2LMHeadModel
+        if config.pretrained_model_name:
+            self.model = GPT2LMHeadModel.from_pretrained(config.pretrained_model_name)
+            if vocab_size and vocab_size != self.model.config.vocab_size:
+                self.model.resize_token_embeddings(vocab_size)
+        else:
+            self.model = GPT2LMHeadModel(GPT2Config(
+                vocab_size=vocab_size, n_positions=config.max_length, n_ctx=config.max_length, n_embd=config.hidden_dim,
+                n_layer=config.num_layers, n_head=config.num_heads, resid_pdrop=config.dropout,
+                embd_pdrop=config.dropout, attn_pdrop=config.dropout))
+        self.pad_token_id = pad_token_id or 0
+        self.bos_token_id = bos_token_id or 1
+        self.eos_token_id = eos_token_id or 2
+        self.precision = precision
+        self.visual_projection = nn.Linear(config.hidden_dim, self.model.config.n_embd)
+        self.prefix_length = 10
+        self.image_prefix = nn.Parameter(torch.randn(1, self.prefix_length, self.model.config.n_embd))
+        self.image_to_prefix = nn.Linear(config.hidden_dim, self.prefix_length * self.model.config.n_embd)
+        self._feature_dim = config.hidden_dim
+
+    def _engine(self, device) -> Engine:
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(device), self.precision)
+        if getattr(self, "_eng_sig", None) != sig:
+            gc = self.model.config
+            cfg = _capi.Config(arch=_capi.ARCH_GPT2, attention=_capi.ATT["multi_head"], precision=_capi.PREC[self.precision],
+                               vocab_size=gc.vocab_size, hidden_dim=gc.n_embd, embed_dim=gc.n_embd,
+                               feature_dim=self._feature_dim, attention_dim=gc.n_embd, num_layers=gc.n_layer,
+                               num_heads=gc.n_head, temperature=1.0, pad_token_id=int(self.pad_token_id),
+                               bos_token_id=int(self.bos_token_id), eos_token_id=int(self.eos_token_id))
+            sd = {}
+            for name, t in self.state_dict().items():
+                if name.startswith("model.transformer.h.") and name.endswith(
+                        ("attn.c_attn.weight", "attn.c_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")):
+                    t = t.t()                       # HF Conv1D stores [in, out]; libcapdec takes nn.Linear layout
+                if name.endswith((".attn.bias", ".attn.masked_bias")) or name in ("image_prefix",) or name.startswith("visual_projection"):
+                    continue                        # causal-mask buffers / parameters generate() never reads
+                sd[name] = t
+            object.__setattr__(self, "_eng", Engine(cfg, sd, device))
+            object.__setattr__(self, "_eng_sig", sig)
+        return self._eng
+
+    def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
+        if captions is None:
+            return self.generate(encoder_features, 50)      # decoders.py:572-574
+        raise NotImplementedError(
+            "teacher-forced training forward is outside the accelerated decode path; for the SCST rollout "
+            "(trainer.py:383-438) call generate(..., do_sample=True)")
+
+    def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, num_beams: int = 4,
+                 do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
+                 uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
+                 **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        pooled = encoder_features["pooled_features"]
+        B = pooled.shape[0]
+        if self.prefix_length + max_length > self.model.config.n_positions:
+            raise IndexError("prefix + max_length exceeds GPT-2 n_positions (index out of range in self)")
+        eng = self._engine(pooled.device)
+        dummy = torch.empty(B, 1, 4, device=pooled.device)          # region features are not used by this decoder
+        if do_sample:
+            k = num_samples + (1 if with_greedy else 0)
+            if uniforms is None:
+                uniforms = torch.rand(B * k, max_length - 1, device=pooled.device)
+            tok, lp = eng.decode_sample(dummy, pooled, None, num_samples, with_greedy, max_length, uniforms)
+            tok = tok.long()
+            n = _all_eos_cut(tok, self.eos_token_id)
+            return tok[:, :n], {"log_probs": lp[:, : n - 1]}
+        if num_beams > 1:
+            out = eng.decode_beam(dummy, pooled, None, num_beams, max_length, length_penalty, trace=trace)
+            seq = out["tokens"].long()[:, : int(out["lengths"].max().item())]
+            info = {"scores": out["scores"], "lengths": out["lengths"].long()} if trace or kwargs.get("return_scores") else {}
+            if trace:
+                info.update({k: out[k] for k in ("top_logprob", "top_token", "top_beam")})
+            return seq, info
+        # num_beams == 1: HF greedy search -- rows stop at their own EOS and are padded, the loop ends when all did
+        tok, _ = eng.decode_greedy(dummy, pooled, None, max_length, self.bos_token_id, want_alpha=False)
+        tok = tok.long()
+        done = (tok[:, 1:] == self.eos_token_id).cumsum(dim=1) > 0
+        after = torch.cat([torch.zeros_like(done[:, :1]), done[:, :-1]], dim=1)      # strictly after the first EOS
+        tok[:, 1:][after] = self.pad_token_id
+        all_done = done.all(dim=0)
+        idx = torch.nonzero(all_done).flatten()
+        n = int(idx[0].item()) + 2 if idx.numel() else tok.shape[1]
+        return tok[:, :n], {}
+
+
 def _all_eos_cut(tok: torch.Tensor, eos: int) -> int:
     """The reference stops only when EVERY row emits EOS at the same step (decoders.py:490, trainer.py:435);
     returns the number of columns it would have produced."""
@@ -220,5 +318,6 @@ def build_decoder(config: DecoderConfig, attention_config: AttentionConfig, voca
         return TransformerDecoder(config=config, vocab_size=vocab_size, pad_token_id=pad_token_id,
                                   bos_token_id=bos_token_id, eos_token_id=eos_token_id)
     if kind == DecoderType.GPT2.value:
-        raise NotImplementedError(f"decoder type {kind!r} has no capdec kernels yet (SURVEY.md section 8 row a8)")
+        return GPT2Decoder(config=config, vocab_size=vocab_size, pad_token_id=pad_token_id, bos_token_id=bos_token_id,
+                           eos_token_id=eos_token_id)
     raise ValueError(f"Unsupported decoder type: {config.decoder_type}")

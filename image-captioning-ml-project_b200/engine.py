@@ -27,6 +27,7 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+
 class Engine:
     """One capdec_handle bound to a module's parameters on one CUDA device."""
 

@@ -41,7 +41,10 @@ typedef enum {
 typedef enum {
   CAPDEC_ARCH_LEGACY_SAT = 0,  /* models/decoder.py::Decoder (196x2048 ResNet features, LSTMCell) */
   CAPDEC_ARCH_LSTM = 1,        /* src/models/decoders.py::LSTMDecoder + src/models/attention.py */
-  CAPDEC_ARCH_TRANSFORMER = 2  /* src/models/decoders.py::TransformerDecoder (6x post-LN nn.TransformerDecoderLayer), KV-cached */
+  CAPDEC_ARCH_TRANSFORMER = 2, /* src/models/decoders.py::TransformerDecoder (6x post-LN nn.TransformerDecoderLayer), KV-cached */
+  CAPDEC_ARCH_GPT2 = 3         /* src/models/decoders.py::GPT2Decoder: HF GPT-2 blocks (pre-LN, gelu_new, tied lm_head) over a
+                                  10-token image prefix used as past K == V of every layer; feature_dim = pooled feature width;
+                                  Conv1D weights are bound transposed ([out,in]) */
 } capdec_arch;
 
 /* src/config.py::AttentionType (LSTM arch only; legacy always uses its additive-ReLU attention) */

@@ -59,3 +59,13 @@ def transformer_decoder(H=128, layers=2, heads=4, V=500, max_length=50, seed=0):
                           max_length=max_length)
     m = cd.TransformerDecoder(dc, vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
     return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def gpt2_decoder(H=64, layers=2, heads=4, V=300, max_length=64, seed=0, feature_dim=None):
+    """GPT2Decoder drop-in with a random-init GPT2LMHeadModel (no pretrained weights offline)."""
+    import capdec_b200 as cd
+    torch.manual_seed(seed)
+    dc = cd.DecoderConfig(decoder_type=cd.DecoderType.GPT2, pretrained_model_name="", hidden_dim=H, num_layers=layers,
+                          num_heads=heads, dropout=0.0, max_length=max_length)
+    m = cd.GPT2Decoder(dc, vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}

@@ -12,8 +12,8 @@ import torch
 import capdec_b200 as cd
 from capdec_b200 import engine as eng_mod
 from capdec_b200._capi import CapdecError
-from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, sample as osample, transformer as otr
-from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
+from oracle import attention as oatt, beam as obeam, gpt2 as ogpt, legacy as olegacy, lstm as olstm, sample as osample, transformer as otr
+from tests.helpers import GOLDEN, gpt2_decoder, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
@@ -390,6 +390,59 @@ def test_transformer_all_eos_break_and_beam_and_sample(cuda):
     ids, _ = m.generate(ef, T)
     assert ids.shape == (B, 2) and ids[:, 1].eq(2).all()
     assert torch.equal(ids.cpu(), otr.generate_greedy(sd2, feats, layers, heads, T))
+
+
+# ------------------------------------------------------------------------------------------------ src GPT2Decoder
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_gpt2_beam_and_sample_vs_hf(cuda, precision):
+    """GPT2Decoder.generate (src/models/decoders.py:619-656) against transformers itself on the CPU: default
+    num_beams=4, the 10-token image prefix as past K == V of every layer, per-step candidates via the oracle driver."""
+    H, layers, heads, V, B, T, k = 64, 2, 4, 300, 6, 12, 4
+    m, sd = gpt2_decoder(H=H, layers=layers, heads=heads, V=V)
+    m.precision = precision
+    hf = m.model                                    # CPU copy used by the oracle before the module moves to the GPU
+    import copy
+    hf = copy.deepcopy(hf)
+    pooled = torch.randn(B, H, generator=torch.Generator().manual_seed(9))
+    seq_hf, sc_hf = ogpt.hf_generate(hf, sd, pooled, k, T)
+    ref = obeam.beam_search(ogpt.HFStepper(hf, sd, pooled, k), B, k, T, record_steps=True)
+    assert torch.equal(seq_hf, obeam.crop_like_hf(ref["sequences"], ref["lengths"]))
+    mg = m.to(cuda)
+    seq, info = mg.generate({"pooled_features": pooled.to(cuda)}, T, trace=True)       # num_beams defaults to 4
+    out = {"tokens": torch.nn.functional.pad(seq, (0, T - seq.shape[1]), value=2).int(), "scores": info["scores"],
+           "lengths": info["lengths"], "top_logprob": info["top_logprob"], "top_token": info["top_token"],
+           "top_beam": info["top_beam"]}
+
+    def rescore(s_, lengths):
+        return osample.rescore(ogpt.HFStepper(hf, sd, pooled, 1), s_, lengths)
+    _compare_beam(out, ref, B, k, f"gpt2 beam {precision}", rescore=rescore, min_identical=0.0)
+    seq2, info2 = mg.generate({"pooled_features": pooled.to(cuda)}, T)
+    assert info2 == {} and torch.equal(seq2, seq)
+    if precision == "fp32":
+        # SCST rollout, config 5 shape: 5 samples + 1 greedy row per image
+        u = torch.rand(B * 6, T - 1, generator=torch.Generator().manual_seed(10))
+        tok, sinfo = mg.generate({"pooled_features": pooled.to(cuda)}, T, do_sample=True, num_samples=5, with_greedy=True,
+                                 uniforms=u.to(cuda))
+        _check_sampling(ogpt.HFStepper(hf, sd, pooled, 6), tok.cpu(), sinfo["log_probs"].cpu()[:, : tok.shape[1] - 1], u, B, 6,
+                        tok.shape[1], greedy_slot=5)
+
+
+def test_gpt2_124m_config4_vs_hf(cuda):
+    """BASELINE config 4 shape: GPT-2 124M (12 layers, 12 heads, 768, vocab 50257), beam 5, max_len 20, random init."""
+    B, T, k = 4, 20, 5
+    m, sd = gpt2_decoder(H=768, layers=12, heads=12, V=50257, max_length=64)
+    import copy
+    hf = copy.deepcopy(m.model)
+    pooled = torch.randn(B, 768, generator=torch.Generator().manual_seed(11))
+    ref = obeam.beam_search(ogpt.HFStepper(hf, sd, pooled, k), B, k, T, record_steps=True)
+    seq, info = m.to(cuda).generate({"pooled_features": pooled.to(cuda)}, T, num_beams=k, trace=True)
+    out = {"tokens": torch.nn.functional.pad(seq, (0, T - seq.shape[1]), value=2).int(), "scores": info["scores"],
+           "lengths": info["lengths"], "top_logprob": info["top_logprob"], "top_token": info["top_token"],
+           "top_beam": info["top_beam"]}
+
+    def rescore(s_, lengths):
+        return osample.rescore(ogpt.HFStepper(hf, sd, pooled, 1), s_, lengths)
+    _compare_beam(out, ref, B, k, "gpt2-124M beam5", rescore=rescore, min_identical=0.0)
 
 
 # ------------------------------------------------------------------------------------------------ properties at size

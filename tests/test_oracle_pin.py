@@ -7,8 +7,8 @@ import os
 import pytest
 import torch
 
-from oracle import attention as oatt, beam as obeam, legacy as olegacy, lstm as olstm, refshim, sample as osample, transformer as otr
-from tests.helpers import GOLDEN, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
+from oracle import attention as oatt, beam as obeam, gpt2 as ogpt, legacy as olegacy, lstm as olstm, refshim, sample as osample, transformer as otr
+from tests.helpers import GOLDEN, gpt2_decoder, legacy_features, legacy_weights, lstm_decoder, lstm_inputs, transformer_decoder
 
 needs_ref = pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not present on this box")
 torch.set_grad_enabled(False)
@@ -213,6 +213,32 @@ def test_beam_driver_matches_hf(k, scale, eos_bias, lp):
     seq = obeam.crop_like_hf(seq, out["lengths"])
     assert hf.sequences.shape == seq.shape and torch.equal(hf.sequences, seq)
     assert torch.allclose(hf.sequences_scores, out["scores"], atol=1e-5)
+
+
+@needs_ref
+def test_gpt2_dropin_init_equals_reference_init():
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(0)
+    ref = ns.decoders.GPT2Decoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.GPT2, pretrained_model_name="", hidden_dim=64, num_layers=2,
+                        num_heads=4, dropout=0.0, max_length=64), vocab_size=300, pad_token_id=0, bos_token_id=1,
+        eos_token_id=2)
+    _, sd = gpt2_decoder()
+    assert set(sd) == set(ref.state_dict())
+    assert all(torch.equal(sd[k], v) for k, v in ref.state_dict().items())
+
+
+@pytest.mark.parametrize("k,lp", [(4, 1.0), (5, 0.8)])
+def test_gpt2_oracle_stepper_matches_hf_generate(k, lp):
+    """a8: the pinned beam driver over an HF GPT-2 stepper with the image prefix as past K == V reproduces
+    transformers' own generate() for the computation GPT2Decoder.generate intends (decoders.py:619-656)."""
+    m, sd = gpt2_decoder()
+    pooled = torch.randn(3, 64, generator=torch.Generator().manual_seed(5))
+    seq, sc = ogpt.hf_generate(m.model, sd, pooled, k, 12, length_penalty=lp)
+    out = obeam.beam_search(ogpt.HFStepper(m.model, sd, pooled, k), 3, k, 12, length_penalty=lp)
+    assert torch.equal(seq, obeam.crop_like_hf(out["sequences"], out["lengths"]))
+    assert torch.allclose(sc, out["scores"], atol=1e-5)
 
 
 def test_sample_rollout_inverse_cdf():
