@@ -81,6 +81,9 @@ struct SmemLayout {
   static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
 };
 
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
+// so the CTAs running concurrently share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x BN columns)
+// so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1; the shared-memory ring runs across tiles.
 template <int BN, int EPI, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -91,22 +94,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = n_tiles * ((p.M + BM - 1) / BM);
   const int num_kb = (p.K + BK - 1) / BK;
+  constexpr uint32_t kTmemCols = 2 * BN;           // 256 or 512: a power of two >= 32
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    if (TERMS == 3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -117,17 +127,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * SL::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes);
-        tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m_tile * BM);
-        tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, n_tile * BN);
-        if (TERMS == 3) {
-          tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, m_tile * BM);
-          tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, n_tile * BN);
+      uint32_t it = 0;  // global k-block counter across tiles -> ring stage / phase
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * SL::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes);
+          tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m_tile * BM);
+          tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, n_tile * BN);
+          if (TERMS == 3) {
+            tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, m_tile * BM);
+            tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, n_tile * BN);
+          }
         }
       }
     }
@@ -135,64 +149,84 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t ab = local & 1;                       // accumulator buffer
+        mbar_wait(&tmem_empty_bar[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         tcgen05_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * SL::kStageBytes);
-        const uint32_t a_lo = a_hi + SL::kABytes;
-        const uint32_t w_hi = a_hi + 2 * SL::kABytes;
-        const uint32_t w_lo = w_hi + SL::kWBytes;
+        const uint32_t tmem_d = tmem_base + ab * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * SL::kStageBytes);
+          const uint32_t a_lo = a_hi + SL::kABytes;
+          const uint32_t w_hi = a_hi + 2 * SL::kABytes;
+          const uint32_t w_lo = w_hi + SL::kWBytes;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span
-          const uint32_t first = (kb | k) == 0 ? 0u : 1u;
-          if (TERMS == 3) {
-            mma_tf32(tmem_base, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), idesc, first);
-            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), idesc, 1u);
-            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, 1u);
-          } else {
-            mma_tf32(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, first);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span
+            const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+            if (TERMS == 3) {
+              mma_tf32(tmem_d, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), idesc, first);
+              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), idesc, 1u);
+              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, 1u);
+            } else {
+              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, first);
+            }
           }
+          tcgen05_commit(&empty_bar[s]);                           // frees this shared-memory stage when the MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[ab]);  // accumulator complete
         }
-        tcgen05_commit(&empty_bar[s]);                      // frees this shared-memory stage when the MMAs retire
-        if (kb == num_kb - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
       }
     }
     __syncwarp();
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int m = m_tile * BM + q * 32 + lane;   // accumulator row == TMEM lane
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      const uint32_t ab = local & 1;
+      mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
+      tcgen05_fence_after();
+      const int m = m_tile * BM + q * 32 + lane;   // accumulator row == TMEM lane
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int n0 = n_tile * BN + c0;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= BN) {
+          // every accumulator column of this tile is now in registers: hand the TMEM buffer back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
+        }
+        const int n0 = n_tile * BN + c0;
+        if (n0 < p.N) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                       __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                           __uint_as_float(v[j + 3]));
+        }
+      }
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -258,11 +292,23 @@ int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int6
   return CAPDEC_OK;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int TERMS>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
               const GemmArgs& g, int epi, cudaStream_t s) {
   constexpr int smem = SmemLayout<BN>::kTotal;
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+  const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM);
+  dim3 grid(num_tiles < num_sms() ? num_tiles : num_sms());
 #define CAPDEC_TC_CASE(E)                                                                                         \
   case E: {                                                                                                       \
     auto kern = gemm_tcgen05_kernel<BN, E, TERMS>;                                                                \
