@@ -71,6 +71,9 @@ def _load() -> C.CDLL:
     lib.capdec_stage_times.argtypes = [p, C.POINTER(f32), C.POINTER(i32)]
     lib.capdec_linear.argtypes = [i32, p, i64, p, i64, p, p, i64, i32, i32, i32, p]
     lib.capdec_lse_topk.argtypes = [p, i64, i32, i32, i32, p, p, p, p]
+    lib.capdec_linear_topk_workspace.argtypes = [i32, i32, i32]
+    lib.capdec_linear_topk_workspace.restype = sz
+    lib.capdec_linear_topk.argtypes = [i32, p, i64, p, i64, p, i32, i32, i32, i32, p, p, p, p, sz, p]
     return lib
 
 

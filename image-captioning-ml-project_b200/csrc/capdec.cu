@@ -7,6 +7,7 @@
 // hoisted into a per-call prologue; the reference recomputes them every step (models/decoder.py:152,
 // src/models/attention.py:77,172-174).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "handle.cuh"
@@ -115,6 +116,8 @@ struct Session {
   int32_t* anc[2] = {nullptr, nullptr};
   int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
+  // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
+  float* tk_part = nullptr; int fuse_k = 0;
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
@@ -125,6 +128,16 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   S.B = B; S.L = L; S.k = k; S.R = B * k; S.T = T;
   const size_t R = (size_t)S.R;
   const int layers = c.num_layers;
+  // beam / greedy on the tensor-core path: the vocabulary GEMM's epilogue keeps only per-tile log-sum-exp partials
+  // and top-k candidates, so no [R,V] logits buffer exists (sampling and the teacher-forced forward need full rows)
+  const int want_k = mode == MODE_BEAM ? 2 * k : mode == MODE_GREEDY ? 1 : 0;
+  S.fuse_k = 0;
+  if (want_k > 0 && c.precision != CAPDEC_PREC_FP32 && tk_supported(V, want_k) && !getenv("CAPDEC_NO_FUSED_TOPK"))
+    S.fuse_k = want_k;
+  auto take_logits = [&]() {
+    if (S.fuse_k > 0) S.tk_part = ar.take<float>(R * tk_tiles(V) * tk_stride(S.fuse_k));
+    else S.logits = ar.take<float>(R * V);
+  };
   if (is_tf_family(h)) {
     const DevTensor* f1 = h->find(is_gpt2(h) ? "model.transformer.h.0.mlp.c_fc.weight" : "transformer_decoder.layers.0.linear1.weight");
     const size_t F = f1 ? (size_t)f1->shape[0] : (size_t)4 * H;
@@ -145,7 +158,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.tcache_v[l] = ar.take<float>(R * T * H);
     }
     S.anc[0] = ar.take<int32_t>(R * T); S.anc[1] = ar.take<int32_t>(R * T);
-    S.logits = ar.take<float>(R * V);
+    take_logits();
     S.next_tok = ar.take<int32_t>(R); S.src_row = ar.take<int32_t>(R); S.step_lp = ar.take<float>(R);
     S.cand_lp = ar.take<float>(R * 2 * k); S.cand_idx = ar.take<int32_t>(R * 2 * k);
     if (mode == MODE_BEAM) {
@@ -165,7 +178,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.cnew[l] = ar.take<float>(R * H);
       S.hnew[l] = ar.take<float>(R * (c.attention == CAPDEC_ATT_ADAPTIVE && l == layers - 1 && !is_legacy(h) ? 2 * H : H));
     }
-    if (mode != MODE_TEACHER) S.logits = ar.take<float>(R * V);
+    if (mode != MODE_TEACHER) take_logits();
     S.next_tok = ar.take<int32_t>(R);
     S.src_row = ar.take<int32_t>(R);
     S.step_lp = ar.take<float>(R);
@@ -222,6 +235,29 @@ int linear(const capdec_handle* h, const float* A, int64_t lda, const std::strin
   g.A = A; g.lda = lda; g.W = w->p; g.ldw = w->shape[1]; g.bias = b ? b->p : nullptr;
   g.C = C; g.ldc = ldc; g.M = M; g.N = (int)w->shape[0]; g.K = (int)w->shape[1]; g.C2 = C2; g.ldc2 = ldc2;
   return gemm(h, h->cfg.precision, g, epi, s);
+}
+
+// vocabulary projection: logits [rows,V] into `logits`, or (logits == nullptr, beam/greedy on the tensor-core path) the
+// fused EPI_TOPK partial records into S.tk_part
+int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t lda, const float* W, const float* bias,
+                  int rows, float* logits, int64_t ld_logits, cudaStream_t s) {
+  const capdec_config& c = h->cfg;
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = c.hidden_dim; g.bias = bias; g.M = rows; g.N = c.vocab_size; g.K = c.hidden_dim;
+  if (logits == nullptr) {
+    CAPDEC_REQUIRE(S.fuse_k > 0 && S.tk_part, CAPDEC_ERR_STATE, "vocab_project: no logits buffer and no fused top-k buffer");
+    g.tk_part = S.tk_part; g.tk_k = S.fuse_k;
+    return gemm(h, c.precision, g, EPI_TOPK, s);
+  }
+  g.C = logits; g.ldc = ld_logits;
+  return gemm(h, c.precision, g, EPI_STORE, s);
+}
+
+// per-row sorted top-`topk` log-probs of the step's vocabulary distribution
+int select_topk(const capdec_handle* h, Session& S, int topk, float* out_lp, int32_t* out_idx, cudaStream_t s) {
+  const int V = h->cfg.vocab_size;
+  if (S.fuse_k > 0) return topk_merge(S.tk_part, S.R, V, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
+  return lse_topk(S.logits, V, S.R, V, topk, out_lp, out_idx, nullptr, s);
 }
 
 int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool expand, cudaStream_t s) {
@@ -363,7 +399,8 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   l.c_in = S.c[0]; l.ldcin = H; l.c_out = S.cnew[0]; l.ldcout = H;
   { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, l, EPI_LSTM, s)); }
   // fc(h)  (:171; dropout is the identity in eval)
-  { StageScope sc(h, STAGE_VOCAB_GEMM, s); CAPDEC_RETURN_IF(linear(h, S.hnew[0], H, "fc", logits, ld_logits, rows, EPI_STORE, s)); }
+  { StageScope sc(h, STAGE_VOCAB_GEMM, s);
+    CAPDEC_RETURN_IF(vocab_project(h, S, S.hnew[0], H, h->W("fc.weight"), h->W("fc.bias"), rows, logits, ld_logits, s)); }
   (void)V;
   return CAPDEC_OK;
 }
@@ -402,7 +439,8 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
   }
   // logits = output_layer(context)  (decoders.py:303)
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
-  CAPDEC_RETURN_IF(linear(h, S.ctx, H, "output_layer", S.logits, c.vocab_size, rows, EPI_STORE, s));
+  CAPDEC_RETURN_IF(vocab_project(h, S, S.ctx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits,
+                                 c.vocab_size, s));
   return CAPDEC_OK;
 }
 
@@ -476,7 +514,7 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
       CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm3.weight")), h->W(tl(l, "norm3.bias")), nullptr, S.tx, rows, H, eps, s)); }
   }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
-  return linear(h, S.tx, H, "output_layer", S.logits, c.vocab_size, rows, EPI_STORE, s);
+  return vocab_project(h, S, S.tx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits, c.vocab_size, s);
 }
 
 // after position t_done: record tokens, and (beam) re-point every row's earlier cache positions at its parent's
@@ -548,7 +586,7 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
     CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s)); }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   // lm_head is tied to wte and has no bias
-  return gemm_w(h, S.txn, H, h->W("model.lm_head.weight"), H, nullptr, S.logits, c.vocab_size, rows, c.vocab_size, H, EPI_STORE, s);
+  return vocab_project(h, S, S.txn, H, h->W("model.lm_head.weight"), nullptr, rows, S.logits, c.vocab_size, s);
 }
 
 int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
@@ -878,14 +916,14 @@ int capdec_finalize(capdec_handle* h, void* stream) {
 
 size_t capdec_workspace_bytes(const capdec_handle* h, int32_t B, int32_t L, int32_t k, int32_t T) {
   if (!h) return 0;
-  Arena ar(nullptr, 0);
-  Session S;
-  carve(h, ar, S, B, L, k, T, MODE_BEAM);
-  size_t beam = ar.off;
-  Arena ar2(nullptr, 0);
-  Session S2;
-  carve(h, ar2, S2, B, L, k, T, MODE_TEACHER);
-  return align_up((beam > ar2.off ? beam : ar2.off) + 4096, 4096);
+  size_t need = 0;
+  for (Mode m : {MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER}) {   // one workspace serves every entry point
+    Arena ar(nullptr, 0);
+    Session S;
+    carve(h, ar, S, B, L, k, T, m);
+    need = ar.off > need ? ar.off : need;
+  }
+  return align_up(need + 4096, 4096);
 }
 
 int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
@@ -912,7 +950,7 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
   for (int cur_len = 1; cur_len < T; ++cur_len) {
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, cur_len - 1, s));
     { StageScope sc(h, STAGE_SELECT, s);
-      CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, k2, S.cand_lp, S.cand_idx, nullptr, s)); }
+      CAPDEC_RETURN_IF(select_topk(h, S, k2, S.cand_lp, S.cand_idx, s)); }
     // prompt length is 1 (BOS): finished score / (cur_len+1-1)^lp ; heuristic uses ((cur_len+1)-1)^lp
     const float div_fin = (float)pow((double)cur_len, (double)length_penalty);
     const float div_heur = div_fin;
@@ -950,7 +988,7 @@ int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pool
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha, (int64_t)T * L, t, s));
     if (t + 1 == T) break;  // the last argmax is discarded (decoders.py:306 after the final store at :271)
     { StageScope sc(h, STAGE_SELECT, s);
-      CAPDEC_RETURN_IF(lse_topk(S.logits, c.vocab_size, S.R, c.vocab_size, 1, S.cand_lp, S.next_tok, nullptr, s)); }
+      CAPDEC_RETURN_IF(select_topk(h, S, 1, S.cand_lp, S.next_tok, s)); }
     CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, t + 1, true, s));
   }
   return CAPDEC_OK;
@@ -1133,6 +1171,26 @@ int capdec_linear(int32_t precision, const float* a, int64_t lda, const float* w
   GemmArgs g{};
   g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.C = c; g.ldc = ldc; g.M = m; g.N = n; g.K = k;
   return gemm(nullptr, precision, g, EPI_STORE, (cudaStream_t)stream);
+}
+
+size_t capdec_linear_topk_workspace(int32_t m, int32_t n, int32_t topk) {
+  if (m < 0 || !tk_supported(n, topk)) return 0;
+  return align_up((size_t)m * tk_tiles(n) * tk_stride(topk) * sizeof(float) + 256, 256);
+}
+
+int capdec_linear_topk(int32_t precision, const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,
+                       int32_t m, int32_t n, int32_t k, int32_t topk, float* out_lp, int32_t* out_idx, float* out_lse,
+                       void* ws, size_t ws_bytes, void* stream) {
+  CAPDEC_REQUIRE(precision != CAPDEC_PREC_FP32, CAPDEC_ERR_UNSUPPORTED,
+                 "capdec_linear_topk: the fused epilogue exists on the tensor-core path only");
+  CAPDEC_REQUIRE(tk_supported(n, topk), CAPDEC_ERR_UNSUPPORTED, "capdec_linear_topk: topk %d / vocab %d unsupported", topk, n);
+  CAPDEC_REQUIRE(ws && ws_bytes >= capdec_linear_topk_workspace(m, n, topk), CAPDEC_ERR_WORKSPACE,
+                 "capdec_linear_topk: workspace too small");
+  GemmArgs g{};
+  g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.M = m; g.N = n; g.K = k;
+  g.tk_part = (float*)ws; g.tk_k = topk;
+  CAPDEC_RETURN_IF(gemm(nullptr, precision, g, EPI_TOPK, (cudaStream_t)stream));
+  return topk_merge((const float*)ws, m, n, topk, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
 }
 
 int capdec_lse_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t topk, float* out_lp,

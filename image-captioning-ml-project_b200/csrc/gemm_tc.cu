@@ -10,8 +10,10 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A_hi/A_lo/W_hi/W_lo tiles, mbarrier tx
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8),
 //               tcgen05.commit releases shared-memory stages and publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+//   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global; warp w reads TMEM
+//               lane quadrant w % 4 and column half (w - 2) / 4 of the tile, so every scheduler has two epilogue warps
 #include <cuda.h>
+#include <limits.h>
 
 #include "gemm_epilogue.cuh"
 #include "handle.cuh"
@@ -21,7 +23,7 @@ namespace {
 
 constexpr int BM = 128, BK = 32;
 constexpr int kStages = 2;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -84,7 +86,7 @@ struct SmemLayout {
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
 // so the CTAs running concurrently share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x BN columns)
 // so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1; the shared-memory ring runs across tiles.
-template <int BN, int EPI, int TERMS>
+template <int BN, int EPI, int TERMS, int TK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -112,7 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
     }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -185,6 +187,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;            // which BN/2 column half of the tile this warp drains
+    constexpr int HN = BN / 2;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
@@ -192,8 +196,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
       tcgen05_fence_after();
       const int m = m_tile * BM + q * 32 + lane;   // accumulator row == TMEM lane
+      // EPI_TOPK state: online log-sum-exp and a sorted top-TK list of this row over the tile's BN columns
+      float rmax = -INFINITY, rsum = 0.f;
+      float tv[TK > 0 ? TK : 1];
+      int ti[TK > 0 ? TK : 1];
+      if (EPI == EPI_TOPK) {
+#pragma unroll
+        for (int j = 0; j < TK; ++j) { tv[j] = -INFINITY; ti[j] = INT_MAX; }
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
         asm volatile(
@@ -206,19 +218,82 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= BN) {
-          // every accumulator column of this tile is now in registers: hand the TMEM buffer back to the MMA warp
+        if (c0 + 32 >= (half + 1) * HN) {
+          // every accumulator column this warp owns is now in registers: hand the TMEM buffer back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
         }
         const int n0 = n_tile * BN + c0;
         if (n0 < p.N) {
+          if constexpr (EPI == EPI_TOPK) {
+            // logits of this 32-column chunk (bias added, columns beyond N masked out)
+            float x[32];
+            const bool full = n0 + 32 <= p.N;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                           __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) {
+                if (full) b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+                else {
+                  b.x = n0 + j < p.N ? p.bias[n0 + j] : 0.f;         b.y = n0 + j + 1 < p.N ? p.bias[n0 + j + 1] : 0.f;
+                  b.z = n0 + j + 2 < p.N ? p.bias[n0 + j + 2] : 0.f; b.w = n0 + j + 3 < p.N ? p.bias[n0 + j + 3] : 0.f;
+                }
+              }
+              x[j] = __uint_as_float(v[j]) + b.x;         x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+              x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+            }
+            if (!full) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n0 + j >= p.N) x[j] = -INFINITY;
+            }
+            float cm = x[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, x[j]);
+            if (cm > rmax) { rsum *= __expf(rmax - cm); rmax = cm; }   // x[0] is always a real column, so cm is finite
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rsum += __expf(x[j] - rmax);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (x[j] > tv[TK - 1]) {
+                // branch-free sorted insert (every list position is independent, so the ALU latency pipelines):
+                // x lands behind any equal value, i.e. among equal logits the lower vocabulary index stays ahead
+                const float xv = x[j];
+                const int xi = n0 + j;
+                bool gt[TK];
+#pragma unroll
+                for (int t = 0; t < TK; ++t) gt[t] = xv > tv[t];
+#pragma unroll
+                for (int t = TK - 1; t > 0; --t) {
+                  ti[t] = gt[t] ? (gt[t - 1] ? ti[t - 1] : xi) : ti[t];
+                  tv[t] = fmaxf(tv[t], fminf(tv[t - 1], xv));
+                }
+                ti[0] = gt[0] ? xi : ti[0];
+                tv[0] = fmaxf(tv[0], xv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+          }
         }
+      }
+      if constexpr (EPI == EPI_TOPK) if (m < p.M && n_tile * BN + half * HN < p.N) {
+        // partial record of (row m, tile n_tile): {max, sum exp(x - max), TK values, TK indices}, 16-byte stores
+        constexpr int PS = (2 + 2 * TK + 3) & ~3;
+        float rec[PS];
+        rec[0] = rmax; rec[1] = rsum;
+#pragma unroll
+        for (int j = 0; j < TK; ++j) { rec[2 + j] = tv[j]; rec[2 + TK + j] = __int_as_float(ti[j]); }
+#pragma unroll
+        for (int j = 2 + 2 * TK; j < PS; ++j) rec[j] = 0.f;
+        const int n_rec = (p.N + HN - 1) / HN;    // records are per (row, BN/2-column half tile)
+        const int rec_id = n_tile * 2 + half;
+        float4* dst = reinterpret_cast<float4*>(p.tk_part + ((int64_t)m * n_rec + rec_id) * PS);
+#pragma unroll
+        for (int j = 0; j < PS / 4; ++j) dst[j] = make_float4(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3]);
       }
     }
   }
@@ -309,13 +384,13 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   constexpr int smem = SmemLayout<BN>::kTotal;
   const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM);
   dim3 grid(num_tiles < num_sms() ? num_tiles : num_sms());
-#define CAPDEC_TC_CASE(E)                                                                                         \
-  case E: {                                                                                                       \
-    auto kern = gemm_tcgen05_kernel<BN, E, TERMS>;                                                                \
+#define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
+  {                                                                                                               \
+    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV>;                                                           \
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
     kern<<<grid, kThreads, smem, s>>>(a_hi, a_lo, w_hi, w_lo, g);                                                 \
-    break;                                                                                                        \
   }
+#define CAPDEC_TC_CASE(E) case E: CAPDEC_TC_LAUNCH(E, 0) break;
   switch (epi) {
     CAPDEC_TC_CASE(EPI_STORE)
     CAPDEC_TC_CASE(EPI_SIGMOID_TAIL)
@@ -324,9 +399,22 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     CAPDEC_TC_CASE(EPI_AOA)
     CAPDEC_TC_CASE(EPI_GELU)
     CAPDEC_TC_CASE(EPI_GELU_TANH)
+    case EPI_TOPK:
+      if constexpr (BN == 2 * kTkTileCols) {   // the record layout is defined on halves of 256-column tiles
+        switch (tk_bucket(g.tk_k)) {
+          case 1: CAPDEC_TC_LAUNCH(EPI_TOPK, 1) break;
+          case 6: CAPDEC_TC_LAUNCH(EPI_TOPK, 6) break;
+          case 10: CAPDEC_TC_LAUNCH(EPI_TOPK, 10) break;
+          default: CAPDEC_TC_LAUNCH(EPI_TOPK, 16) break;
+        }
+        break;
+      } else {
+        CAPDEC_REQUIRE(false, CAPDEC_ERR_INVALID, "gemm_tc: EPI_TOPK needs the 256-column tile");
+      }
     default: CAPDEC_REQUIRE(false, CAPDEC_ERR_INVALID, "gemm_tc: unknown epilogue %d", epi);
   }
 #undef CAPDEC_TC_CASE
+#undef CAPDEC_TC_LAUNCH
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -359,6 +447,9 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     CAPDEC_REQUIRE(a.N % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "gemm: fused epilogue needs N %% 4 == 0 (N=%d)", a.N);
   CAPDEC_REQUIRE((((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.bias | (uintptr_t)a.C) & 15) == 0, CAPDEC_ERR_INVALID,
                  "gemm: A/W/bias/C must be 16-byte aligned");
+  if (epilogue == EPI_TOPK)
+    CAPDEC_REQUIRE(a.tk_part && (((uintptr_t)a.tk_part) & 15) == 0 && tk_supported(a.N, a.tk_k), CAPDEC_ERR_INVALID,
+                   "gemm: EPI_TOPK needs an aligned partial buffer, 1 <= k <= 16 and N <= 65536 (k=%d N=%d)", a.tk_k, a.N);
   const int terms = precision == CAPDEC_PREC_TF32X3 ? 3 : 1;
   const int K = a.K;
 
@@ -395,7 +486,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   float* a_hi = scratch;
   float* a_lo = scratch + a_elems;
 
-  const int bn = a.N <= 128 ? 128 : 256;
+  const int bn = (a.N <= 128 && epilogue != EPI_TOPK) ? 128 : 256;
   CUtensorMap map_w_hi, map_w_lo;
   CAPDEC_RETURN_IF(make_map(&map_w_hi, w_hi, a.N, K, K, bn));
   CAPDEC_RETURN_IF(make_map(&map_w_lo, w_lo, a.N, K, K, bn));
@@ -412,6 +503,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
     if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
+    if (a.tk_part) g.tk_part = a.tk_part + (int64_t)m0 * tk_tiles(a.N) * tk_stride(a.tk_k);
     int st;
     if (bn == 128) st = terms == 3 ? launch_tc<128, 3>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
                                    : launch_tc<128, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);

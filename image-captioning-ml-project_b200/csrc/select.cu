@@ -102,6 +102,58 @@ __global__ void __launch_bounds__(kThreads) lse_topk_kernel(const float* __restr
   }
 }
 
+// Combine the per-half-tile partial records of the fused vocabulary GEMM (EPI_TOPK, gemm_tc.cu) into the row's
+// log-sum-exp and sorted top-K:  one warp per row; lane l owns records l, l+32, ... and keeps a read position per
+// owned record in shared memory; each of the K rounds is a warp arg-max over the lanes' best list heads
+// (ties -> lower vocabulary index, as torch.topk / the unfused kernel).
+constexpr int kMergeMaxRecords = 1024;
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ part, int n_rec, int PS, int TKB,
+                                                         int rows, int K, float* __restrict__ out_lp,
+                                                         int32_t* __restrict__ out_idx, float* __restrict__ out_lse) {
+  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const float* pr = part + (int64_t)row * n_rec * PS;
+  uint8_t* pos = s_pos[warp];
+  float M = -INFINITY;
+  for (int t = lane; t < n_rec; t += 32) { M = fmaxf(M, pr[(int64_t)t * PS]); pos[t] = 0; }
+  M = warp_max(M);
+  float S = 0.f;
+  for (int t = lane; t < n_rec; t += 32) S += pr[(int64_t)t * PS + 1] * expf(pr[(int64_t)t * PS] - M);
+  S = warp_sum(S);
+  const float logS = logf(S);
+  if (lane == 0 && out_lse) out_lse[row] = M + logS;
+
+  // lane-local best head, recomputed only by the lane whose head was taken
+  auto scan = [&](float& bv, int& bi, int& bt) {
+    bv = -INFINITY; bi = INT_MAX; bt = -1;
+    for (int t = lane; t < n_rec; t += 32) {
+      const int pp = pos[t];
+      if (pp >= TKB) continue;
+      const int idx = __float_as_int(pr[(int64_t)t * PS + 2 + TKB + pp]);
+      const float v = pr[(int64_t)t * PS + 2 + pp];
+      if (idx != INT_MAX && better(v, idx, bv, bi)) { bv = v; bi = idx; bt = t; }
+    }
+  };
+  float bv; int bi, bt;
+  scan(bv, bi, bt);
+  for (int r = 0; r < K; ++r) {
+    float wv = bv;
+    int wi = bi;
+    warp_argmax(wv, wi);
+    const bool valid = wi != INT_MAX;
+    if (lane == 0) {
+      out_lp[(int64_t)row * K + r] = valid ? (wv - M) - logS : -INFINITY;
+      out_idx[(int64_t)row * K + r] = valid ? wi : -1;
+    }
+    if (valid && bi == wi) {   // vocabulary indices are unique, so exactly one lane advances
+      pos[bt] += 1;
+      scan(bv, bi, bt);
+    }
+  }
+}
+
 // One CTA per row: inverse-CDF draw in vocabulary index order (double prefix sums), or argmax for the greedy slot.
 __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restrict__ logits, int64_t ld, int V,
                                                           const float* __restrict__ uniforms, int64_t ld_u, int step,
@@ -390,6 +442,17 @@ int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, flo
   if (smem > 48 * 1024)
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(lse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   lse_topk_kernel<<<rows, kThreads, smem, s>>>(logits, ld, vocab, topk, out_lp, out_idx, out_lse);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int topk_merge(const float* part, int rows, int vocab, int part_k, int topk, float* out_lp, int32_t* out_idx,
+               float* out_lse, cudaStream_t s) {
+  CAPDEC_REQUIRE(tk_supported(vocab, part_k) && tk_tiles(vocab) <= kMergeMaxRecords && topk >= 1 && topk <= tk_bucket(part_k), CAPDEC_ERR_INVALID,
+                 "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
+  if (rows == 0) return CAPDEC_OK;
+  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(part, tk_tiles(vocab), tk_stride(part_k), tk_bucket(part_k), rows,
+                                                       topk, out_lp, out_idx, out_lse);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }

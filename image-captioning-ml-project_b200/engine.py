@@ -225,3 +225,21 @@ def lse_topk(logits: torch.Tensor, topk: int):
         check(lib.capdec_lse_topk(_ptr(logits), logits.stride(0), R, V, topk, _ptr(lp), _ptr(idx), _ptr(lse),
                                   _stream(logits.device)))
     return lp, idx, lse
+
+
+def linear_topk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], topk: int, precision: str = "tf32x3"):
+    """Stage-level entry (unit tests): vocabulary projection fused with log-softmax + top-k (no logits in HBM)."""
+    M, K = a.shape
+    N = w.shape[0]
+    dev = a.device
+    lp = torch.empty(M, topk, dtype=torch.float32, device=dev)
+    idx = torch.empty(M, topk, dtype=torch.int32, device=dev)
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    nbytes = int(lib.capdec_linear_topk_workspace(M, N, topk))
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+    if os.environ.get("CAPDEC_POISON_WORKSPACE"):
+        ws.fill_(0xFF)
+    with torch.cuda.device(dev):
+        check(lib.capdec_linear_topk(_capi.PREC[precision], _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), M, N, K,
+                                     topk, _ptr(lp), _ptr(idx), _ptr(lse), _ptr(ws), ws.numel(), _stream(dev)))
+    return lp, idx, lse

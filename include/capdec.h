@@ -185,6 +185,16 @@ int capdec_linear(int32_t precision, const float* a_dev, int64_t lda, const floa
 int capdec_lse_topk(const float* logits_dev, int64_t ld, int32_t rows, int32_t vocab, int32_t topk,
                     float* out_logprob_dev, int32_t* out_index_dev, float* out_lse_dev, void* stream);
 
+/* The fused form the beam / greedy decoders use on the tensor-core path (replaces fc / output_layer / lm_head followed
+ * by log_softmax + topk: models/decoder.py:171, src/models/decoders.py:303,483, HF _beam_search): the GEMM epilogue
+ * emits per-256-column-tile {max, sum-exp, top-k} partial records, a merge kernel combines them; the [m,n] logits are
+ * never written.  Outputs as capdec_lse_topk.  precision must be a tensor-core mode. */
+size_t capdec_linear_topk_workspace(int32_t m, int32_t n, int32_t topk);
+int capdec_linear_topk(int32_t precision, const float* a_dev, int64_t lda, const float* w_dev, int64_t ldw,
+                       const float* bias_dev, int32_t m, int32_t n, int32_t k, int32_t topk,
+                       float* out_logprob_dev, int32_t* out_index_dev, float* out_lse_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,39 @@ def test_lse_topk(cuda, R, V, K):
     assert torch.allclose(lse.cpu(), torch.logsumexp(x, -1), atol=1e-5)
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("M,N,K,topk", [(37, 10000, 512, 10), (300, 10000, 512, 6), (5, 50257, 768, 10), (129, 1000, 64, 1),
+                                        (64, 300, 128, 16), (3, 7, 32, 10), (260, 4096, 256, 10)])
+def test_linear_topk_fused(cuda, precision, M, N, K, topk):
+    """Vocabulary GEMM with the fused log-softmax + top-k epilogue (logits never written) against the unfused
+    GEMM -> lse_topk pipeline of the same precision (bit-identical logits, so identical indices) and torch."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
+    a, w, b = a.to(cuda), w.to(cuda), b.to(cuda)
+    lp, idx, lse = eng_mod.linear_topk(a, w, b, topk, precision=precision)
+    logits = eng_mod.linear(a, w, b, precision=precision)
+    kk = min(topk, N)
+    ref_lp, ref_idx = torch.log_softmax(logits.double(), -1).topk(kk, dim=-1)
+    assert torch.equal(idx[:, :kk].long(), ref_idx), (idx[:, :kk] != ref_idx).sum()
+    assert torch.allclose(lp[:, :kk].double(), ref_lp, atol=1e-5)
+    assert torch.allclose(lse.double(), torch.logsumexp(logits.double(), -1), atol=1e-5)
+    if kk < topk:   # fewer vocabulary entries than requested: the tail is (-inf, -1) like lse_topk
+        assert (idx[:, kk:] == -1).all() and torch.isinf(lp[:, kk:]).all()
+    # no bias (GPT-2 tied lm_head)
+    lp2, idx2, _ = eng_mod.linear_topk(a, w, None, topk, precision=precision)
+    ref2 = torch.log_softmax(eng_mod.linear(a, w, None, precision=precision).double(), -1).topk(kk, dim=-1)
+    assert torch.equal(idx2[:, :kk].long(), ref2[1]) and torch.allclose(lp2[:, :kk].double(), ref2[0], atol=1e-5)
+
+
+def test_linear_topk_fused_ties_take_lowest_index(cuda):
+    a = torch.zeros(4, 32, device=cuda)
+    w = torch.zeros(1000, 32, device=cuda)
+    b = torch.zeros(1000, device=cuda)
+    b[[700, 3, 259, 256]] = 5.0
+    _, idx, _ = eng_mod.linear_topk(a, w, b, 6)
+    assert idx[0].tolist() == [3, 256, 259, 700, 0, 1]
+
+
 def test_lse_topk_ties_take_lowest_index(cuda):
     x = torch.zeros(2, 100)
     x[0, [7, 3, 50]] = 5.0
