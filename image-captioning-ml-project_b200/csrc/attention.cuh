@@ -27,6 +27,9 @@ struct AddAttnArgs {
   int B, L, A, D, k;
 };
 int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s);
+// persistent TMA-streamed form (attn_stream.cu): returns 1 if it took the call, 0 if the shape is left to the generic
+// kernel in attn_additive.cu, < 0 on error
+int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s);
 
 // Multi-head dot-product attention on hoisted per-image K/V projections, all k rows of an image per CTA:
 //   s[b,h,l] = q[row_b,h,:] . K[img,l,h,:] / denom      (masked -> -1e9)

@@ -211,6 +211,8 @@ int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s) {
   CAPDEC_REQUIRE(a.ld_att2 % 4 == 0 && a.ld_ctx % 4 == 0 && (!a.gate || a.ld_gate % 4 == 0), CAPDEC_ERR_INVALID,
                  "additive_attention: row strides must be multiples of 4");
   if (a.B == 0) return CAPDEC_OK;
+  const int took = additive_attention_stream(a, act, s);   // persistent TMA-streamed kernel for the shapes it covers
+  if (took != 0) return took > 0 ? CAPDEC_OK : took;
   switch (a.k) {
     case 1: return launch_kb<1>(a, act, s);
     case 2: return launch_kb<2>(a, act, s);

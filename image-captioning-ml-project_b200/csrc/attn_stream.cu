@@ -1,0 +1,404 @@
+// Streaming additive attention: the HBM-bound stage of the decode step as a persistent, warp-specialised kernel.
+//
+//   e[b,l]   = (w . act(att1[img,l,:] + att2[row_b,:]) + w_bias) / temperature      (masked -> -1e9)
+//   alpha    = softmax_l(e)
+//   ctx[b,:] = sum_l alpha[b,l] * feats[img,l,:]   (* gate[row_b,:])
+//   legacy models/decoder.py:152-161 (relu, gate) / src/models/attention.py:76-111 (tanh)
+//
+// Per image-step the kernel must read att1 [L,A] and feats [L,D] exactly once (2.0 MB fp32 for 196 x (512+2048));
+// everything else is noise.  One CTA per SM walks images blockIdx.x, blockIdx.x + gridDim.x, ...:
+//   warps 0, 1    producers: one thread each streams feats / att1 through its own shared-memory ring with 1-D TMA bulk
+//                 copies (cp.async.bulk, mbarrier complete_tx).  The rows of an image are contiguous in HBM, so a ring
+//                 stage is simply a run of whole rows.  The two streams are independent: the att1 producer runs up to
+//                 two images ahead, so HBM requests never pause at an image boundary.
+//   warps 2-9     score warps: att1 chunks -> scores (lanes split the attention dim, the k beams of the image reuse every
+//                 loaded element, warp-shuffle reduction) -> softmax -> alpha in a triple-buffered shared array.
+//   warps 10-17   context warps: feats chunks x alpha -> k context rows in registers -> gate multiply -> written
+//                 straight into the LSTM operand.
+// The ALU-heavy score work of image i+1 therefore overlaps the load-heavy context work of image i inside one CTA, and
+// up to ~170 KB of loads are in flight per SM without costing registers.
+#include <stdlib.h>
+
+#include "attention.cuh"
+
+namespace capdec {
+namespace {
+
+constexpr int kScoreWarps = 8, kCtxWarps = 8;
+constexpr int kScoreThreads = 32 * kScoreWarps, kCtxThreads = 32 * kCtxWarps;
+constexpr int kThreads = 64 + kScoreThreads + kCtxThreads;   // 576
+constexpr int kStagesA = 2, kStagesF = 4;
+constexpr int kEBuf = 3;                                     // alpha buffers: scores of image i+1 while context reads image i
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct StreamLayout {
+  int rowsA, rowsF, nA, nF;            // rows per ring stage, stages per image
+  uint32_t stageA, stageF;             // bytes per stage
+  uint32_t off_ringA, off_ringF, off_att2, off_w, off_e, off_red, off_bar, total;
+  int Lp, G;                           // padded L; context row groups (threads split rows when D/4 <= 128)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > kSpinLimit) __trap();   // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) { return ACT == ACT_RELU ? fmaxf(x, 0.f) : tanhf(x); }
+
+template <int KB, int ACT, int NC>
+__global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(const AddAttnArgs p, const StreamLayout y) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ringA = smem + y.off_ringA;
+  uint8_t* ringF = smem + y.off_ringF;
+  float* s_att2 = reinterpret_cast<float*>(smem + y.off_att2);   // [2][KB][A]
+  float* s_w = reinterpret_cast<float*>(smem + y.off_w);         // [A]
+  float* s_e = reinterpret_cast<float*>(smem + y.off_e);         // [kEBuf][KB][Lp]
+  float* s_red = reinterpret_cast<float*>(smem + y.off_red);     // [G-1][KB][D]
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + y.off_bar);
+  uint64_t* emptyA = fullA + kStagesA;
+  uint64_t* fullF = emptyA + kStagesA;
+  uint64_t* emptyF = fullF + kStagesF;
+  uint64_t* e_full = emptyF + kStagesF;
+  uint64_t* e_empty = e_full + kEBuf;
+
+  const int A = p.A, L = p.L, D = p.D, k = p.k, Lp = y.Lp;
+  const int A4 = A >> 2, D4 = D >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_img = ((int)blockIdx.x < p.B) ? (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStagesA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], kScoreWarps); }
+    for (int s = 0; s < kStagesF; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], kCtxWarps); }
+    for (int s = 0; s < kEBuf; ++s) { mbar_init(&e_full[s], kScoreWarps); mbar_init(&e_empty[s], kCtxWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ================================ feats producer ================================
+    if (lane == 0) {
+      uint32_t itF = 0;
+      const size_t rowF = (size_t)D * sizeof(float);
+      for (int i = 0; i < n_img; ++i) {
+        const int img = blockIdx.x + i * gridDim.x;
+        for (int c = 0; c < y.nF; ++c, ++itF) {
+          const int s = itF % kStagesF;
+          mbar_wait(&emptyF[s], ((itF / kStagesF) & 1) ^ 1);
+          const int rows = min(y.rowsF, L - c * y.rowsF);
+          const uint32_t bytes = (uint32_t)(rows * rowF);
+          mbar_expect_tx(&fullF[s], bytes);
+          bulk_load(ringF + (size_t)s * y.stageF, p.feats + ((size_t)img * L + (size_t)c * y.rowsF) * D, bytes, &fullF[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ att1 producer ================================
+    if (lane == 0) {
+      uint32_t itA = 0;
+      const size_t rowA = (size_t)A * sizeof(float);
+      for (int i = 0; i < n_img; ++i) {
+        const int img = blockIdx.x + i * gridDim.x;
+        for (int c = 0; c < y.nA; ++c, ++itA) {
+          const int s = itA % kStagesA;
+          mbar_wait(&emptyA[s], ((itA / kStagesA) & 1) ^ 1);
+          const int rows = min(y.rowsA, L - c * y.rowsA);
+          const uint32_t bytes = (uint32_t)(rows * rowA);
+          mbar_expect_tx(&fullA[s], bytes);
+          bulk_load(ringA + (size_t)s * y.stageA, p.att1 + ((size_t)img * L + (size_t)c * y.rowsA) * A, bytes, &fullA[s]);
+        }
+      }
+    }
+  } else if (warp < 2 + kScoreWarps) {
+    // ================================ score warps ================================
+    const int sw = warp - 2, t = threadIdx.x - 64;
+    for (int i = t; i < A4; i += kScoreThreads) reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(p.w)[i];
+    uint32_t itA = 0;
+    for (int i = 0; i < n_img; ++i) {
+      const int img = blockIdx.x + i * gridDim.x;
+      const int64_t row0 = (int64_t)img * k;
+      const int buf = i % kEBuf;
+      float* q2 = s_att2 + (size_t)(i & 1) * KB * A;
+      for (int j = t; j < KB * A4; j += kScoreThreads) {
+        const int b = j / A4, a4 = j - b * A4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < k) v = *reinterpret_cast<const float4*>(p.att2 + (row0 + b) * p.ld_att2 + a4 * 4);
+        reinterpret_cast<float4*>(q2)[j] = v;
+      }
+      named_barrier(1, kScoreThreads);
+      mbar_wait(&e_empty[buf], (((uint32_t)i / kEBuf) & 1) ^ 1);   // the context warps are done with this alpha buffer
+      float* e = s_e + (size_t)buf * KB * Lp;
+      for (int c = 0; c < y.nA; ++c, ++itA) {
+        const int s = itA % kStagesA;
+        mbar_wait(&fullA[s], (itA / kStagesA) & 1);
+        const int rows = min(y.rowsA, L - c * y.rowsA);
+        const float* tile = reinterpret_cast<const float*>(ringA + (size_t)s * y.stageA);
+        for (int r = sw * 2; r < rows; r += kScoreWarps * 2) {
+          const int r1 = min(r + 1, rows - 1);
+          const float4* x0p = reinterpret_cast<const float4*>(tile + (size_t)r * A);
+          const float4* x1p = reinterpret_cast<const float4*>(tile + (size_t)r1 * A);
+          float acc0[KB], acc1[KB];
+#pragma unroll
+          for (int b = 0; b < KB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+          for (int a4 = lane; a4 < A4; a4 += 32) {
+            const float4 x0 = x0p[a4], x1 = x1p[a4];
+            const float4 wv = reinterpret_cast<const float4*>(s_w)[a4];
+#pragma unroll
+            for (int b = 0; b < KB; ++b) {
+              const float4 q = reinterpret_cast<const float4*>(q2)[b * A4 + a4];
+              float u = acc0[b], v = acc1[b];
+              u = fmaf(wv.x, act_fn<ACT>(x0.x + q.x), u); v = fmaf(wv.x, act_fn<ACT>(x1.x + q.x), v);
+              u = fmaf(wv.y, act_fn<ACT>(x0.y + q.y), u); v = fmaf(wv.y, act_fn<ACT>(x1.y + q.y), v);
+              u = fmaf(wv.z, act_fn<ACT>(x0.z + q.z), u); v = fmaf(wv.z, act_fn<ACT>(x1.z + q.z), v);
+              u = fmaf(wv.w, act_fn<ACT>(x0.w + q.w), u); v = fmaf(wv.w, act_fn<ACT>(x1.w + q.w), v);
+              acc0[b] = u; acc1[b] = v;
+            }
+          }
+          const int l0 = c * y.rowsA + r;
+#pragma unroll
+          for (int b = 0; b < KB; ++b) {
+            const float v0 = warp_sum(acc0[b]), v1 = warp_sum(acc1[b]);
+            if (lane == 0) {
+              float e0 = (v0 + p.w_bias) / p.temperature;
+              if (p.mask && p.mask[(int64_t)img * L + l0]) e0 = -1.0e9f;
+              e[b * Lp + l0] = e0;
+              if (r + 1 < rows) {
+                float e1 = (v1 + p.w_bias) / p.temperature;
+                if (p.mask && p.mask[(int64_t)img * L + l0 + 1]) e1 = -1.0e9f;
+                e[b * Lp + l0 + 1] = e1;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&emptyA[s]);
+      }
+      named_barrier(1, kScoreThreads);   // every score of the image is in shared memory
+      for (int b = sw; b < k; b += kScoreWarps) {
+        float* eb = e + b * Lp;
+        float m = -INFINITY;
+        for (int l = lane; l < L; l += 32) m = fmaxf(m, eb[l]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int l = lane; l < L; l += 32) {
+          const float v = expf(eb[l] - m);
+          eb[l] = v;
+          sum += v;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        float* aout = p.alpha ? p.alpha + (row0 + b) * p.ld_alpha : nullptr;
+        for (int l = lane; l < L; l += 32) {
+          const float v = eb[l] * inv;
+          eb[l] = v;
+          if (aout) aout[l] = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_full[buf]);   // release: alpha of this image is ready for the context warps
+    }
+  } else {
+    // ================================ context warps ================================
+    const int t = threadIdx.x - 64 - kScoreThreads;   // 0..255
+    const int Dw = D4 < kCtxThreads ? D4 : kCtxThreads;   // float4 columns covered per pass
+    const int g = t / Dw, c0 = t - g * Dw;
+    const bool active = g < y.G;
+    uint32_t itF = 0;
+    for (int i = 0; i < n_img; ++i) {
+      const int img = blockIdx.x + i * gridDim.x;
+      const int64_t row0 = (int64_t)img * k;
+      const int buf = i % kEBuf;
+      mbar_wait(&e_full[buf], ((uint32_t)i / kEBuf) & 1);
+      const float* e = s_e + (size_t)buf * KB * Lp;
+      float4 acc[NC][KB];
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int b = 0; b < KB; ++b) acc[j][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < y.nF; ++c, ++itF) {
+        const int s = itF % kStagesF;
+        mbar_wait(&fullF[s], (itF / kStagesF) & 1);
+        const int rows = min(y.rowsF, L - c * y.rowsF);
+        const float4* tile = reinterpret_cast<const float4*>(ringF + (size_t)s * y.stageF);
+        if (active) {
+          for (int r = g; r < rows; r += y.G) {
+            const int l = c * y.rowsF + r;
+            float4 x[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+              const int col = c0 + j * kCtxThreads;
+              x[j] = col < D4 ? tile[(size_t)r * D4 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int b = 0; b < KB; ++b) {
+              const float al = e[b * Lp + l];
+#pragma unroll
+              for (int j = 0; j < NC; ++j) {
+                acc[j][b].x = fmaf(al, x[j].x, acc[j][b].x); acc[j][b].y = fmaf(al, x[j].y, acc[j][b].y);
+                acc[j][b].z = fmaf(al, x[j].z, acc[j][b].z); acc[j][b].w = fmaf(al, x[j].w, acc[j][b].w);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&emptyF[s]);
+      }
+      if (y.G > 1) {   // (NC == 1 here) fold the row groups through shared memory
+        if (active && g > 0) {
+#pragma unroll
+          for (int b = 0; b < KB; ++b) reinterpret_cast<float4*>(s_red)[((size_t)(g - 1) * KB + b) * D4 + c0] = acc[0][b];
+        }
+        named_barrier(2, kCtxThreads);
+        if (active && g == 0) {
+#pragma unroll
+          for (int b = 0; b < KB; ++b)
+            for (int gg = 1; gg < y.G; ++gg) {
+              const float4 v = reinterpret_cast<const float4*>(s_red)[((size_t)(gg - 1) * KB + b) * D4 + c0];
+              acc[0][b].x += v.x; acc[0][b].y += v.y; acc[0][b].z += v.z; acc[0][b].w += v.w;
+            }
+        }
+        named_barrier(2, kCtxThreads);   // s_red may be overwritten by the next image only after everyone has read it
+      }
+      if (active && g == 0) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int col = c0 + j * kCtxThreads;
+          if (col >= D4) continue;
+#pragma unroll
+          for (int b = 0; b < KB; ++b) {
+            if (b >= k) continue;
+            float4 v = acc[j][b];
+            if (p.gate) {
+              const float4 gt = *reinterpret_cast<const float4*>(p.gate + (row0 + b) * p.ld_gate + col * 4);
+              v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
+            }
+            *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + col * 4) = v;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_empty[buf]);
+    }
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Shared-memory plan; returns false when the shape does not fit this kernel (the caller uses the generic kernel).
+bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
+  const int A4 = a.A / 4, D4 = a.D / 4;
+  if (a.A % 4 || a.D % 4 || D4 > 2 * kCtxThreads || a.L < 1) return false;
+  if ((((uintptr_t)a.att1 | (uintptr_t)a.feats | (uintptr_t)a.att2 | (uintptr_t)a.w) & 15) != 0) return false;
+  int G = 1;
+  if (D4 <= kCtxThreads / 2) { while (D4 * G * 2 <= kCtxThreads) G *= 2; }
+  const size_t rowA = (size_t)a.A * 4, rowF = (size_t)a.D * 4;
+  const int Lp = (a.L + 3) & ~3;
+  size_t fixed = 0;
+  auto take = [&](size_t bytes) { const size_t o = fixed; fixed = (fixed + bytes + 127) & ~(size_t)127; return (uint32_t)o; };
+  y->off_att2 = take((size_t)2 * KB * a.A * 4);
+  y->off_w = take((size_t)a.A * 4);
+  y->off_e = take((size_t)kEBuf * KB * Lp * 4);
+  y->off_red = take(G > 1 ? (size_t)(G - 1) * KB * a.D * 4 : 16);
+  y->off_bar = take((size_t)(2 * kStagesA + 2 * kStagesF + 2 * kEBuf) * 8);
+  const size_t budget = 220 * 1024;
+  if (fixed + kStagesA * rowA + kStagesF * rowF > budget) return false;
+  // att1 ring: one full pass of the score warps (2 rows each) per stage when it fits; the feats ring gets the rest
+  const size_t left = budget - fixed;
+  int rowsA = 2 * kScoreWarps, rowsF = 0;
+  if (rowsA > a.L) rowsA = a.L;
+  for (; rowsA >= 1; rowsA = rowsA > 1 ? rowsA / 2 : 0) {
+    const size_t needA = (size_t)kStagesA * (((size_t)rowsA * rowA + 127) & ~(size_t)127);
+    if (needA + kStagesF * (rowF + 128) > left) continue;
+    rowsF = (int)(((left - needA) / kStagesF - 128) / rowF);
+    if (rowsF >= 1) break;
+  }
+  if (rowsA < 1 || rowsF < 1) return false;
+  rowsF = rowsF > a.L ? a.L : rowsF;
+  if (rowsF > G) rowsF = rowsF / G * G;
+  y->rowsA = rowsA; y->rowsF = rowsF;
+  y->nA = (a.L + rowsA - 1) / rowsA; y->nF = (a.L + rowsF - 1) / rowsF;
+  y->stageA = (uint32_t)(((size_t)rowsA * rowA + 127) & ~(size_t)127);
+  y->stageF = (uint32_t)(((size_t)rowsF * rowF + 127) & ~(size_t)127);
+  y->off_ringA = take((size_t)kStagesA * y->stageA);
+  y->off_ringF = take((size_t)kStagesF * y->stageF);
+  y->total = (uint32_t)fixed;
+  y->Lp = Lp; y->G = G;
+  (void)A4;
+  return fixed <= 227 * 1024;
+}
+
+template <int KB>
+int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStream_t s) {
+  const int nc = (a.D / 4 + kCtxThreads - 1) / kCtxThreads;
+  const int grid = a.B < sm_count() ? a.B : sm_count();
+#define CAPDEC_STREAM_LAUNCH(ACTV, NCV)                                                                                   \
+  {                                                                                                                       \
+    auto kern = additive_attention_stream_kernel<KB, ACTV, NCV>;                                                          \
+    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));             \
+    kern<<<grid, kThreads, y.total, s>>>(a, y);                                                                           \
+  }
+  if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2) }
+  else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2) }
+#undef CAPDEC_STREAM_LAUNCH
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+}  // namespace
+
+// returns 1 when the streaming kernel took the call, 0 when the shape is left to the generic kernel, < 0 on error
+int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s) {
+  static const bool disabled = getenv("CAPDEC_ATTN_GENERIC") != nullptr;
+  if (disabled || a.k < 1 || a.k > kMaxRowsPerImage) return 0;
+  if (a.ld_att2 % 4 || a.ld_ctx % 4 || (a.gate && a.ld_gate % 4)) return 0;
+  const int KB = a.k <= 6 ? a.k : 8;
+  StreamLayout y{};
+  if (!plan(a, KB, &y)) return 0;
+  int st;
+  switch (KB) {
+    case 1: st = launch_stream<1>(a, act, y, s); break;
+    case 2: st = launch_stream<2>(a, act, y, s); break;
+    case 3: st = launch_stream<3>(a, act, y, s); break;
+    case 4: st = launch_stream<4>(a, act, y, s); break;
+    case 5: st = launch_stream<5>(a, act, y, s); break;
+    case 6: st = launch_stream<6>(a, act, y, s); break;
+    default: st = launch_stream<8>(a, act, y, s); break;
+  }
+  return st == CAPDEC_OK ? 1 : st;
+}
+
+}  // namespace capdec

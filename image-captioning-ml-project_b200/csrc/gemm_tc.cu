@@ -14,6 +14,7 @@
 //               lane quadrant w % 4 and column half (w - 2) / 4 of the tile, so every scheduler has two epilogue warps
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "gemm_epilogue.cuh"
 #include "handle.cuh"
@@ -22,7 +23,6 @@ namespace capdec {
 namespace {
 
 constexpr int BM = 128, BK = 32;
-constexpr int kStages = 2;
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
@@ -52,6 +52,40 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: both CTAs of the pair run the same code; TMA completions of either CTA are
+// counted on the LEADER's full barrier, tcgen05.commit multicasts its arrive to the same barrier offset in both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {   // address of the same offset in `cta_rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -70,14 +104,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // cute/arch/mma_sm100_desc.hpp::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major A and B,
 // n_dim = N>>3 @17, m_dim = M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+// CG = CTAs cooperating on one output tile: 1 -> 128 x BN tile per CTA; 2 -> CTA pair (cta_group::2) on a 256 x BN tile,
+// each CTA staging its own 128 rows of A and HALF of the W tile (BN/2 rows), which halves the shared-memory bytes per
+// flop -- a single CTA's 3xTF32 main loop needs ~158 B/clk of shared-memory bandwidth (MMA operand reads + TMA fills),
+// more than the SM's 128 B/clk; the pair needs ~106 B/clk.
+template <int BN, int CG>
 struct SmemLayout {
+  static constexpr int kStages = CG == 2 ? 3 : 2;
   static constexpr uint32_t kABytes = BM * BK * 4;
-  static constexpr uint32_t kWBytes = BN * BK * 4;
+  static constexpr uint32_t kWBytes = (BN / CG) * BK * 4;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
@@ -86,12 +125,13 @@ struct SmemLayout {
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
 // so the CTAs running concurrently share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x BN columns)
 // so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1; the shared-memory ring runs across tiles.
-template <int BN, int EPI, int TERMS, int TK>
+template <int BN, int EPI, int TERMS, int TK, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const GemmArgs p) {
-  using SL = SmemLayout<BN>;
+  using SL = SmemLayout<BN, CG>;
+  constexpr int kStages = SL::kStages;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::kBarOffset);
@@ -101,8 +141,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; rank 0 issues the MMAs
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  constexpr int TM = BM * CG;                                // output tile rows per CTA group
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = n_tiles * ((p.M + BM - 1) / BM);
+  const int num_tiles = n_tiles * ((p.M + TM - 1) / TM);
   const int num_kb = (p.K + BK - 1) / BK;
   constexpr uint32_t kTmemCols = 2 * BN;           // 256 or 512: a power of two >= 32
 
@@ -114,47 +157,70 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
     }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers initialised + TMEM allocated in BOTH CTAs of the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs of a pair: own 128 rows of A, own BN/CG rows of W) =====
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter across tiles -> ring stage / phase
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+        const int a_row = m_tile * TM + (int)rank * BM;
+        const int w_row = n_tile * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * SL::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes);
-          tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m_tile * BM);
-          tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, n_tile * BN);
-          if (TERMS == 3) {
-            tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, m_tile * BM);
-            tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, n_tile * BN);
+          constexpr uint32_t kTx = TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes;
+          if (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * kTx);   // bytes of both CTAs land on the leader's barrier
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, a_row);
+            tma_load_2d_pair(st + 2 * SL::kABytes, &map_w_hi, lbar, kb * BK, w_row);
+            if (TERMS == 3) {
+              tma_load_2d_pair(st + SL::kABytes, &map_a_lo, lbar, kb * BK, a_row);
+              tma_load_2d_pair(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, lbar, kb * BK, w_row);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], kTx);
+            tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, a_row);
+            tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, w_row);
+            if (TERMS == 3) {
+              tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, a_row);
+              tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, w_row);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BN);
+    // ===== MMA issuer (one thread; in pair mode only the leader CTA, its MMAs drive both SMs' tensor cores) =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TM, BN);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (CG == 2) mma_tf32_pair(d, a, b, idesc, acc); else mma_tf32(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) { if (CG == 2) tcgen05_commit_pair(bar); else tcgen05_commit(bar); };
       uint32_t it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
         const uint32_t ab = local & 1;                       // accumulator buffer
-        mbar_wait(&tmem_empty_bar[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this buffer
+        mbar_wait(&tmem_empty_bar[ab], ((local >> 1) & 1) ^ 1);  // the epilogue warps (of both CTAs) drained this buffer
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + ab * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -171,15 +237,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span
             const uint32_t first = (kb | k) == 0 ? 0u : 1u;
             if (TERMS == 3) {
-              mma_tf32(tmem_d, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), idesc, first);
-              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), idesc, 1u);
-              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, 1u);
+              mma(tmem_d, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), first);
+              mma(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), 1u);
+              mma(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), 1u);
             } else {
-              mma_tf32(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, first);
+              mma(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), first);
             }
           }
-          tcgen05_commit(&empty_bar[s]);                           // frees this shared-memory stage when the MMAs retire
-          if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[ab]);  // accumulator complete
+          commit(&empty_bar[s]);                           // frees this shared-memory stage (in both CTAs) when the MMAs retire
+          if (kb == num_kb - 1) commit(&tmem_full_bar[ab]);  // accumulator complete
         }
       }
     }
@@ -190,12 +256,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int half = (warp - 2) >> 2;            // which BN/2 column half of the tile this warp drains
     constexpr int HN = BN / 2;
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    const uint32_t leader_empty_bar0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
       const uint32_t ab = local & 1;
       mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
       tcgen05_fence_after();
-      const int m = m_tile * BM + q * 32 + lane;   // accumulator row == TMEM lane
+      const int m = m_tile * TM + (int)rank * BM + q * 32 + lane;   // accumulator row == TMEM lane of this CTA
       // EPI_TOPK state: online log-sum-exp and a sorted top-TK list of this row over the tile's BN columns
       float rmax = -INFINITY, rsum = 0.f;
       float tv[TK > 0 ? TK : 1];
@@ -222,7 +289,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           // every accumulator column this warp owns is now in registers: hand the TMEM buffer back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(leader_empty_bar0 + ab * 8);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
+          }
         }
         const int n0 = n_tile * BN + c0;
         if (n0 < p.N) {
@@ -298,10 +368,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair mode: the peer's shared memory / barriers stay alive until both are done
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -378,17 +449,43 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int TERMS>
+// number of CTA pairs the device can keep resident for a pair-mode kernel (clusters of 2 need both SMs of a TPC)
+template <typename Kern>
+int max_active_pairs(Kern kern, int smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms()); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+  return n;
+}
+
+template <int BN, int TERMS, int CG>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
               const GemmArgs& g, int epi, cudaStream_t s) {
-  constexpr int smem = SmemLayout<BN>::kTotal;
-  const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM);
-  dim3 grid(num_tiles < num_sms() ? num_tiles : num_sms());
+  constexpr int smem = SmemLayout<BN, CG>::kTotal;
+  const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM * CG);
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
-    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV>;                                                           \
-    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
-    kern<<<grid, kThreads, smem, s>>>(a_hi, a_lo, w_hi, w_lo, g);                                                 \
+    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG>;                                                       \
+    static bool configured = false;                                                                               \
+    static int max_groups = 0;                                                                                    \
+    if (!configured) {                                                                                            \
+      CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
+      max_groups = CG == 2 ? max_active_pairs(kern, smem) : num_sms();                                            \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    const int groups = num_tiles < max_groups ? num_tiles : max_groups;                                           \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = dim3(groups * CG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
+    cudaLaunchAttribute at[1];                                                                                    \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                               \
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                             \
+    CAPDEC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, g));                                 \
   }
 #define CAPDEC_TC_CASE(E) case E: CAPDEC_TC_LAUNCH(E, 0) break;
   switch (epi) {
@@ -487,9 +584,12 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   float* a_lo = scratch + a_elems;
 
   const int bn = (a.N <= 128 && epilogue != EPI_TOPK) ? 128 : 256;
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work and a 256-wide tile
+  static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
+  const int cg = (bn == 256 && a.M > BM && !no_pair) ? 2 : 1;
   CUtensorMap map_w_hi, map_w_lo;
-  CAPDEC_RETURN_IF(make_map(&map_w_hi, w_hi, a.N, K, K, bn));
-  CAPDEC_RETURN_IF(make_map(&map_w_lo, w_lo, a.N, K, K, bn));
+  CAPDEC_RETURN_IF(make_map(&map_w_hi, w_hi, a.N, K, K, bn / cg));
+  CAPDEC_RETURN_IF(make_map(&map_w_lo, w_lo, a.N, K, K, bn / cg));
 
   for (int m0 = 0; m0 < a.M; m0 += m_chunk) {
     const int mc = a.M - m0 < m_chunk ? a.M - m0 : m_chunk;
@@ -505,10 +605,12 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
     if (a.tk_part) g.tk_part = a.tk_part + (int64_t)m0 * tk_tiles(a.N) * tk_stride(a.tk_k);
     int st;
-    if (bn == 128) st = terms == 3 ? launch_tc<128, 3>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
-                                   : launch_tc<128, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
-    else           st = terms == 3 ? launch_tc<256, 3>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
-                                   : launch_tc<256, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+    if (bn == 128)    st = terms == 3 ? launch_tc<128, 3, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+                                      : launch_tc<128, 1, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+    else if (cg == 1) st = terms == 3 ? launch_tc<256, 3, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+                                      : launch_tc<256, 1, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+    else              st = terms == 3 ? launch_tc<256, 3, 2>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+                                      : launch_tc<256, 1, 2>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
     CAPDEC_RETURN_IF(st);
   }
   return CAPDEC_OK;
