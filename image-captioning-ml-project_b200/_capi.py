@@ -15,7 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "capdec.h")
 
 ARCH_LEGACY_SAT, ARCH_LSTM, ARCH_TRANSFORMER, ARCH_GPT2 = 0, 1, 2, 3
 ATT = {"soft": 0, "multi_head": 1, "adaptive": 2, "aoa": 3}
-PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "tf32": 3}
+PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "tf32": 3, "bf16x3": 4}
 
 
 class CapdecError(RuntimeError):

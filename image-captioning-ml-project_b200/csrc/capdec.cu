@@ -706,7 +706,7 @@ int capdec_create(const capdec_config* cfg, capdec_handle** out) {
                  CAPDEC_ERR_UNSUPPORTED, "unsupported decoder arch %d", cfg->arch);
   CAPDEC_REQUIRE(cfg->attention >= CAPDEC_ATT_SOFT && cfg->attention <= CAPDEC_ATT_AOA, CAPDEC_ERR_UNSUPPORTED,
                  "Unsupported attention type: %d", cfg->attention);
-  CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
+  CAPDEC_REQUIRE(cfg->precision >= CAPDEC_PREC_FP32 && cfg->precision <= CAPDEC_PREC_BF16X3, CAPDEC_ERR_UNSUPPORTED,
                  "unsupported precision %d", cfg->precision);
   CAPDEC_REQUIRE(cfg->vocab_size > 0 && cfg->hidden_dim > 0 && cfg->embed_dim > 0 && cfg->num_layers >= 1 &&
                      cfg->num_layers <= (cfg->arch >= CAPDEC_ARCH_TRANSFORMER ? 64 : 7),
@@ -740,7 +740,7 @@ void capdec_destroy(capdec_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   gemm_tc_release(h);
   if (h->stage_dev) cudaFree(h->stage_dev);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kHostBufs; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
@@ -1098,7 +1098,7 @@ int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const flo
   const size_t pool_chunk = align_up((size_t)chunk * c.hidden_dim * sizeof(float), 256);
   const size_t ws_bytes = capdec_workspace_bytes(h, chunk, L, k, T);
   const size_t out_bytes = align_up((size_t)B * T * 4, 256) + 2 * align_up((size_t)B * 4, 256);
-  const size_t total = 2 * feat_chunk + 2 * pool_chunk + ws_bytes + out_bytes;
+  const size_t total = kHostBufs * (feat_chunk + pool_chunk) + ws_bytes + out_bytes;
   if (h->stage_bytes < total) {
     if (h->stage_dev) CAPDEC_CHECK_CUDA(cudaFree(h->stage_dev));
     h->stage_dev = nullptr; h->stage_bytes = 0;
@@ -1108,24 +1108,45 @@ int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const flo
   if (!h->stream_compute) {
     CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_compute, cudaStreamNonBlocking));
     CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHostBufs; ++i) {
       CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
       CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
   }
   char* base = (char*)h->stage_dev;
-  float* d_feat[2] = {(float*)base, (float*)(base + feat_chunk)};
-  float* d_pool[2] = {(float*)(base + 2 * feat_chunk), (float*)(base + 2 * feat_chunk + pool_chunk)};
-  void* d_ws = base + 2 * feat_chunk + 2 * pool_chunk;
+  float* d_feat[kHostBufs];
+  float* d_pool[kHostBufs];
+  for (int i = 0; i < kHostBufs; ++i) {
+    d_feat[i] = (float*)(base + (size_t)i * feat_chunk);
+    d_pool[i] = (float*)(base + (size_t)kHostBufs * feat_chunk + (size_t)i * pool_chunk);
+  }
+  void* d_ws = base + (size_t)kHostBufs * (feat_chunk + pool_chunk);
   int32_t* d_tok = (int32_t*)((char*)d_ws + ws_bytes);
   int32_t* d_len = (int32_t*)((char*)d_tok + align_up((size_t)B * T * 4, 256));
   float* d_score = (float*)((char*)d_len + align_up((size_t)B * 4, 256));
   const size_t img_floats = (size_t)L * c.feature_dim;
-  int idx = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++idx) {
-    const int nb = B - b0 < chunk ? B - b0 : chunk;
-    const int buf = idx & 1;
-    if (idx >= 2) CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_done[buf], 0));
+  // Chunk schedule: the copy engine runs back to back from t = 0, so the call ends one chunk-decode after the last
+  // byte lands (and starts decoding one chunk-copy after the first).  Ramp the chunk size up from chunk/8 at the start
+  // and down to chunk/8 at the end so both exposed pieces are small; full-size chunks in between keep the GEMMs efficient.
+  std::vector<int> sizes;
+  {
+    const int small = chunk / 8 > 32 ? chunk / 8 : (chunk < 32 ? chunk : 32);
+    std::vector<int> head, tail;
+    int left = B;
+    const char* ramp = getenv("CAPDEC_E2E_RAMP");   // "0" (default): none, "1": tail only, "2": head and tail.  Measured on B200: small chunks decode too slowly
+                                                    // (K-serial GEMM tiles, launch latency) for the ramp to pay, so it is off
+    const int mode = ramp ? atoi(ramp) : 0;
+    if (mode >= 2) for (int n = small; n < chunk && left > 2 * chunk; n *= 2) { head.push_back(n); left -= n; }
+    if (mode >= 1) for (int n = small; n < chunk && left > 2 * chunk; n *= 2) { tail.push_back(n); left -= n; }
+    sizes = head;
+    while (left > 0) { const int n = left < chunk ? left : chunk; sizes.push_back(n); left -= n; }
+    for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+  }
+  int idx = 0, b0 = 0;
+  for (size_t ci = 0; ci < sizes.size(); b0 += sizes[ci], ++ci, ++idx) {
+    const int nb = sizes[ci];
+    const int buf = idx % kHostBufs;   // three staging buffers: the copy engine never waits on the decode of the previous chunk
+    if (idx >= kHostBufs) CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_done[buf], 0));
     CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_feat[buf], feats_host + (size_t)b0 * img_floats, (size_t)nb * img_floats * sizeof(float),
                                       cudaMemcpyHostToDevice, h->stream_copy));
     if (pooled_host)

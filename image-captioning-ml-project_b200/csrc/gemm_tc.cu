@@ -13,6 +13,7 @@
 //   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global; warp w reads TMEM
 //               lane quadrant w % 4 and column half (w - 2) / 4 of the tile, so every scheduler has two epilogue warps
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <limits.h>
 #include <stdlib.h>
 
@@ -22,7 +23,9 @@
 namespace capdec {
 namespace {
 
-constexpr int BM = 128, BK = 32;
+constexpr int BM = 128;
+constexpr int kRowBytes = 128;        // one K block = one 128-byte swizzle row: 32 tf32 or 64 bf16 elements
+enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1 };
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
@@ -97,6 +100,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO), LBO unused (=1),
 // descriptor version 1 (sm_100), layout type 2.  cute/arch/mma_sm100_desc.hpp::SmemDescriptor.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -104,8 +119,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // cute/arch/mma_sm100_desc.hpp::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major A and B,
 // n_dim = N>>3 @17, m_dim = M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::tf32 operands use format code 2 (TF32); kind::f16 operands use 1 (BF16).
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int m, int n) {
+  const uint32_t fmt = kind == KIND_BF16 ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // CG = CTAs cooperating on one output tile: 1 -> 128 x BN tile per CTA; 2 -> CTA pair (cta_group::2) on a 256 x BN tile,
@@ -115,8 +132,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 template <int BN, int CG>
 struct SmemLayout {
   static constexpr int kStages = CG == 2 ? 3 : 2;
-  static constexpr uint32_t kABytes = BM * BK * 4;
-  static constexpr uint32_t kWBytes = (BN / CG) * BK * 4;
+  static constexpr uint32_t kABytes = BM * kRowBytes;
+  static constexpr uint32_t kWBytes = (BN / CG) * kRowBytes;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
@@ -125,7 +142,7 @@ struct SmemLayout {
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
 // so the CTAs running concurrently share A tiles in L2).  The accumulator is double-buffered in TMEM (2 x BN columns)
 // so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1; the shared-memory ring runs across tiles.
-template <int BN, int EPI, int TERMS, int TK, int CG>
+template <int BN, int EPI, int TERMS, int TK, int CG, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -146,6 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   constexpr int TM = BM * CG;                                // output tile rows per CTA group
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = n_tiles * ((p.M + TM - 1) / TM);
+  constexpr int BK = KIND == KIND_BF16 ? 64 : 32;   // elements per 128-byte K block
   const int num_kb = (p.K + BK - 1) / BK;
   constexpr uint32_t kTmemCols = 2 * BN;           // 256 or 512: a power of two >= 32
 
@@ -212,9 +230,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   } else if (warp == 1) {
     // ===== MMA issuer (one thread; in pair mode only the leader CTA, its MMAs drive both SMs' tensor cores) =====
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TM, BN);
+      constexpr uint32_t idesc = make_idesc(KIND, TM, BN);
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-        if (CG == 2) mma_tf32_pair(d, a, b, idesc, acc); else mma_tf32(d, a, b, idesc, acc);
+        if (KIND == KIND_BF16) { if (CG == 2) mma_bf16_pair(d, a, b, idesc, acc); else mma_bf16(d, a, b, idesc, acc); }
+        else                   { if (CG == 2) mma_tf32_pair(d, a, b, idesc, acc); else mma_tf32(d, a, b, idesc, acc); }
       };
       auto commit = [&](uint64_t* bar) { if (CG == 2) tcgen05_commit_pair(bar); else tcgen05_commit(bar); };
       uint32_t it = 0, local = 0;
@@ -233,8 +252,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           const uint32_t w_hi = a_hi + 2 * SL::kABytes;
           const uint32_t w_lo = w_hi + SL::kWBytes;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle span
+          for (int k = 0; k < kRowBytes / 32; ++k) {
+            const uint32_t koff = k * 32;  // one MMA consumes 32 bytes along K (8 tf32 / 16 bf16) inside the 128-byte swizzle span
             const uint32_t first = (kb | k) == 0 ? 0u : 1u;
             if (TERMS == 3) {
               mma(tmem_d, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), first);
@@ -376,29 +395,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   }
 }
 
-// hi = round-to-nearest TF32 of x (exactly representable, so the tensor core's own fp32->tf32 conversion is the
-// identity whatever its rounding), lo = x - hi (exact).  Output is dense [rows, cols].
-__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, float* __restrict__ hi,
-                                  float* __restrict__ lo) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
-  const int c4 = cols >> 2;
+// Operand split for the tensor-core modes.  Output is dense [rows, Kp] (Kp >= cols, zero padded so that a row is a
+// multiple of 16 bytes for TMA).
+//   tf32: hi = round-to-nearest TF32 of x (exactly representable, so the tensor core's own fp32->tf32 conversion is the
+//         identity whatever its rounding), lo = x - hi (exact in fp32)
+//   bf16: hi = bf16_rn(x), lo = bf16_rn(x - hi)
+// lo == nullptr (single-pass modes) skips the residual.
+template <int KIND>
+__global__ void split_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, int Kp, void* __restrict__ hi,
+                             void* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 columns
+  const int c4 = Kp >> 2;
   if (i >= (int64_t)rows * c4) return;
   const int r = (int)(i / c4), c = (int)(i - (int64_t)r * c4);
-  const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ld + c * 4);
-  float4 h, l;
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
-  reinterpret_cast<float4*>(hi)[i] = h;
-  reinterpret_cast<float4*>(lo)[i] = l;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c * 4 < cols) v = *reinterpret_cast<const float4*>(x + (int64_t)r * ld + c * 4);   // cols % 4 == 0
+  if (KIND == KIND_TF32) {
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    if (lo) reinterpret_cast<float4*>(lo)[i] = l;
+  } else {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                        h3 = __float2bfloat16_rn(v.w);
+    uint2 hp;
+    hp.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    hp.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    reinterpret_cast<uint2*>(hi)[i] = hp;
+    if (lo) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                          l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      uint2 lp;
+      lp.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      lp.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+      reinterpret_cast<uint2*>(lo)[i] = lp;
+    }
+  }
 }
 
-int split_tf32(const float* x, int64_t ld, int rows, int cols, float* hi, float* lo, cudaStream_t s) {
-  const int64_t n = (int64_t)rows * (cols / 4);
+int split_operand(int kind, const float* x, int64_t ld, int rows, int cols, int Kp, void* hi, void* lo, cudaStream_t s) {
+  const int64_t n = (int64_t)rows * (Kp / 4);
   if (n == 0) return CAPDEC_OK;
-  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, hi, lo);
+  if (kind == KIND_BF16) split_kernel<KIND_BF16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, Kp, hi, lo);
+  else                   split_kernel<KIND_TF32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, Kp, hi, lo);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -422,17 +465,19 @@ int get_encode_fn(EncodeTiledFn* out) {
   return CAPDEC_OK;
 }
 
-// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [box_rows, BK]; 128-byte swizzle; OOB -> 0
-int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D tensor [rows, cols] of tf32/bf16 elements with row stride ld (elements); box = [box_rows, one 128-byte K block];
+// 128-byte swizzle; OOB -> 0
+int make_map(CUtensorMap* m, int kind, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn;
   CAPDEC_RETURN_IF(get_encode_fn(&fn));
+  const size_t es = kind == KIND_BF16 ? 2 : 4;
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / es), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(m, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CAPDEC_REQUIRE(r == CUDA_SUCCESS, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)",
                  (int)r, (long long)rows, (long long)cols, (long long)ld);
   return CAPDEC_OK;
@@ -463,14 +508,14 @@ int max_active_pairs(Kern kern, int smem) {
   return n;
 }
 
-template <int BN, int TERMS, int CG>
+template <int BN, int TERMS, int CG, int KIND>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
               const GemmArgs& g, int epi, cudaStream_t s) {
   constexpr int smem = SmemLayout<BN, CG>::kTotal;
   const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM * CG);
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
-    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG>;                                                       \
+    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                       \
     static bool configured = false;                                                                               \
     static int max_groups = 0;                                                                                    \
     if (!configured) {                                                                                            \
@@ -534,8 +579,9 @@ int ensure(float** p, size_t* have, size_t need) {
 }  // namespace
 
 int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
-  CAPDEC_REQUIRE(precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_TF32, CAPDEC_ERR_UNSUPPORTED,
-                 "precision mode %d has no kernel in this build", precision);
+  CAPDEC_REQUIRE(precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_TF32 || precision == CAPDEC_PREC_BF16 ||
+                     precision == CAPDEC_PREC_BF16X3,
+                 CAPDEC_ERR_UNSUPPORTED, "precision mode %d has no kernel in this build", precision);
   CAPDEC_REQUIRE(a.M >= 0 && a.N > 0 && a.K > 0, CAPDEC_ERR_INVALID, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   if (a.M == 0) return CAPDEC_OK;
   CAPDEC_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0, CAPDEC_ERR_UNSUPPORTED,
@@ -546,71 +592,78 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
                  "gemm: A/W/bias/C must be 16-byte aligned");
   if (epilogue == EPI_TOPK)
     CAPDEC_REQUIRE(a.tk_part && (((uintptr_t)a.tk_part) & 15) == 0 && tk_supported(a.N, a.tk_k), CAPDEC_ERR_INVALID,
-                   "gemm: EPI_TOPK needs an aligned partial buffer, 1 <= k <= 16 and N <= 65536 (k=%d N=%d)", a.tk_k, a.N);
-  const int terms = precision == CAPDEC_PREC_TF32X3 ? 3 : 1;
+                   "gemm: EPI_TOPK needs an aligned partial buffer, 1 <= k <= 16 and N <= 131072 (k=%d N=%d)", a.tk_k, a.N);
+  const int terms = (precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_BF16X3) ? 3 : 1;
+  const int kind = (precision == CAPDEC_PREC_BF16 || precision == CAPDEC_PREC_BF16X3) ? KIND_BF16 : KIND_TF32;
+  const size_t es = kind == KIND_BF16 ? 2 : 4;
   const int K = a.K;
+  const int Kp = kind == KIND_BF16 ? (K + 7) & ~7 : K;   // operand rows must be multiples of 16 bytes for TMA
 
   // ---- weight split: cached per handle (weights are immutable after capdec_finalize)
-  float *w_hi = nullptr, *w_lo = nullptr;
-  const size_t w_elems = (size_t)a.N * K;
+  char *w_hi = nullptr, *w_lo = nullptr;
+  const size_t w_bytes = align_up((size_t)a.N * Kp * es, 256);
   if (h) {
     auto it = h->tc_weights.find(a.W);
     if (it == h->tc_weights.end()) {
       float* buf = nullptr;
-      CAPDEC_CHECK_CUDA(cudaMalloc((void**)&buf, 2 * w_elems * sizeof(float)));
-      CAPDEC_RETURN_IF(split_tf32(a.W, a.ldw, a.N, K, buf, buf + w_elems, s));
+      CAPDEC_CHECK_CUDA(cudaMalloc((void**)&buf, 2 * w_bytes));
+      CAPDEC_RETURN_IF(split_operand(kind, a.W, a.ldw, a.N, K, Kp, buf, terms == 3 ? (char*)buf + w_bytes : nullptr, s));
       h->tc_weights[a.W] = buf;
       it = h->tc_weights.find(a.W);
     }
-    w_hi = it->second; w_lo = w_hi + w_elems;
+    w_hi = (char*)it->second; w_lo = w_hi + w_bytes;
   }
   // ---- activation split scratch, M chunked so the scratch stays <= ~1 GiB
   const size_t cap_bytes = (size_t)1 << 30;
-  int m_chunk = (int)((cap_bytes / (2 * (size_t)K * sizeof(float))) / BM * BM);
-  if (m_chunk < BM) m_chunk = BM;
+  int m_chunk = (int)((cap_bytes / (2 * (size_t)Kp * es)) / (2 * BM) * (2 * BM));
+  if (m_chunk < 2 * BM) m_chunk = 2 * BM;
   if (m_chunk > a.M) m_chunk = a.M;
-  const size_t a_elems = (size_t)m_chunk * K;
-  float* scratch = nullptr;
+  const size_t a_bytes = align_up((size_t)m_chunk * Kp * es, 256);
+  char* scratch = nullptr;
   if (h) {
-    CAPDEC_RETURN_IF(ensure(&h->tc_scratch, &h->tc_scratch_bytes, 2 * a_elems * sizeof(float)));
-    scratch = h->tc_scratch;
+    CAPDEC_RETURN_IF(ensure(&h->tc_scratch, &h->tc_scratch_bytes, 2 * a_bytes));
+    scratch = (char*)h->tc_scratch;
   } else {
-    CAPDEC_RETURN_IF(ensure(&g_scratch.p, &g_scratch.bytes, (2 * a_elems + 2 * w_elems) * sizeof(float)));
-    scratch = g_scratch.p;
-    w_hi = scratch + 2 * a_elems; w_lo = w_hi + w_elems;
-    CAPDEC_RETURN_IF(split_tf32(a.W, a.ldw, a.N, K, w_hi, w_lo, s));
+    CAPDEC_RETURN_IF(ensure(&g_scratch.p, &g_scratch.bytes, 2 * a_bytes + 2 * w_bytes));
+    scratch = (char*)g_scratch.p;
+    w_hi = scratch + 2 * a_bytes; w_lo = w_hi + w_bytes;
+    CAPDEC_RETURN_IF(split_operand(kind, a.W, a.ldw, a.N, K, Kp, w_hi, terms == 3 ? w_lo : nullptr, s));
   }
-  float* a_hi = scratch;
-  float* a_lo = scratch + a_elems;
+  char* a_hi = scratch;
+  char* a_lo = scratch + a_bytes;
 
-  const int bn = (a.N <= 128 && epilogue != EPI_TOPK) ? 128 : 256;
-  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work and a 256-wide tile
+  constexpr int bn = 256;
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work
   static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
-  const int cg = (bn == 256 && a.M > BM && !no_pair) ? 2 : 1;
+  const int cg = (a.M > BM && !no_pair) ? 2 : 1;
   CUtensorMap map_w_hi, map_w_lo;
-  CAPDEC_RETURN_IF(make_map(&map_w_hi, w_hi, a.N, K, K, bn / cg));
-  CAPDEC_RETURN_IF(make_map(&map_w_lo, w_lo, a.N, K, K, bn / cg));
+  CAPDEC_RETURN_IF(make_map(&map_w_hi, kind, w_hi, a.N, Kp, Kp, bn / cg));
+  CAPDEC_RETURN_IF(make_map(&map_w_lo, kind, terms == 3 ? w_lo : w_hi, a.N, Kp, Kp, bn / cg));
 
   for (int m0 = 0; m0 < a.M; m0 += m_chunk) {
     const int mc = a.M - m0 < m_chunk ? a.M - m0 : m_chunk;
-    CAPDEC_RETURN_IF(split_tf32(a.A + (int64_t)m0 * a.lda, a.lda, mc, K, a_hi, a_lo, s));
+    CAPDEC_RETURN_IF(split_operand(kind, a.A + (int64_t)m0 * a.lda, a.lda, mc, K, Kp, a_hi, terms == 3 ? a_lo : nullptr, s));
     CUtensorMap map_a_hi, map_a_lo;
-    CAPDEC_RETURN_IF(make_map(&map_a_hi, a_hi, mc, K, K, BM));
-    CAPDEC_RETURN_IF(make_map(&map_a_lo, a_lo, mc, K, K, BM));
+    CAPDEC_RETURN_IF(make_map(&map_a_hi, kind, a_hi, mc, Kp, Kp, BM));
+    CAPDEC_RETURN_IF(make_map(&map_a_lo, kind, terms == 3 ? a_lo : a_hi, mc, Kp, Kp, BM));
     GemmArgs g = a;
     g.M = mc;
+    g.K = Kp;
     g.C = a.C + (int64_t)m0 * a.ldc;
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
     if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
     if (a.tk_part) g.tk_part = a.tk_part + (int64_t)m0 * tk_tiles(a.N) * tk_stride(a.tk_k);
     int st;
-    if (bn == 128)    st = terms == 3 ? launch_tc<128, 3, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
-                                      : launch_tc<128, 1, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
-    else if (cg == 1) st = terms == 3 ? launch_tc<256, 3, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
-                                      : launch_tc<256, 1, 1>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
-    else              st = terms == 3 ? launch_tc<256, 3, 2>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
-                                      : launch_tc<256, 1, 2>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s);
+#define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+    if (kind == KIND_TF32) {
+      if (cg == 1) st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 1, KIND_TF32) : CAPDEC_TC_DISPATCH(1, 1, KIND_TF32);
+      else         st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 2, KIND_TF32) : CAPDEC_TC_DISPATCH(1, 2, KIND_TF32);
+    } else {
+      if (cg == 1) st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 1, KIND_BF16) : CAPDEC_TC_DISPATCH(1, 1, KIND_BF16);
+      else         st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 2, KIND_BF16) : CAPDEC_TC_DISPATCH(1, 2, KIND_BF16);
+    }
+#undef CAPDEC_TC_DISPATCH
     CAPDEC_RETURN_IF(st);
   }
   return CAPDEC_OK;

@@ -14,6 +14,8 @@ struct DevTensor {
   int64_t numel = 0;
 };
 
+constexpr int kHostBufs = 3;   // staging buffers of the host-buffer entry point
+
 struct capdec_handle {
   capdec_config cfg{};
   std::map<std::string, DevTensor> w;  // reference state_dict name -> owned device copy
@@ -35,7 +37,7 @@ struct capdec_handle {
   // ---- host-API staging (capdec_decode_beam_host) ----
   void* stage_dev = nullptr; size_t stage_bytes = 0;
   cudaStream_t stream_compute = nullptr, stream_copy = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[kHostBufs] = {}, ev_done[kHostBufs] = {};
 
   // ---- optional per-stage device timing (capdec_stage_timing): cudaEvent pairs around every stage launch
   mutable bool timing = false;

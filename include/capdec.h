@@ -59,8 +59,10 @@ typedef enum {
 typedef enum {
   CAPDEC_PREC_FP32 = 0,    /* CUDA-core FFMA, IEEE fp32 accumulate: the exact mode            */
   CAPDEC_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
-  CAPDEC_PREC_BF16 = 2,    /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate (not built yet: UNSUPPORTED) */
-  CAPDEC_PREC_TF32 = 3     /* tcgen05 kind::tf32 single pass on round-to-nearest TF32 operands, fp32 accumulate */
+  CAPDEC_PREC_BF16 = 2,    /* tcgen05 kind::f16 on round-to-nearest bf16 operands, fp32 accumulate (north star "bf16 mode") */
+  CAPDEC_PREC_TF32 = 3,    /* tcgen05 kind::tf32 single pass on round-to-nearest TF32 operands, fp32 accumulate */
+  CAPDEC_PREC_BF16X3 = 4   /* tcgen05 kind::f16, 3-term bf16 split (hi*hi + hi*lo + lo*hi): ~16 mantissa bits per operand,
+                              fp32 accumulate, at half the tensor time of TF32X3 */
 } capdec_precision;
 
 typedef struct {

@@ -21,8 +21,10 @@ LOGP_TOL = 1e-3
 # Random-init decoders have nearly flat logits, so a few argmax decisions sit on near-ties that no two fp32
 # implementations (here: oneDNN on the CPU vs CUDA) resolve alike.  A token divergence is excused only when the
 # oracle's own top-1/top-2 gap at that step is below this fraction of its logit spread; everything else fails.
-MARGIN_EXCUSE = {"fp32": 2e-3, "tf32x3": 2e-2}
-PRECISIONS = ["fp32", "tf32x3"]     # exact CUDA-core mode and the tcgen05 3xTF32 split mode (fp32-equivalent)
+MARGIN_EXCUSE = {"fp32": 2e-3, "tf32x3": 2e-2, "bf16x3": 2e-2}
+# exact CUDA-core mode, the tcgen05 3xTF32 split mode (fp32-equivalent) and the tcgen05 3-term bf16 split mode (~16
+# mantissa bits per operand, fp32 accumulate) -- all three are held to the fp32-mode tolerances of the north star
+PRECISIONS = ["fp32", "tf32x3", "bf16x3"]
 
 
 def _rna_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -44,17 +46,20 @@ def test_linear_fp32(cuda, M, N, K):
     assert err < 2e-5 * (K ** 0.5), err
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "bf16", "bf16x3"])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 64), (1, 4, 4), (37, 10000, 512), (300, 2048, 3072),
-                                   (129, 2560, 512), (5, 50257, 768), (1000, 512, 2048), (260, 128, 100)])
+                                   (129, 2560, 512), (5, 50257, 768), (1000, 512, 2048), (260, 128, 100), (513, 300, 72)])
 def test_linear_tcgen05(cuda, precision, M, N, K):
-    """tcgen05 GEMM (TMA -> smem -> UTCMMA -> TMEM -> registers): single-pass TF32 must equal the product of
-    the TF32-rounded operands, the 3-term split must be fp32-accurate."""
+    """tcgen05 GEMM (TMA -> smem -> UTCMMA -> TMEM -> registers, CTA pairs above 128 rows): a single-pass mode must
+    equal the product of its rounded operands (fp32 accumulate), the 3xTF32 split must be fp32-accurate and the 3-term
+    bf16 split accurate to ~2^-16 per product."""
     g = torch.Generator().manual_seed(M + N + K)
     a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
     out = eng_mod.linear(a.to(cuda), w.to(cuda), b.to(cuda), precision=precision).cpu()
     if precision == "tf32":
         ref = (_rna_tf32(a).double() @ _rna_tf32(w).double().t() + b.double()).float()
+    elif precision == "bf16":
+        ref = (a.bfloat16().double() @ w.bfloat16().double().t() + b.double()).float()
     else:
         ref = (a.double() @ w.double().t() + b.double()).float()
     err = (out - ref).abs().max().item()
@@ -73,7 +78,7 @@ def test_lse_topk(cuda, R, V, K):
     assert torch.allclose(lse.cpu(), torch.logsumexp(x, -1), atol=1e-5)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "bf16x3"])
 @pytest.mark.parametrize("M,N,K,topk", [(37, 10000, 512, 10), (300, 10000, 512, 6), (5, 50257, 768, 10), (129, 1000, 64, 1),
                                         (64, 300, 128, 16), (3, 7, 32, 10), (260, 4096, 256, 10)])
 def test_linear_topk_fused(cuda, precision, M, N, K, topk):
