@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="capdec", choices=["capdec", "reference"])
     ap.add_argument("--images", type=int, default=env_int("CAPDEC_BENCH_IMAGES", 4096), help="images per GPU")
-    ap.add_argument("--precision", default=os.environ.get("CAPDEC_BENCH_PRECISION", "tf32x3"))
+    ap.add_argument("--precision", default=os.environ.get("CAPDEC_BENCH_PRECISION", "bf16x3"))
     ap.add_argument("--chunk", type=int, default=env_int("CAPDEC_BENCH_CHUNK", 512), help="e2e H2D pipeline chunk (images)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
