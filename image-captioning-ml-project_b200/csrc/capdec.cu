@@ -135,7 +135,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   if (want_k > 0 && c.precision != CAPDEC_PREC_FP32 && tk_supported(V, want_k) && !getenv("CAPDEC_NO_FUSED_TOPK"))
     S.fuse_k = want_k;
   auto take_logits = [&]() {
-    if (S.fuse_k > 0) S.tk_part = ar.take<float>(R * tk_tiles(V) * tk_stride(S.fuse_k));
+    if (S.fuse_k > 0) S.tk_part = ar.take<float>(R * tk_records(S.R, V) * tk_stride(S.fuse_k));
     else S.logits = ar.take<float>(R * V);
   };
   if (is_tf_family(h)) {
@@ -1196,7 +1196,7 @@ int capdec_linear(int32_t precision, const float* a, int64_t lda, const float* w
 
 size_t capdec_linear_topk_workspace(int32_t m, int32_t n, int32_t topk) {
   if (m < 0 || !tk_supported(n, topk)) return 0;
-  return align_up((size_t)m * tk_tiles(n) * tk_stride(topk) * sizeof(float) + 256, 256);
+  return align_up((size_t)m * tk_records(m, n) * tk_stride(topk) * sizeof(float) + 256, 256);
 }
 
 int capdec_linear_topk(int32_t precision, const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,

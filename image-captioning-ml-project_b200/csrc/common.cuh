@@ -88,15 +88,16 @@ enum Epilogue : int {
   EPI_GELU_TANH = 6,     // tanh-approximated GELU ("gelu_new")    (HF GPT-2 MLP)
   EPI_TOPK = 7           // vocabulary projection fused with log-softmax partials + per-row top-k: the logits never
                          // reach HBM.  Per (row, 128-column half tile) the epilogue emits {max, sum exp(x-max), top-TK values,
-                         // top-TK indices}; topk_merge (select.cu) combines the tiles.  Tensor-core path only.
+                         // top-TK indices}; topk_merge (select.cu) combines the records.  Tensor-core path only.
 };
 
 // ---- fused vocab top-k partial records (EPI_TOPK) ---------------------------------------------------------
-constexpr int kTkTileCols = 128;   // == BN/2 of the tcgen05 kernel: one record per (row, epilogue-warp column half)
+// The GEMM's CTA groups own contiguous runs of tiles, so a row block's n tiles fall into at most a few runs; per
+// (row, run, 128-column-parity half) the epilogue emits one record {max, sum exp(x-max), top-TK values, top-TK indices}.
 static inline int tk_bucket(int k) { return k <= 1 ? 1 : k <= 6 ? 6 : k <= 10 ? 10 : 16; }   // compiled list lengths
 static inline int tk_stride(int k) { return (2 + 2 * tk_bucket(k) + 3) & ~3; }              // floats per record
-static inline int tk_tiles(int vocab) { return (vocab + kTkTileCols - 1) / kTkTileCols; }
-static inline bool tk_supported(int vocab, int k) { return k >= 1 && k <= 16 && tk_tiles(vocab) <= 1024; }
+int tk_records(int M, int N);                                                              // records per row (gemm_tc.cu)
+static inline bool tk_supported(int vocab, int k) { return k >= 1 && k <= 16 && vocab >= 1; }
 
 struct GemmArgs {
   const float* A; int64_t lda;      // [M,K]
@@ -108,7 +109,7 @@ struct GemmArgs {
   const float* c_in; int64_t ldcin; // EPI_LSTM: previous cell state [M,H]
   float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
   float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
-  float* tk_part; int tk_k;         // EPI_TOPK: partial records [M, tk_tiles(N), tk_stride(tk_k)], requested list length
+  float* tk_part; int tk_k;         // EPI_TOPK: partial records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
 };
 
 int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s);

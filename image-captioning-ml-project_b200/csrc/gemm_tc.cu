@@ -136,7 +136,10 @@ struct SmemLayout {
   static constexpr uint32_t kWBytes = (BN / CG) * kRowBytes;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kStashOffset = kBarOffset + 256;   // EPI_TOPK only: 8 warps x 32 columns x 32 lanes floats
+  static constexpr uint32_t kStashBytes = 8 * 32 * 32 * 4;
   static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
+  static constexpr uint32_t kTotalTopk = kTotal + kStashBytes;
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
@@ -163,6 +166,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   constexpr int TM = BM * CG;                                // output tile rows per CTA group
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = n_tiles * ((p.M + TM - 1) / TM);
+  // Every CTA group owns one CONTIGUOUS run of `quota` tiles in m-major order (n fastest): consecutive tiles reuse the
+  // same A rows from L2, and the epilogue threads (thread == output row) can carry per-row state across the n tiles of a
+  // row block -- the fused vocabulary top-k keeps ONE candidate list per row and column half for the whole run.
+  // The other epilogues keep the interleaved order (tile = group + i * num_groups): the groups running concurrently then
+  // work on neighbouring tiles and their requests for the same A / W blocks coalesce in L2, which matters because the
+  // 3-term main loop runs at the L2 -> shared-memory bandwidth limit.
+  constexpr bool kContiguous = EPI == EPI_TOPK;
+  const int quota = (num_tiles + num_groups - 1) / num_groups;
+  const int tile_begin = kContiguous ? min(group * quota, num_tiles) : group;
+  const int tile_end = kContiguous ? min(tile_begin + quota, num_tiles) : num_tiles;
+  const int tile_step = kContiguous ? 1 : num_groups;
   constexpr int BK = KIND == KIND_BF16 ? 64 : 32;   // elements per 128-byte K block
   const int num_kb = (p.K + BK - 1) / BK;
   constexpr uint32_t kTmemCols = 2 * BN;           // 256 or 512: a power of two >= 32
@@ -196,7 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // ===== TMA producer (both CTAs of a pair: own 128 rows of A, own BN/CG rows of W) =====
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter across tiles -> ring stage / phase
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
         const int a_row = m_tile * TM + (int)rank * BM;
         const int w_row = n_tile * BN + (int)rank * (BN / CG);
@@ -237,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       };
       auto commit = [&](uint64_t* bar) { if (CG == 2) tcgen05_commit_pair(bar); else tcgen05_commit(bar); };
       uint32_t it = 0, local = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
         const uint32_t ab = local & 1;                       // accumulator buffer
         mbar_wait(&tmem_empty_bar[ab], ((local >> 1) & 1) ^ 1);  // the epilogue warps (of both CTAs) drained this buffer
         tcgen05_fence_after();
@@ -276,19 +290,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     constexpr int HN = BN / 2;
     uint32_t local = 0;
     const uint32_t leader_empty_bar0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
-    for (int tile = group; tile < num_tiles; tile += num_groups, ++local) {
+    float* stash = reinterpret_cast<float*>(smem + SL::kStashOffset);   // (allocated for EPI_TOPK launches only)
+    // EPI_TOPK state carried across the tiles of one row block: online log-sum-exp and a sorted top-TK list of this
+    // thread's row over the columns of this warp's column half
+    float rmax = -INFINITY, rsum = 0.f;
+    float tv[TK > 0 ? TK : 1];
+    int ti[TK > 0 ? TK : 1];
+    int cur_block = -1;
+    auto tk_reset = [&]() {
+      rmax = -INFINITY; rsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < (TK > 0 ? TK : 1); ++j) { tv[j] = -INFINITY; ti[j] = INT_MAX; }
+    };
+    auto tk_flush = [&](int block) {
+      // record of (row, run segment of the block, column half): {max, sum exp(x - max), TK values, TK indices}
+      constexpr int PS = (2 + 2 * (TK > 0 ? TK : 1) + 3) & ~3;
+      const int row = block * TM + (int)rank * BM + q * 32 + lane;
+      if (row >= p.M) return;
+      const int slot = group - (block * n_tiles) / quota;   // which CTA group's run inside this row block
+      const int n_rec = 2 * ((n_tiles + quota - 1) / quota + 1);
+      float rec[PS];
+      rec[0] = rmax; rec[1] = rsum;
+#pragma unroll
+      for (int j = 0; j < TK; ++j) { rec[2 + j] = tv[j]; rec[2 + TK + j] = __int_as_float(ti[j]); }
+#pragma unroll
+      for (int j = 2 + 2 * TK; j < PS; ++j) rec[j] = 0.f;
+      float4* dst = reinterpret_cast<float4*>(p.tk_part + ((int64_t)row * n_rec + slot * 2 + half) * PS);
+#pragma unroll
+      for (int j = 0; j < PS / 4; ++j) dst[j] = make_float4(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3]);
+    };
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
       const uint32_t ab = local & 1;
       mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
       tcgen05_fence_after();
       const int m = m_tile * TM + (int)rank * BM + q * 32 + lane;   // accumulator row == TMEM lane of this CTA
-      // EPI_TOPK state: online log-sum-exp and a sorted top-TK list of this row over the tile's BN columns
-      float rmax = -INFINITY, rsum = 0.f;
-      float tv[TK > 0 ? TK : 1];
-      int ti[TK > 0 ? TK : 1];
-      if (EPI == EPI_TOPK) {
-#pragma unroll
-        for (int j = 0; j < TK; ++j) { tv[j] = -INFINITY; ti[j] = INT_MAX; }
+      if constexpr (EPI == EPI_TOPK) {
+        if (m_tile != cur_block) {
+          if (cur_block >= 0) tk_flush(cur_block);
+          tk_reset();
+          cur_block = m_tile;
+        }
       }
 #pragma unroll 1
       for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
@@ -342,23 +384,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             if (cm > rmax) { rsum *= __expf(rmax - cm); rmax = cm; }   // x[0] is always a real column, so cm is finite
 #pragma unroll
             for (int j = 0; j < 32; ++j) rsum += __expf(x[j] - rmax);
+            // Candidates of this chunk: columns above the row's current TK-th best.  Lanes (rows) find theirs at
+            // different columns, so walking the columns in lockstep would make the warp pay for the union; instead the
+            // chunk is parked in shared memory ([column][lane], conflict-free) and every lane pops ITS next candidate per
+            // round -- the number of rounds is the largest per-lane count, not the size of the union.
+            float* st = stash + (size_t)(warp - 2) * 1024 + lane;
+            unsigned cand = 0u;
+            const float thr = tv[TK - 1];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (x[j] > tv[TK - 1]) {
-                // branch-free sorted insert (every list position is independent, so the ALU latency pipelines):
-                // x lands behind any equal value, i.e. among equal logits the lower vocabulary index stays ahead
-                const float xv = x[j];
-                const int xi = n0 + j;
-                bool gt[TK];
+              st[j * 32] = x[j];
+              cand |= (x[j] > thr ? 1u : 0u) << j;
+            }
+            while (__any_sync(0xffffffffu, cand != 0u)) {
+              if (cand != 0u) {
+                const int j = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                const float xv = st[j * 32];
+                if (xv > tv[TK - 1]) {
+                  // branch-free sorted insert: x lands behind any equal value, so the lower vocabulary index stays
+                  // ahead among equal logits (columns are popped in increasing order)
+                  const int xi = n0 + j;
+                  bool gt[TK];
 #pragma unroll
-                for (int t = 0; t < TK; ++t) gt[t] = xv > tv[t];
+                  for (int t = 0; t < TK; ++t) gt[t] = xv > tv[t];
 #pragma unroll
-                for (int t = TK - 1; t > 0; --t) {
-                  ti[t] = gt[t] ? (gt[t - 1] ? ti[t - 1] : xi) : ti[t];
-                  tv[t] = fmaxf(tv[t], fminf(tv[t - 1], xv));
+                  for (int t = TK - 1; t > 0; --t) {
+                    ti[t] = gt[t] ? (gt[t - 1] ? ti[t - 1] : xi) : ti[t];
+                    tv[t] = fmaxf(tv[t], fminf(tv[t - 1], xv));
+                  }
+                  ti[0] = gt[0] ? xi : ti[0];
+                  tv[0] = fmaxf(tv[0], xv);
                 }
-                ti[0] = gt[0] ? xi : ti[0];
-                tv[0] = fmaxf(tv[0], xv);
               }
             }
           } else {
@@ -369,21 +426,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           }
         }
       }
-      if constexpr (EPI == EPI_TOPK) if (m < p.M && n_tile * BN + half * HN < p.N) {
-        // partial record of (row m, tile n_tile): {max, sum exp(x - max), TK values, TK indices}, 16-byte stores
-        constexpr int PS = (2 + 2 * TK + 3) & ~3;
-        float rec[PS];
-        rec[0] = rmax; rec[1] = rsum;
-#pragma unroll
-        for (int j = 0; j < TK; ++j) { rec[2 + j] = tv[j]; rec[2 + TK + j] = __int_as_float(ti[j]); }
-#pragma unroll
-        for (int j = 2 + 2 * TK; j < PS; ++j) rec[j] = 0.f;
-        const int n_rec = (p.N + HN - 1) / HN;    // records are per (row, BN/2-column half tile)
-        const int rec_id = n_tile * 2 + half;
-        float4* dst = reinterpret_cast<float4*>(p.tk_part + ((int64_t)m * n_rec + rec_id) * PS);
-#pragma unroll
-        for (int j = 0; j < PS / 4; ++j) dst[j] = make_float4(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3]);
-      }
+    }
+    if constexpr (EPI == EPI_TOPK) {
+      if (cur_block >= 0) tk_flush(cur_block);
     }
   }
   tcgen05_fence_before();
@@ -494,35 +539,48 @@ int num_sms() {
   return n;
 }
 
-// number of CTA pairs the device can keep resident for a pair-mode kernel (clusters of 2 need both SMs of a TPC)
-template <typename Kern>
-int max_active_pairs(Kern kern, int smem) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * num_sms()); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+// CTA groups one launch may keep resident: every SM for single CTAs; for pairs, what the occupancy calculator grants
+// clusters of 2 (both SMs of a TPC).  All instantiations of a mode share thread count and shared-memory size, so one
+// representative kernel answers for all of them.  tk_records() (the EPI_TOPK record layout) depends on this number.
+int tc_max_groups(int cg) {
+  static int cache[3] = {0, 0, 0};
+  if (cache[cg]) return cache[cg];
+  if (cg == 1) return cache[1] = num_sms();
+  auto kern = gemm_tcgen05_kernel<256, EPI_STORE, 3, 0, 2, KIND_TF32>;
+  constexpr int smem = SmemLayout<256, 2>::kTotal;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
-  return n;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * num_sms()); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  cudaGetLastError();
+  if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
+  return cache[2] = n;
+}
+int tc_cta_group(int M) {
+  static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
+  return (M > BM && !no_pair) ? 2 : 1;   // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile
 }
 
 template <int BN, int TERMS, int CG, int KIND>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
               const GemmArgs& g, int epi, cudaStream_t s) {
-  constexpr int smem = SmemLayout<BN, CG>::kTotal;
   const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM * CG);
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
-    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                       \
+    auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                 \
+    constexpr int smem = E == EPI_TOPK ? SmemLayout<BN, CG>::kTotalTopk : SmemLayout<BN, CG>::kTotal;             \
     static bool configured = false;                                                                               \
-    static int max_groups = 0;                                                                                    \
     if (!configured) {                                                                                            \
       CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
-      max_groups = CG == 2 ? max_active_pairs(kern, smem) : num_sms();                                            \
       configured = true;                                                                                          \
     }                                                                                                             \
+    const int max_groups = tc_max_groups(CG);                                                                     \
     const int groups = num_tiles < max_groups ? num_tiles : max_groups;                                           \
     cudaLaunchConfig_t cfg = {};                                                                                  \
     cfg.gridDim = dim3(groups * CG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
@@ -542,7 +600,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     CAPDEC_TC_CASE(EPI_GELU)
     CAPDEC_TC_CASE(EPI_GELU_TANH)
     case EPI_TOPK:
-      if constexpr (BN == 2 * kTkTileCols) {   // the record layout is defined on halves of 256-column tiles
+      if constexpr (BN == 256) {   // the record layout is defined on the column halves of 256-column tiles
         switch (tk_bucket(g.tk_k)) {
           case 1: CAPDEC_TC_LAUNCH(EPI_TOPK, 1) break;
           case 6: CAPDEC_TC_LAUNCH(EPI_TOPK, 6) break;
@@ -577,6 +635,17 @@ int ensure(float** p, size_t* have, size_t need) {
 }
 
 }  // namespace
+
+// records per row the EPI_TOPK epilogue writes for an [M,N] problem: 2 column halves x (runs a row block can span)
+int tk_records(int M, int N) {
+  if (M <= 0) return 2;
+  const int cg = tc_cta_group(M);
+  const int n_tiles = ceil_div(N, 256), num_tiles = n_tiles * ceil_div(M, BM * cg);
+  const int max_groups = tc_max_groups(cg);
+  const int groups = num_tiles < max_groups ? num_tiles : max_groups;
+  const int quota = ceil_div(num_tiles, groups);
+  return 2 * (ceil_div(n_tiles, quota) + 1);
+}
 
 int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s) {
   CAPDEC_REQUIRE(precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_TF32 || precision == CAPDEC_PREC_BF16 ||
@@ -633,9 +702,12 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   char* a_lo = scratch + a_bytes;
 
   constexpr int bn = 256;
-  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work
-  static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
-  const int cg = (a.M > BM && !no_pair) ? 2 : 1;
+  const int cg = tc_cta_group(a.M);
+  if (epilogue == EPI_TOPK) {
+    CAPDEC_REQUIRE(a.M <= m_chunk, CAPDEC_ERR_UNSUPPORTED, "gemm: EPI_TOPK with %d rows exceeds the single-launch limit %d", a.M, m_chunk);
+    // slots a launch does not write (row blocks that fall into a single run) must read as empty: NaN sum, index -1
+    CAPDEC_CHECK_CUDA(cudaMemsetAsync(a.tk_part, 0xFF, (size_t)a.M * tk_records(a.M, a.N) * tk_stride(a.tk_k) * sizeof(float), s));
+  }
   CUtensorMap map_w_hi, map_w_lo;
   CAPDEC_RETURN_IF(make_map(&map_w_hi, kind, w_hi, a.N, Kp, Kp, bn / cg));
   CAPDEC_RETURN_IF(make_map(&map_w_lo, kind, terms == 3 ? w_lo : w_hi, a.N, Kp, Kp, bn / cg));
@@ -653,7 +725,6 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
     if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
-    if (a.tk_part) g.tk_part = a.tk_part + (int64_t)m0 * tk_tiles(a.N) * tk_stride(a.tk_k);
     int st;
 #define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
     if (kind == KIND_TF32) {

@@ -10,7 +10,7 @@ constexpr int kMaxTopK = 16;  // 2 * max beams
 int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, float* out_lp, int32_t* out_idx,
              float* out_lse, cudaStream_t s);
 
-// fused path: merge the EPI_TOPK partial records [rows, tk_tiles(vocab), tk_stride(part_k)] written by the vocabulary
+// fused path: merge the EPI_TOPK partial records [rows, tk_records(rows, vocab), tk_stride(part_k)] written by the vocabulary
 // GEMM (gemm_tc.cu) into the same outputs as lse_topk; the logits themselves never exist in HBM
 int topk_merge(const float* part, int rows, int vocab, int part_k, int topk, float* out_lp, int32_t* out_idx,
                float* out_lse, cudaStream_t s);
