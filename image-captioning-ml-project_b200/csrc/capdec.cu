@@ -117,7 +117,7 @@ struct Session {
   int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
-  float* tk_part = nullptr; int fuse_k = 0;
+  float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
@@ -135,7 +135,10 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   if (want_k > 0 && c.precision != CAPDEC_PREC_FP32 && tk_supported(V, want_k) && !getenv("CAPDEC_NO_FUSED_TOPK"))
     S.fuse_k = want_k;
   auto take_logits = [&]() {
-    if (S.fuse_k > 0) S.tk_part = ar.take<float>(R * tk_records(S.R, V) * tk_stride(S.fuse_k));
+    if (S.fuse_k > 0) {
+      S.tk_part = ar.take<float>(R * tk_records(S.R, V) * tk_stride(S.fuse_k));
+      S.tk_lse = ar.take<float>(R * tk_lse_pairs(V) * 2);
+    }
     else S.logits = ar.take<float>(R * V);
   };
   if (is_tf_family(h)) {
@@ -246,7 +249,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
   g.A = A; g.lda = lda; g.W = W; g.ldw = c.hidden_dim; g.bias = bias; g.M = rows; g.N = c.vocab_size; g.K = c.hidden_dim;
   if (logits == nullptr) {
     CAPDEC_REQUIRE(S.fuse_k > 0 && S.tk_part, CAPDEC_ERR_STATE, "vocab_project: no logits buffer and no fused top-k buffer");
-    g.tk_part = S.tk_part; g.tk_k = S.fuse_k;
+    g.tk_part = S.tk_part; g.tk_k = S.fuse_k; g.tk_lse = S.tk_lse;
     return gemm(h, c.precision, g, EPI_TOPK, s);
   }
   g.C = logits; g.ldc = ld_logits;
@@ -256,7 +259,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
 // per-row sorted top-`topk` log-probs of the step's vocabulary distribution
 int select_topk(const capdec_handle* h, Session& S, int topk, float* out_lp, int32_t* out_idx, cudaStream_t s) {
   const int V = h->cfg.vocab_size;
-  if (S.fuse_k > 0) return topk_merge(S.tk_part, S.R, V, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
+  if (S.fuse_k > 0) return topk_merge(S.tk_part, S.tk_lse, S.R, V, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
   return lse_topk(S.logits, V, S.R, V, topk, out_lp, out_idx, nullptr, s);
 }
 
@@ -1196,7 +1199,8 @@ int capdec_linear(int32_t precision, const float* a, int64_t lda, const float* w
 
 size_t capdec_linear_topk_workspace(int32_t m, int32_t n, int32_t topk) {
   if (m < 0 || !tk_supported(n, topk)) return 0;
-  return align_up((size_t)m * tk_records(m, n) * tk_stride(topk) * sizeof(float) + 256, 256);
+  return align_up((size_t)m * tk_records(m, n) * tk_stride(topk) * sizeof(float), 256) +
+         align_up((size_t)m * tk_lse_pairs(n) * 2 * sizeof(float), 256) + 256;
 }
 
 int capdec_linear_topk(int32_t precision, const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,
@@ -1210,8 +1214,9 @@ int capdec_linear_topk(int32_t precision, const float* a, int64_t lda, const flo
   GemmArgs g{};
   g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.M = m; g.N = n; g.K = k;
   g.tk_part = (float*)ws; g.tk_k = topk;
+  g.tk_lse = (float*)((char*)ws + align_up((size_t)m * tk_records(m, n) * tk_stride(topk) * sizeof(float), 256));
   CAPDEC_RETURN_IF(gemm(nullptr, precision, g, EPI_TOPK, (cudaStream_t)stream));
-  return topk_merge((const float*)ws, m, n, topk, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
+  return topk_merge(g.tk_part, g.tk_lse, m, n, topk, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
 }
 
 int capdec_lse_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t topk, float* out_lp,

@@ -93,10 +93,12 @@ enum Epilogue : int {
 
 // ---- fused vocab top-k partial records (EPI_TOPK) ---------------------------------------------------------
 // The GEMM's CTA groups own contiguous runs of tiles, so a row block's n tiles fall into at most a few runs; per
-// (row, run, 128-column-parity half) the epilogue emits one record {max, sum exp(x-max), top-TK values, top-TK indices}.
+// (row, run, 128-column-parity half) the epilogue emits one candidate record {top-TK values, top-TK indices}; the
+// log-sum-exp partials {max, sum exp(x-max)} are emitted per (row, tile half) so their combination order is canonical.
 static inline int tk_bucket(int k) { return k <= 1 ? 1 : k <= 6 ? 6 : k <= 10 ? 10 : 16; }   // compiled list lengths
 static inline int tk_stride(int k) { return (2 + 2 * tk_bucket(k) + 3) & ~3; }              // floats per record
 int tk_records(int M, int N);                                                              // records per row (gemm_tc.cu)
+static inline int tk_lse_pairs(int vocab) { return 2 * ((vocab + 255) / 256); }                // 128-column halves of 256-column tiles
 static inline bool tk_supported(int vocab, int k) { return k >= 1 && k <= 16 && vocab >= 1; }
 
 struct GemmArgs {
@@ -109,7 +111,8 @@ struct GemmArgs {
   const float* c_in; int64_t ldcin; // EPI_LSTM: previous cell state [M,H]
   float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
   float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
-  float* tk_part; int tk_k;         // EPI_TOPK: partial records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
+  float* tk_part; int tk_k;         // EPI_TOPK: candidate records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
+  float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(N), 2]
 };
 
 int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s);

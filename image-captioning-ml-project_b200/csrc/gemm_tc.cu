@@ -303,14 +303,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       for (int j = 0; j < (TK > 0 ? TK : 1); ++j) { tv[j] = -INFINITY; ti[j] = INT_MAX; }
     };
     auto tk_flush = [&](int block) {
-      // record of (row, run segment of the block, column half): {max, sum exp(x - max), TK values, TK indices}
+      // record of (row, run segment of the block, column half): {0, 0, TK values, TK indices}
       constexpr int PS = (2 + 2 * (TK > 0 ? TK : 1) + 3) & ~3;
       const int row = block * TM + (int)rank * BM + q * 32 + lane;
       if (row >= p.M) return;
       const int slot = group - (block * n_tiles) / quota;   // which CTA group's run inside this row block
       const int n_rec = 2 * ((n_tiles + quota - 1) / quota + 1);
       float rec[PS];
-      rec[0] = rmax; rec[1] = rsum;
+      rec[0] = 0.f; rec[1] = 0.f;
 #pragma unroll
       for (int j = 0; j < TK; ++j) { rec[2 + j] = tv[j]; rec[2 + TK + j] = __int_as_float(ti[j]); }
 #pragma unroll
@@ -331,6 +331,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           tk_reset();
           cur_block = m_tile;
         }
+        rmax = -INFINITY; rsum = 0.f;   // log-sum-exp partials are per (row, tile half): see tk_lse below
       }
 #pragma unroll 1
       for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
@@ -425,6 +426,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                              __uint_as_float(v[j + 3]));
           }
         }
+      }
+      if constexpr (EPI == EPI_TOPK) {
+        // {max, sum exp(x - max)} of this row over this tile half.  Kept per tile (not folded along the run) so that the
+        // merge kernel can combine them in one canonical order: the result does not depend on how the tiles were
+        // distributed over CTA groups, i.e. a row decodes identically whatever the batch size.
+        if (m < p.M && n_tile * BN + half * HN < p.N)
+          *reinterpret_cast<float2*>(p.tk_lse + ((int64_t)m * (2 * n_tiles) + n_tile * 2 + half) * 2) = make_float2(rmax, rsum);
       }
     }
     if constexpr (EPI == EPI_TOPK) {
@@ -660,7 +668,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   CAPDEC_REQUIRE((((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.bias | (uintptr_t)a.C) & 15) == 0, CAPDEC_ERR_INVALID,
                  "gemm: A/W/bias/C must be 16-byte aligned");
   if (epilogue == EPI_TOPK)
-    CAPDEC_REQUIRE(a.tk_part && (((uintptr_t)a.tk_part) & 15) == 0 && tk_supported(a.N, a.tk_k), CAPDEC_ERR_INVALID,
+    CAPDEC_REQUIRE(a.tk_part && a.tk_lse && ((((uintptr_t)a.tk_part) | (uintptr_t)a.tk_lse) & 15) == 0 && tk_supported(a.N, a.tk_k), CAPDEC_ERR_INVALID,
                    "gemm: EPI_TOPK needs an aligned partial buffer, 1 <= k <= 16 and N <= 131072 (k=%d N=%d)", a.tk_k, a.N);
   const int terms = (precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_BF16X3) ? 3 : 1;
   const int kind = (precision == CAPDEC_PREC_BF16 || precision == CAPDEC_PREC_BF16X3) ? KIND_BF16 : KIND_TF32;
@@ -705,7 +713,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   const int cg = tc_cta_group(a.M);
   if (epilogue == EPI_TOPK) {
     CAPDEC_REQUIRE(a.M <= m_chunk, CAPDEC_ERR_UNSUPPORTED, "gemm: EPI_TOPK with %d rows exceeds the single-launch limit %d", a.M, m_chunk);
-    // slots a launch does not write (row blocks that fall into a single run) must read as empty: NaN sum, index -1
+    // slots a launch does not write (row blocks that fall into a single run) must read as empty: index -1
     CAPDEC_CHECK_CUDA(cudaMemsetAsync(a.tk_part, 0xFF, (size_t)a.M * tk_records(a.M, a.N) * tk_stride(a.tk_k) * sizeof(float), s));
   }
   CUtensorMap map_w_hi, map_w_lo;

@@ -105,9 +105,10 @@ __global__ void __launch_bounds__(kThreads) lse_topk_kernel(const float* __restr
 // Combine the partial records of the fused vocabulary GEMM (EPI_TOPK, gemm_tc.cu) into the row's log-sum-exp and
 // sorted top-K:  one warp per row; lane l owns records l, l+32, ... and keeps a read position per owned record in
 // shared memory; each of the K rounds is a warp arg-max over the lanes' best list heads (ties -> lower vocabulary
-// index, as torch.topk / the unfused kernel).  Slots the GEMM did not write carry the 0xFF fill (NaN sum) and are skipped.
+// index, as torch.topk / the unfused kernel).  Slots the GEMM did not write carry the 0xFF fill (index -1) and are skipped.
 constexpr int kMergeMaxRecords = 1024;
-__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ part, int n_rec, int PS, int TKB,
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ part, const float* __restrict__ lse_part,
+                                                         int n_lse, int vocab, int n_rec, int PS, int TKB,
                                                          int rows, int K, float* __restrict__ out_lp,
                                                          int32_t* __restrict__ out_idx, float* __restrict__ out_lse) {
   __shared__ uint8_t s_pos[4][kMergeMaxRecords];
@@ -116,17 +117,17 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
   if (row >= rows) return;
   const float* pr = part + (int64_t)row * n_rec * PS;
   uint8_t* pos = s_pos[warp];
+  // log-sum-exp from the per-(tile half) partials, in a fixed order: lane-strided sequential sums, then the shuffle tree
+  const float2* lp2 = reinterpret_cast<const float2*>(lse_part) + (int64_t)row * n_lse;
   float M = -INFINITY;
-  for (int t = lane; t < n_rec; t += 32) {
-    const bool valid = pr[(int64_t)t * PS + 1] >= 0.f;        // false for the NaN fill
-    pos[t] = valid ? 0 : 255;
-    if (valid) M = fmaxf(M, pr[(int64_t)t * PS]);
-  }
+  for (int t = lane; t < n_lse; t += 32)
+    if (t * 128 < vocab) M = fmaxf(M, lp2[t].x);
   M = warp_max(M);
   float S = 0.f;
-  for (int t = lane; t < n_rec; t += 32)
-    if (pos[t] != 255) S += pr[(int64_t)t * PS + 1] * expf(pr[(int64_t)t * PS] - M);
+  for (int t = lane; t < n_lse; t += 32)
+    if (t * 128 < vocab) { const float2 v = lp2[t]; S += v.y * expf(v.x - M); }
   S = warp_sum(S);
+  for (int t = lane; t < n_rec; t += 32) pos[t] = 0;
   const float logS = logf(S);
   if (lane == 0 && out_lse) out_lse[row] = M + logS;
 
@@ -451,13 +452,13 @@ int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, flo
   return CAPDEC_OK;
 }
 
-int topk_merge(const float* part, int rows, int vocab, int part_k, int topk, float* out_lp, int32_t* out_idx,
-               float* out_lse, cudaStream_t s) {
+int topk_merge(const float* part, const float* lse_part, int rows, int vocab, int part_k, int topk, float* out_lp,
+               int32_t* out_idx, float* out_lse, cudaStream_t s) {
   const int n_rec = tk_records(rows, vocab);
   CAPDEC_REQUIRE(tk_supported(vocab, part_k) && n_rec <= kMergeMaxRecords && topk >= 1 && topk <= tk_bucket(part_k), CAPDEC_ERR_INVALID,
                  "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
   if (rows == 0) return CAPDEC_OK;
-  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(part, n_rec, tk_stride(part_k), tk_bucket(part_k), rows,
+  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows,
                                                        topk, out_lp, out_idx, out_lse);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
