@@ -364,7 +364,9 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
 template <int KB>
 int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStream_t s) {
   const int nc = (a.D / 4 + kCtxThreads - 1) / kCtxThreads;
-  const int grid = a.B < sm_count() ? a.B : sm_count();
+  static const int cap = getenv("CAPDEC_ATTN_MAX_CTAS") ? atoi(getenv("CAPDEC_ATTN_MAX_CTAS")) : 0;   // experiments: SM partitioning
+  int grid = a.B < sm_count() ? a.B : sm_count();
+  if (cap > 0 && grid > cap) grid = cap;
 #define CAPDEC_STREAM_LAUNCH(ACTV, NCV)                                                                                   \
   {                                                                                                                       \
     auto kern = additive_attention_stream_kernel<KB, ACTV, NCV>;                                                          \

@@ -568,6 +568,7 @@ int tc_max_groups(int cg) {
   }
   cudaGetLastError();
   if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
+  if (const char* e = getenv("CAPDEC_GEMM_MAX_GROUPS")) { const int c = atoi(e); if (c > 0 && c < n) n = c; }   // experiments: SM partitioning
   return cache[2] = n;
 }
 int tc_cta_group(int M) {
