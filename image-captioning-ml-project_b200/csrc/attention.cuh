@@ -17,6 +17,8 @@ enum AddAct : int { ACT_RELU = 0, ACT_TANH = 1 };
 struct AddAttnArgs {
   const float* att1;                    // [B,L,A]  hoisted enc_att(enc) / key_proj(key), bias included
   const float* att2; int64_t ld_att2;   // [R,A]    dec_att(h) / query_proj(q), bias included
+  const int32_t* row_src;               // [R] or nullptr: att2 / gate of row r are read from row row_src[r] (the projections were
+                                        // computed before the beam reorder; the back-pointer is applied here instead of by a copy)
   const float* w;                       // [A]      att.weight / energy.weight
   float w_bias, temperature;
   const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) additive_attention_kernel(const AddA
   for (int i = tid; i < KB * A4; i += kThreads) {
     const int b = i / A4, a4 = i - b * A4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < k) v = *reinterpret_cast<const float4*>(p.att2 + (row0 + b) * p.ld_att2 + a4 * 4);
+    if (b < k) v = *reinterpret_cast<const float4*>(p.att2 + (p.row_src ? p.row_src[row0 + b] : row0 + b) * p.ld_att2 + a4 * 4);
     reinterpret_cast<float4*>(s_att2)[b * A4 + a4] = v;
   }
   for (int i = tid; i < A4; i += kThreads) reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(p.w)[i];
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) additive_attention_kernel(const AddA
   };
   auto emit = [&](int c, int b, float4 v) {
     if (p.gate) {
-      const float4 gt = *reinterpret_cast<const float4*>(p.gate + (row0 + b) * p.ld_gate + c * 4);
+      const float4 gt = *reinterpret_cast<const float4*>(p.gate + (p.row_src ? p.row_src[row0 + b] : row0 + b) * p.ld_gate + c * 4);
       v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
     }
     *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + c * 4) = v;

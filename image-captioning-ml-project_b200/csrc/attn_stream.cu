@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       for (int j = t; j < KB * A4; j += kScoreThreads) {
         const int b = j / A4, a4 = j - b * A4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < k) v = *reinterpret_cast<const float4*>(p.att2 + (row0 + b) * p.ld_att2 + a4 * 4);
+        if (b < k) {
+          const int64_t rs = p.row_src ? p.row_src[row0 + b] : row0 + b;
+          v = *reinterpret_cast<const float4*>(p.att2 + rs * p.ld_att2 + a4 * 4);
+        }
         reinterpret_cast<float4*>(q2)[j] = v;
       }
       named_barrier(1, kScoreThreads);
@@ -294,7 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
             if (b >= k) continue;
             float4 v = acc[j][b];
             if (p.gate) {
-              const float4 gt = *reinterpret_cast<const float4*>(p.gate + (row0 + b) * p.ld_gate + col * 4);
+              const int64_t rs = p.row_src ? p.row_src[row0 + b] : row0 + b;
+              const float4 gt = *reinterpret_cast<const float4*>(p.gate + rs * p.ld_gate + col * 4);
               v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
             }
             *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + col * 4) = v;

@@ -118,6 +118,9 @@ struct Session {
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
   float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
+  int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
+  bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
+  const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
@@ -136,7 +139,8 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
     S.fuse_k = want_k;
   auto take_logits = [&]() {
     if (S.fuse_k > 0) {
-      S.tk_part = ar.take<float>(R * tk_records(S.R, V) * tk_stride(S.fuse_k));
+      S.tk_ntotal = (is_legacy(h) && h->w_vocab_cat) ? h->vocab_cat_n : V;
+      S.tk_part = ar.take<float>(R * tk_records(S.R, S.tk_ntotal) * tk_stride(S.fuse_k));
       S.tk_lse = ar.take<float>(R * tk_lse_pairs(V) * 2);
     }
     else S.logits = ar.take<float>(R * V);
@@ -249,7 +253,13 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
   g.A = A; g.lda = lda; g.W = W; g.ldw = c.hidden_dim; g.bias = bias; g.M = rows; g.N = c.vocab_size; g.K = c.hidden_dim;
   if (logits == nullptr) {
     CAPDEC_REQUIRE(S.fuse_k > 0 && S.tk_part, CAPDEC_ERR_STATE, "vocab_project: no logits buffer and no fused top-k buffer");
-    g.tk_part = S.tk_part; g.tk_k = S.fuse_k; g.tk_lse = S.tk_lse;
+    g.tk_part = S.tk_part; g.tk_k = S.fuse_k; g.tk_lse = S.tk_lse; g.tk_vocab = c.vocab_size;
+    if (S.tk_ntotal != c.vocab_size) {
+      // legacy: the same GEMM also projects the new hidden state for the next step's attention (models/decoder.py:153,160)
+      g.W = h->w_vocab_cat; g.bias = h->b_vocab_cat; g.N = S.tk_ntotal;
+      g.C = S.hproj; g.ldc = c.attention_dim + c.feature_dim; g.n_split = c.attention_dim;
+      S.hproj_ready = true;
+    }
     return gemm(h, c.precision, g, EPI_TOPK, s);
   }
   g.C = logits; g.ldc = ld_logits;
@@ -259,7 +269,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
 // per-row sorted top-`topk` log-probs of the step's vocabulary distribution
 int select_topk(const capdec_handle* h, Session& S, int topk, float* out_lp, int32_t* out_idx, cudaStream_t s) {
   const int V = h->cfg.vocab_size;
-  if (S.fuse_k > 0) return topk_merge(S.tk_part, S.tk_lse, S.R, V, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
+  if (S.fuse_k > 0) return topk_merge(S.tk_part, S.tk_lse, S.R, V, S.tk_ntotal, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
   return lse_topk(S.logits, V, S.R, V, topk, out_lp, out_idx, nullptr, s);
 }
 
@@ -387,9 +397,14 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   GemmArgs g{};
   g.A = S.X[0] + E + D; g.lda = S.ldX[0]; g.W = h->w_hproj; g.ldw = H; g.bias = h->b_hproj;
   g.C = S.hproj; g.ldc = A + D; g.M = rows; g.N = A + D; g.K = H; g.n_split = A;
-  { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_SIGMOID_TAIL, s)); }
+  // (steps >= 1 of the fused path: the previous step's vocabulary GEMM already produced these rows, indexed before the
+  //  beam reorder, so the attention kernel applies the back-pointer instead)
+  const bool reuse = S.hproj_ready;
+  if (!reuse) { StageScope sc(h, STAGE_SMALL_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, g, EPI_SIGMOID_TAIL, s)); }
+  S.hproj_ready = false;
   // scores -> softmax -> gated context, written straight into the LSTM operand (:154-161)
   AddAttnArgs a{};
+  a.row_src = reuse ? S.row_src : nullptr;
   a.att1 = S.att1; a.att2 = S.hproj; a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
   a.temperature = 1.f; a.mask = nullptr; a.feats = feats; a.gate = S.hproj + A; a.ld_gate = A + D;
   a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;
@@ -604,6 +619,7 @@ int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8
 int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
            bool with_state, cudaStream_t s, int t_done = -1) {
   if (is_tf_family(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
+  S.row_src = src;
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim;
   GatherArgs g{};
@@ -779,6 +795,7 @@ int capdec_finalize(capdec_handle* h, void* stream) {
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear(); h->w_gates.clear(); h->b_gates.clear(); h->gate_in.clear();
   h->w_hproj = h->b_hproj = h->w_init = h->b_init = h->w_aoa = h->b_aoa = nullptr;
+  h->w_vocab_cat = h->b_vocab_cat = nullptr; h->vocab_cat_n = 0;
 
   if (is_gpt2(h)) {
     // src/models/decoders.py:513-561 + transformers GPT2LMHeadModel parameter names; Conv1D weights are bound
@@ -850,6 +867,18 @@ int capdec_finalize(capdec_handle* h, void* stream) {
     CAPDEC_RETURN_IF(scatter_rows(h->w_hproj + A * H, H, 1, 0, 0, h->W("f_beta.weight"), H, (int)D, (int)H, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj, 1, 1, 0, 0, h->W("dec_att.bias"), 1, (int)A, 1, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj + A, 1, 1, 0, 0, h->W("f_beta.bias"), 1, (int)D, 1, false, s));
+    if (c.precision != CAPDEC_PREC_FP32 && !getenv("CAPDEC_NO_HPROJ_TAIL")) {
+      const int64_t Vp = (V + 255) / 256 * 256, Nc = Vp + A + D;
+      CAPDEC_RETURN_IF(dev_alloc(h, &h->w_vocab_cat, (size_t)Nc * H));
+      CAPDEC_RETURN_IF(dev_alloc(h, &h->b_vocab_cat, (size_t)Nc));
+      CAPDEC_CHECK_CUDA(cudaMemsetAsync(h->w_vocab_cat, 0, (size_t)Nc * H * sizeof(float), s));
+      CAPDEC_CHECK_CUDA(cudaMemsetAsync(h->b_vocab_cat, 0, (size_t)Nc * sizeof(float), s));
+      CAPDEC_RETURN_IF(scatter_rows(h->w_vocab_cat, H, 1, 0, 0, h->W("fc.weight"), H, (int)V, (int)H, false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->b_vocab_cat, 1, 1, 0, 0, h->W("fc.bias"), 1, (int)V, 1, false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->w_vocab_cat + Vp * H, H, 1, 0, 0, h->w_hproj, H, (int)(A + D), (int)H, false, s));
+      CAPDEC_RETURN_IF(scatter_rows(h->b_vocab_cat + Vp, 1, 1, 0, 0, h->b_hproj, 1, (int)(A + D), 1, false, s));
+      h->vocab_cat_n = (int)Nc;
+    }
     CAPDEC_RETURN_IF(dev_alloc(h, &h->w_init, (size_t)2 * H * D));
     CAPDEC_RETURN_IF(dev_alloc(h, &h->b_init, (size_t)2 * H));
     CAPDEC_RETURN_IF(scatter_rows(h->w_init, D, 1, 0, 0, h->W("h_lin.weight"), D, (int)H, (int)D, false, s));
@@ -1213,10 +1242,10 @@ int capdec_linear_topk(int32_t precision, const float* a, int64_t lda, const flo
                  "capdec_linear_topk: workspace too small");
   GemmArgs g{};
   g.A = a; g.lda = lda; g.W = w; g.ldw = ldw; g.bias = bias; g.M = m; g.N = n; g.K = k;
-  g.tk_part = (float*)ws; g.tk_k = topk;
+  g.tk_part = (float*)ws; g.tk_k = topk; g.tk_vocab = n;
   g.tk_lse = (float*)((char*)ws + align_up((size_t)m * tk_records(m, n) * tk_stride(topk) * sizeof(float), 256));
   CAPDEC_RETURN_IF(gemm(nullptr, precision, g, EPI_TOPK, (cudaStream_t)stream));
-  return topk_merge(g.tk_part, g.tk_lse, m, n, topk, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
+  return topk_merge(g.tk_part, g.tk_lse, m, n, n, topk, topk, out_lp, out_idx, out_lse, (cudaStream_t)stream);
 }
 
 int capdec_lse_topk(const float* logits, int64_t ld, int32_t rows, int32_t vocab, int32_t topk, float* out_lp,

@@ -63,6 +63,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-based forms for the tensor-core epilogues (ex2.approx + rcp: ~1e-6 relative / 2e-7 absolute error, far below the
+// MMA accumulation noise of those modes); the exact-fp32 GEMM keeps expf / IEEE division
+__device__ __forceinline__ float sigmoid_fast_(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast_(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
 __device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_tanh_(float x) {   // transformers.activations.NewGELUActivation
   return 0.5f * x * (1.f + tanhf(0.79788456080286535588f * (x + 0.044715f * x * x * x)));
@@ -112,7 +116,9 @@ struct GemmArgs {
   float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
   float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
   float* tk_part; int tk_k;         // EPI_TOPK: candidate records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
-  float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(N), 2]
+  float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(tk_vocab), 2]
+  int tk_vocab;                     // EPI_TOPK: vocabulary columns V <= N.  Columns [ceil(V/256)*256, N) are a tail block stored
+                                    // to C (ld ldc) as a plain projection, sigmoid on tail columns >= n_split
 };
 
 int gemm_ffma(const GemmArgs& a, int epilogue, cudaStream_t s);

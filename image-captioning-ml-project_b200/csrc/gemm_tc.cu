@@ -291,6 +291,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     uint32_t local = 0;
     const uint32_t leader_empty_bar0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     float* stash = reinterpret_cast<float*>(smem + SL::kStashOffset);   // (allocated for EPI_TOPK launches only)
+    const int V = EPI == EPI_TOPK ? p.tk_vocab : p.N;                  // vocabulary columns; [n_vtiles*BN, N) is the tail block
+    const int n_vtiles = (V + BN - 1) / BN;
     // EPI_TOPK state carried across the tiles of one row block: online log-sum-exp and a sorted top-TK list of this
     // thread's row over the columns of this warp's column half
     float rmax = -INFINITY, rsum = 0.f;
@@ -336,6 +338,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll 1
       for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
         uint32_t v[32];
+        // this chunk's bias, requested before the accumulator load is waited for (full, 16-byte aligned chunks only)
+        const int nb0 = n_tile * BN + c0;
+        const bool pre_b = p.bias != nullptr && nb0 + 32 <= p.N;
+        float4 bia[8];
+        if (pre_b) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nb0) + j);
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -359,17 +369,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const int n0 = n_tile * BN + c0;
         if (n0 < p.N) {
           if constexpr (EPI == EPI_TOPK) {
-            // logits of this 32-column chunk (bias added, columns beyond N masked out)
+           if (n_tile >= n_vtiles) {
+            // tail block behind the (padded) vocabulary columns: a plain projection of the same A rows, stored to C with
+            // sigmoid on its columns >= n_split (the legacy step's [dec_att | f_beta] of the NEXT step rides here)
+            const int c_tail = n0 - n_vtiles * BN;
+            if (m < p.M) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int col = c_tail + j;
+                if (n0 + j < p.N) {
+                  const float4 b = pre_b ? bia[j >> 2] : (p.bias ? *reinterpret_cast<const float4*>(p.bias + n0 + j) : make_float4(0.f, 0.f, 0.f, 0.f));
+                  float4 t = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                                         __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+                  if (col >= p.n_split) { t.x = sigmoid_fast_(t.x); t.y = sigmoid_fast_(t.y); t.z = sigmoid_fast_(t.z); t.w = sigmoid_fast_(t.w); }
+#ifdef CAPDEC_EXP_NOSTORE
+                  if (t.x == 1234.5f)
+#endif
+                  *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + col) = t;
+                }
+              }
+            }
+           } else if (n0 < V) {
+            // logits of this 32-column chunk (bias added, columns beyond the vocabulary masked out)
             float x[32];
-            const bool full = n0 + 32 <= p.N;
+            const bool full = n0 + 32 <= V;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) {
+              if (pre_b) b = bia[j >> 2];
+              else if (p.bias) {
                 if (full) b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
                 else {
-                  b.x = n0 + j < p.N ? p.bias[n0 + j] : 0.f;         b.y = n0 + j + 1 < p.N ? p.bias[n0 + j + 1] : 0.f;
-                  b.z = n0 + j + 2 < p.N ? p.bias[n0 + j + 2] : 0.f; b.w = n0 + j + 3 < p.N ? p.bias[n0 + j + 3] : 0.f;
+                  b.x = n0 + j < V ? p.bias[n0 + j] : 0.f;         b.y = n0 + j + 1 < V ? p.bias[n0 + j + 1] : 0.f;
+                  b.z = n0 + j + 2 < V ? p.bias[n0 + j + 2] : 0.f; b.w = n0 + j + 3 < V ? p.bias[n0 + j + 3] : 0.f;
                 }
               }
               x[j] = __uint_as_float(v[j]) + b.x;         x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
@@ -377,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             }
             if (!full) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (n0 + j >= p.N) x[j] = -INFINITY;
+              for (int j = 0; j < 32; ++j) if (n0 + j >= V) x[j] = -INFINITY;
             }
             float cm = x[0];
 #pragma unroll
@@ -419,11 +451,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
               }
             }
+           }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              epilogue4<EPI>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                             __uint_as_float(v[j + 3]));
+              epilogue4<EPI, true>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]), pre_b ? &bia[j >> 2] : nullptr);
           }
         }
       }
@@ -431,8 +464,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         // {max, sum exp(x - max)} of this row over this tile half.  Kept per tile (not folded along the run) so that the
         // merge kernel can combine them in one canonical order: the result does not depend on how the tiles were
         // distributed over CTA groups, i.e. a row decodes identically whatever the batch size.
-        if (m < p.M && n_tile * BN + half * HN < p.N)
-          *reinterpret_cast<float2*>(p.tk_lse + ((int64_t)m * (2 * n_tiles) + n_tile * 2 + half) * 2) = make_float2(rmax, rsum);
+        if (m < p.M && n_tile < n_vtiles && n_tile * BN + half * HN < V)
+          *reinterpret_cast<float2*>(p.tk_lse + ((int64_t)m * (2 * n_vtiles) + n_tile * 2 + half) * 2) = make_float2(rmax, rsum);
       }
     }
     if constexpr (EPI == EPI_TOPK) {
@@ -713,6 +746,9 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   constexpr int bn = 256;
   const int cg = tc_cta_group(a.M);
   if (epilogue == EPI_TOPK) {
+    const int tail = a.N - ceil_div(a.tk_vocab, 256) * 256;
+    CAPDEC_REQUIRE(a.tk_vocab >= 1 && a.tk_vocab <= a.N && (tail <= 0 || (tail % 4 == 0 && a.C && a.ldc % 4 == 0)), CAPDEC_ERR_INVALID,
+                   "gemm: EPI_TOPK tail block must start at a 256-column boundary behind the vocabulary and be a multiple of 4 wide");
     CAPDEC_REQUIRE(a.M <= m_chunk, CAPDEC_ERR_UNSUPPORTED, "gemm: EPI_TOPK with %d rows exceeds the single-launch limit %d", a.M, m_chunk);
     // slots a launch does not write (row blocks that fall into a single run) must read as empty: index -1
     CAPDEC_CHECK_CUDA(cudaMemsetAsync(a.tk_part, 0xFF, (size_t)a.M * tk_records(a.M, a.N) * tk_stride(a.tk_k) * sizeof(float), s));

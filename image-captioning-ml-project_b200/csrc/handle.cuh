@@ -28,6 +28,9 @@ struct capdec_handle {
   std::vector<int> gate_in;            // input width of each layer (without the h part)
   // legacy: h -> [dec_att | f_beta] and mean(enc) -> [h_lin ; c_lin]
   float* w_hproj = nullptr; float* b_hproj = nullptr;
+  // legacy, tensor-core beam/greedy path: [fc ; 0-pad to a 256 multiple ; dec_att ; f_beta] so that the vocabulary GEMM of
+  // step t also emits [dec_att | sigmoid(f_beta)] of the new hidden state for step t+1 (same A operand)
+  float* w_vocab_cat = nullptr; float* b_vocab_cat = nullptr; int vocab_cat_n = 0;
   float* w_init = nullptr;  float* b_init = nullptr;   // legacy [2H,D]; lstm arch [2*H*layers, H] = [init_h ; init_c]
   // aoa: [info ; gate] rows interleaved n = 2*j + {info, gate}
   float* w_aoa = nullptr;   float* b_aoa = nullptr;

@@ -452,9 +452,9 @@ int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, flo
   return CAPDEC_OK;
 }
 
-int topk_merge(const float* part, const float* lse_part, int rows, int vocab, int part_k, int topk, float* out_lp,
-               int32_t* out_idx, float* out_lse, cudaStream_t s) {
-  const int n_rec = tk_records(rows, vocab);
+int topk_merge(const float* part, const float* lse_part, int rows, int vocab, int n_total, int part_k, int topk,
+               float* out_lp, int32_t* out_idx, float* out_lse, cudaStream_t s) {
+  const int n_rec = tk_records(rows, n_total);
   CAPDEC_REQUIRE(tk_supported(vocab, part_k) && n_rec <= kMergeMaxRecords && topk >= 1 && topk <= tk_bucket(part_k), CAPDEC_ERR_INVALID,
                  "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
   if (rows == 0) return CAPDEC_OK;

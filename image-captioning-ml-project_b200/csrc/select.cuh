@@ -12,8 +12,9 @@ int lse_topk(const float* logits, int64_t ld, int rows, int vocab, int topk, flo
 
 // fused path: merge the EPI_TOPK partial records [rows, tk_records(rows, vocab), tk_stride(part_k)] written by the vocabulary
 // GEMM (gemm_tc.cu) into the same outputs as lse_topk; the logits themselves never exist in HBM
-int topk_merge(const float* part, const float* lse_part, int rows, int vocab, int part_k, int topk, float* out_lp,
-               int32_t* out_idx, float* out_lse, cudaStream_t s);
+// (n_total = the GEMM's full N: vocabulary columns plus an optional projection tail, see GemmArgs::tk_vocab)
+int topk_merge(const float* part, const float* lse_part, int rows, int vocab, int n_total, int part_k, int topk,
+               float* out_lp, int32_t* out_idx, float* out_lse, cudaStream_t s);
 
 // inverse-CDF draw per row: token = #{v : cdf[v] <= u}; row r uses uniforms[r*ld_u + step].
 // rows whose (r % rows_per_image) == greedy_slot take the argmax instead (greedy_slot < 0: none).
