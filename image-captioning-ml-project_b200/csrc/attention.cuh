@@ -24,7 +24,8 @@ struct AddAttnArgs {
   const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr
   const float* feats;                   // [B,L,D]
   const float* gate; int64_t ld_gate;   // [R,D] or nullptr
-  float* ctx; int64_t ld_ctx;           // [R,D]
+  float* ctx; int64_t ld_ctx;           // [R,D]  (may be nullptr when ctx_split carries the only consumer's copy)
+  SplitDst ctx_split; int ctx_split_col; // optional: ctx also/only as the split GEMM operand, at column ctx_split_col
   float* alpha; int64_t ld_alpha;       // [R,L] (row stride ld_alpha) or nullptr
   int B, L, A, D, k;
 };

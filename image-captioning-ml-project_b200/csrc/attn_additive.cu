@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(kThreads) additive_attention_kernel(const AddA
       const float4 gt = *reinterpret_cast<const float4*>(p.gate + (p.row_src ? p.row_src[row0 + b] : row0 + b) * p.ld_gate + c * 4);
       v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
     }
-    *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + c * 4) = v;
+    if (p.ctx) *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + c * 4) = v;
+    split_store4(p.ctx_split, row0 + b, p.ctx_split_col + c * 4, v);
   };
 
   if (G == 1) {

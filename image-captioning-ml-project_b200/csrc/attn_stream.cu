@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
               const float4 gt = *reinterpret_cast<const float4*>(p.gate + rs * p.ld_gate + col * 4);
               v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
             }
-            *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + col * 4) = v;
+            if (p.ctx) *reinterpret_cast<float4*>(p.ctx + (row0 + b) * p.ld_ctx + col * 4) = v;
+            split_store4(p.ctx_split, row0 + b, p.ctx_split_col + col * 4, v);
           }
         }
       }

@@ -118,6 +118,9 @@ struct Session {
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
   float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
+  // legacy, tensor-core modes: the producers of the gate / vocabulary GEMM operands (attention context, state gather,
+  // LSTM epilogue) write the hi/lo operand copies themselves, so no split pass runs inside the step loop
+  void* xs_hi = nullptr; void* xs_lo = nullptr; void* hs_hi = nullptr; void* hs_lo = nullptr; bool presplit = false;
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
@@ -207,6 +210,17 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
     }
   }
   if (is_legacy(h)) {
+    S.presplit = false;
+    if (c.precision != CAPDEC_PREC_FP32 && mode != MODE_TEACHER && mode != MODE_ATTENTION && (E + D + H) % 8 == 0 && H % 8 == 0 &&
+        E % 4 == 0 && !getenv("CAPDEC_NO_PRESPLIT")) {
+      const size_t es = tc_kind(c.precision) == KIND_BF16 ? 2 : 4;
+      const bool lo = tc_terms(c.precision) == 3;
+      S.xs_hi = ar.take<char>(R * (E + D + H) * es);
+      S.xs_lo = lo ? ar.take<char>(R * (E + D + H) * es) : nullptr;
+      S.hs_hi = ar.take<char>(R * H * es);
+      S.hs_lo = lo ? ar.take<char>(R * H * es) : nullptr;
+      S.presplit = true;
+    }
     S.att1 = ar.take<float>((size_t)B * L * A);
     S.meanb = ar.take<float>((size_t)B * D);
     S.init = ar.take<float>((size_t)B * 2 * H);
@@ -251,6 +265,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
   const capdec_config& c = h->cfg;
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = c.hidden_dim; g.bias = bias; g.M = rows; g.N = c.vocab_size; g.K = c.hidden_dim;
+  if (S.presplit && is_legacy(h)) { g.A_hi = S.hs_hi; g.A_lo = S.hs_lo; g.ld_as = c.hidden_dim; }   // written by the LSTM epilogue
   if (logits == nullptr) {
     CAPDEC_REQUIRE(S.fuse_k > 0 && S.tk_part, CAPDEC_ERR_STATE, "vocab_project: no logits buffer and no fused top-k buffer");
     g.tk_part = S.tk_part; g.tk_k = S.fuse_k; g.tk_lse = S.tk_lse; g.tk_vocab = c.vocab_size;
@@ -288,6 +303,9 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
   if (expand) {
     CAPDEC_RETURN_IF(expand_rows(S.init, 2 * H, S.X[0] + E + D, S.ldX[0], S.R, S.k, H, s));
     CAPDEC_RETURN_IF(expand_rows(S.init + H, 2 * H, S.c[0], H, S.R, S.k, H, s));
+    // one-off: bring the split mirror of X in line (h0); from here on its producers maintain it
+    if (S.presplit)   // (the emb / ctx columns are rewritten by their producers before the first gate GEMM)
+      CAPDEC_RETURN_IF(tc_split(c.precision, S.X[0], S.ldX[0], S.R, (int)S.ldX[0], S.xs_hi, S.xs_lo, s));
   }
   return CAPDEC_OK;
 }
@@ -409,12 +427,22 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   a.temperature = 1.f; a.mask = nullptr; a.feats = feats; a.gate = S.hproj + A; a.ld_gate = A + D;
   a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;
   a.B = images; a.L = S.L; a.A = A; a.D = D; a.k = S.k;
+  const int kind = tc_kind(c.precision);
+  if (S.presplit) {   // the gated context goes straight into the gate GEMM's split operand; nobody reads the fp32 copy
+    a.ctx = nullptr;
+    a.ctx_split = SplitDst{S.xs_hi, S.xs_lo, S.ldX[0], kind};
+    a.ctx_split_col = E;
+  }
   { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, ACT_RELU, s)); }
   // LSTMCell([emb ; ctx], (h, c)) with the cell update fused into the gate GEMM (:168)
   GemmArgs l{};
   l.A = S.X[0]; l.lda = S.ldX[0]; l.W = h->w_gates[0]; l.ldw = E + D + H; l.bias = h->b_gates[0];
   l.C = S.hnew[0]; l.ldc = H; l.M = rows; l.N = 4 * H; l.K = E + D + H;
   l.c_in = S.c[0]; l.ldcin = H; l.c_out = S.cnew[0]; l.ldcout = H;
+  if (S.presplit) {
+    l.A_hi = S.xs_hi; l.A_lo = S.xs_lo; l.ld_as = S.ldX[0];
+    l.c_split = SplitDst{S.hs_hi, S.hs_lo, H, kind};   // new h as the vocabulary GEMM's operand
+  }
   { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, l, EPI_LSTM, s)); }
   // fc(h)  (:171; dropout is the identity in eval)
   { StageScope sc(h, STAGE_VOCAB_GEMM, s);
@@ -639,6 +667,11 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
     }
   }
   g.n_state = n;
+  if (S.presplit && is_legacy(h)) {
+    g.x_split = SplitDst{S.xs_hi, S.xs_lo, S.ldX[0], tc_kind(c.precision)};
+    for (int i = 0; i < 16; ++i) g.state_split_col[i] = -1;
+    if (with_state) g.state_split_col[0] = E + D;   // state 0 = new h of the single legacy layer -> X[:, E+D:]
+  }
   StageScope sc(h, STAGE_GATHER, s);
   return gather_rows(g, s);
 }

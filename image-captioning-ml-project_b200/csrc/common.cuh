@@ -1,6 +1,7 @@
 // Shared helpers for libcapdec (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -81,6 +82,81 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+// ---- tensor-core operand formats ------------------------------------------------------------------------
+// The tcgen05 GEMM reads K-major operands as hi (+ lo) copies: tf32 = two fp32 arrays (hi = round-to-nearest TF32,
+// lo = exact residual); bf16 = two bf16 arrays (hi = bf16_rn(x), lo = bf16_rn(x - hi)).  Kernels that PRODUCE a GEMM
+// operand (attention context, state gather, LSTM epilogue) can write these copies themselves through a SplitDst, so no
+// separate split pass over the operand is needed.
+enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1 };
+struct SplitDst {
+  void* hi; void* lo;      // lo == nullptr: single-term mode; hi == nullptr: no split copy wanted
+  int64_t ld;              // row stride in ELEMENTS of the operand type
+  int kind;
+};
+__device__ __forceinline__ uint32_t pack_bf16x2_(float a, float b, float* ra, float* rb) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  *ra = a - __bfloat162float(ha); *rb = b - __bfloat162float(hb);
+  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+// write v (4 consecutive columns starting at `col`, col % 4 == 0) of row `row` into the split copies
+__device__ __forceinline__ void split_store4(const SplitDst& d, int64_t row, int col, float4 v) {
+  if (!d.hi) return;
+  if (d.kind == KIND_TF32) {
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.hi) + row * d.ld + col) = h;
+    if (d.lo) *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.lo) + row * d.ld + col) = l;
+  } else {
+    float r0, r1, r2, r3, dummy0, dummy1;
+    uint2 hp, lp;
+    hp.x = pack_bf16x2_(v.x, v.y, &r0, &r1);
+    hp.y = pack_bf16x2_(v.z, v.w, &r2, &r3);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.hi) + row * d.ld + col) = hp;
+    if (d.lo) {
+      lp.x = pack_bf16x2_(r0, r1, &dummy0, &dummy1);
+      lp.y = pack_bf16x2_(r2, r3, &dummy0, &dummy1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.lo) + row * d.ld + col) = lp;
+    }
+  }
+}
+// 8 consecutive columns (col % 8 == 0): one 16-byte store per bf16 copy
+__device__ __forceinline__ void split_store8(const SplitDst& d, int64_t row, int col, const float (&v)[8]) {
+  if (!d.hi) return;
+  if (d.kind == KIND_TF32) {
+    split_store4(d, row, col, make_float4(v[0], v[1], v[2], v[3]));
+    split_store4(d, row, col + 4, make_float4(v[4], v[5], v[6], v[7]));
+  } else {
+    float r[8], dm0, dm1;
+    uint4 hp, lp;
+    hp.x = pack_bf16x2_(v[0], v[1], &r[0], &r[1]); hp.y = pack_bf16x2_(v[2], v[3], &r[2], &r[3]);
+    hp.z = pack_bf16x2_(v[4], v[5], &r[4], &r[5]); hp.w = pack_bf16x2_(v[6], v[7], &r[6], &r[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.hi) + row * d.ld + col) = hp;
+    if (d.lo) {
+      lp.x = pack_bf16x2_(r[0], r[1], &dm0, &dm1); lp.y = pack_bf16x2_(r[2], r[3], &dm0, &dm1);
+      lp.z = pack_bf16x2_(r[4], r[5], &dm0, &dm1); lp.w = pack_bf16x2_(r[6], r[7], &dm0, &dm1);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.lo) + row * d.ld + col) = lp;
+    }
+  }
+}
+__device__ __forceinline__ void split_store1(const SplitDst& d, int64_t row, int col, float v) {
+  if (!d.hi) return;
+  if (d.kind == KIND_TF32) {
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    const float h = __uint_as_float(t);
+    reinterpret_cast<float*>(d.hi)[row * d.ld + col] = h;
+    if (d.lo) reinterpret_cast<float*>(d.lo)[row * d.ld + col] = v - h;
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16*>(d.hi)[row * d.ld + col] = h;
+    if (d.lo) reinterpret_cast<__nv_bfloat16*>(d.lo)[row * d.ld + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 // ---- GEMM front door (gemm_ffma.cu / gemm_tc.cu) ---------------------------------------------------
 enum Epilogue : int {
   EPI_STORE = 0,         // C = acc + bias
@@ -115,6 +191,8 @@ struct GemmArgs {
   const float* c_in; int64_t ldcin; // EPI_LSTM: previous cell state [M,H]
   float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
   float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
+  const void* A_hi; const void* A_lo; int64_t ld_as;   // tensor-core path: A already split by its producer (row stride ld_as elements)
+  SplitDst c_split;                 // EPI_LSTM: also write h_out as the split operand of the GEMM that consumes it
   float* tk_part; int tk_k;         // EPI_TOPK: candidate records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
   float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(tk_vocab), 2]
   int tk_vocab;                     // EPI_TOPK: vocabulary columns V <= N.  Columns [ceil(V/256)*256, N) are a tail block stored

@@ -54,6 +54,7 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
     p.c_out[(int64_t)m * p.ldcout + j] = c2;
     p.C[(int64_t)m * p.ldc + j] = h2;
     if (p.C2) p.C2[(int64_t)m * p.ldc2 + j] = h2;
+    split_store1(p.c_split, m, j, h2);
   } else if (EPI == EPI_AOA) {
     const int j = n >> 1;
     const float o0 = th(v0) * sig(v1);

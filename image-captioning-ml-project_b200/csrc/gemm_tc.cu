@@ -25,7 +25,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int kRowBytes = 128;        // one K block = one 128-byte swizzle row: 32 tf32 or 64 bf16 elements
-enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1 };
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
@@ -452,6 +451,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               }
             }
            }
+          } else if (EPI == EPI_LSTM && pre_b && m < p.M && ((p.ldc | p.ldcin | p.ldcout | p.ldc2) & 3) == 0 &&
+                     (p.c_split.hi == nullptr || ((p.c_split.ld & 7) == 0))) {
+            // LSTM cell on the 8 hidden units of this 32-column chunk at once (gate columns are interleaved 4j + {i,f,g,o}):
+            // 16-byte loads / stores of 8 consecutive units per row instead of 4-byte scattered ones
+            const int j0 = n0 >> 2;
+            const float4 ci0 = *reinterpret_cast<const float4*>(p.c_in + (int64_t)m * p.ldcin + j0);
+            const float4 ci1 = *reinterpret_cast<const float4*>(p.c_in + (int64_t)m * p.ldcin + j0 + 4);
+            const float cp[8] = {ci0.x, ci0.y, ci0.z, ci0.w, ci1.x, ci1.y, ci1.z, ci1.w};
+            float hv[8], cv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float gi = __uint_as_float(v[4 * u]) + bia[u].x, gf = __uint_as_float(v[4 * u + 1]) + bia[u].y;
+              const float gg = __uint_as_float(v[4 * u + 2]) + bia[u].z, go = __uint_as_float(v[4 * u + 3]) + bia[u].w;
+              cv[u] = sigmoid_fast_(gf) * cp[u] + sigmoid_fast_(gi) * tanh_fast_(gg);
+              hv[u] = sigmoid_fast_(go) * tanh_fast_(cv[u]);
+            }
+            float4* co = reinterpret_cast<float4*>(p.c_out + (int64_t)m * p.ldcout + j0);
+            co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]); co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+            float4* ho = reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + j0);
+            ho[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); ho[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            if (p.C2) {
+              float4* h2 = reinterpret_cast<float4*>(p.C2 + (int64_t)m * p.ldc2 + j0);
+              h2[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); h2[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            }
+            split_store8(p.c_split, m, j0, hv);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -495,7 +519,7 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t ld, int rows, 
   if (i >= (int64_t)rows * c4) return;
   const int r = (int)(i / c4), c = (int)(i - (int64_t)r * c4);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c * 4 < cols) v = *reinterpret_cast<const float4*>(x + (int64_t)r * ld + c * 4);   // cols % 4 == 0
+  if (c * 4 < cols) v = ldg_stream(reinterpret_cast<const float4*>(x + (int64_t)r * ld + c * 4));   // cols % 4 == 0
   if (KIND == KIND_TF32) {
     float4 h, l;
     uint32_t t;
@@ -678,6 +702,13 @@ int ensure(float** p, size_t* have, size_t need) {
 
 }  // namespace
 
+int tc_kind(int precision) { return (precision == CAPDEC_PREC_BF16 || precision == CAPDEC_PREC_BF16X3) ? KIND_BF16 : KIND_TF32; }
+int tc_terms(int precision) { return (precision == CAPDEC_PREC_TF32X3 || precision == CAPDEC_PREC_BF16X3) ? 3 : 1; }
+// one-off split of a dense fp32 matrix into caller-provided copies with row pitch `cols` (cols % 8 == 0)
+int tc_split(int precision, const float* x, int64_t ld, int rows, int cols, void* hi, void* lo, cudaStream_t s) {
+  return split_operand(tc_kind(precision), x, ld, rows, cols, cols, hi, tc_terms(precision) == 3 ? lo : nullptr, s);
+}
+
 // records per row the EPI_TOPK epilogue writes for an [M,N] problem: 2 column halves x (runs a row block can span)
 int tk_records(int M, int N) {
   if (M <= 0) return 2;
@@ -757,15 +788,26 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   CAPDEC_RETURN_IF(make_map(&map_w_hi, kind, w_hi, a.N, Kp, Kp, bn / cg));
   CAPDEC_RETURN_IF(make_map(&map_w_lo, kind, terms == 3 ? w_lo : w_hi, a.N, Kp, Kp, bn / cg));
 
+  const bool pre = a.A_hi != nullptr;   // the producer of A already wrote the split copies
+  if (pre) {
+    CAPDEC_REQUIRE((terms == 1 || a.A_lo) && (a.ld_as * es) % 16 == 0 && (((uintptr_t)a.A_hi | (uintptr_t)a.A_lo) & 15) == 0,
+                   CAPDEC_ERR_INVALID, "gemm: pre-split A must be 16-byte aligned with a 16-byte row pitch and carry a lo copy");
+    m_chunk = a.M;
+  }
   for (int m0 = 0; m0 < a.M; m0 += m_chunk) {
     const int mc = a.M - m0 < m_chunk ? a.M - m0 : m_chunk;
-    CAPDEC_RETURN_IF(split_operand(kind, a.A + (int64_t)m0 * a.lda, a.lda, mc, K, Kp, a_hi, terms == 3 ? a_lo : nullptr, s));
     CUtensorMap map_a_hi, map_a_lo;
-    CAPDEC_RETURN_IF(make_map(&map_a_hi, kind, a_hi, mc, Kp, Kp, BM));
-    CAPDEC_RETURN_IF(make_map(&map_a_lo, kind, terms == 3 ? a_lo : a_hi, mc, Kp, Kp, BM));
+    if (pre) {
+      CAPDEC_RETURN_IF(make_map(&map_a_hi, kind, a.A_hi, mc, K, a.ld_as, BM));
+      CAPDEC_RETURN_IF(make_map(&map_a_lo, kind, terms == 3 ? a.A_lo : a.A_hi, mc, K, a.ld_as, BM));
+    } else {
+      CAPDEC_RETURN_IF(split_operand(kind, a.A + (int64_t)m0 * a.lda, a.lda, mc, K, Kp, a_hi, terms == 3 ? a_lo : nullptr, s));
+      CAPDEC_RETURN_IF(make_map(&map_a_hi, kind, a_hi, mc, Kp, Kp, BM));
+      CAPDEC_RETURN_IF(make_map(&map_a_lo, kind, terms == 3 ? a_lo : a_hi, mc, Kp, Kp, BM));
+    }
     GemmArgs g = a;
     g.M = mc;
-    g.K = Kp;
+    g.K = pre ? K : Kp;
     g.C = a.C + (int64_t)m0 * a.ldc;
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;

@@ -110,6 +110,9 @@ struct StageScope {
 // tensor-core GEMM modes (gemm_tc.cu)
 int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
 int gemm_tc_prepare(capdec_handle* h, cudaStream_t s);
+int tc_kind(int precision);
+int tc_terms(int precision);
+int tc_split(int precision, const float* x, int64_t ld, int rows, int cols, void* hi, void* lo, cudaStream_t s);
 void gemm_tc_release(capdec_handle* h);
 int gemm(const capdec_handle* h, int precision, const GemmArgs& a, int epilogue, cudaStream_t s);
 

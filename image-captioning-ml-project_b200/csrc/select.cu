@@ -256,7 +256,10 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
                                  float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
                                  int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
                                  int32_t* dbg_tok, int32_t* dbg_beam) {
-  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per image: every lane evaluates the (tiny) selection logic redundantly on the same inputs, the token
+  // sequences are copied lane-parallel, lane 0 writes the scalars
+  const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (img >= B) return;
   constexpr int KM = kMaxRowsPerImage, K2 = kMaxTopK;
   const int k2 = 2 * k;
@@ -285,7 +288,7 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
     }
     top_lp[j] = bv; top_tok[j] = bt; top_beam[j] = bb < 0 ? 0 : bb;
     if (bb >= 0) ptr[bb]++;
-    if (dbg_lp) {
+    if (dbg_lp && lane == 0) {
       const int64_t o = (int64_t)img * k2 + j;
       dbg_lp[o] = bv; dbg_tok[o] = bt; dbg_beam[o] = top_beam[j];
     }
@@ -312,10 +315,11 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
     new_score[i] = run_lp[bj];
     const int32_t* srcp = run_old + (int64_t)top_beam[bj] * T;
     int32_t* dstp = run_new + (int64_t)i * T;
-    for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
-    dstp[cur_len] = top_tok[bj];
-    next_tok[img * k + i] = top_tok[bj];
-    src_row[img * k + i] = img * k + top_beam[bj];
+    for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? top_tok[bj] : srcp[t];
+    if (lane == 0) {
+      next_tok[img * k + i] = top_tok[bj];
+      src_row[img * k + i] = img * k + top_beam[bj];
+    }
   }
 
   // (f) finished beams: merge the k finished with the 2k candidates, keep the best k (stable)
@@ -343,24 +347,26 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
     int32_t* dstp = fin_new + (int64_t)i * T;
     if (bj < k) {
       const int32_t* srcp = fin_old + (int64_t)bj * T;
-      for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
+      for (int t = lane; t < T; t += 32) dstp[t] = srcp[t];
       f_len[i] = st.fin_len[img * k + bj];
       f_flag[i] = st.fin_flag[img * k + bj];
     } else {
       const int j = bj - k;
       const int32_t* srcp = run_old + (int64_t)top_beam[j] * T;
-      for (int t = 0; t < T; ++t) dstp[t] = srcp[t];
-      dstp[cur_len] = top_tok[j];
+      for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? top_tok[j] : srcp[t];
       f_len[i] = cur_len + 1;
       f_flag[i] = (hits[j] && j < k) ? 1 : 0;
     }
   }
+  __syncwarp();   // every lane has read the old per-image state before lane 0 overwrites it
   float fmin = f_sc[0];
   for (int i = 0; i < k; ++i) {
-    st.fin_score[img * k + i] = f_sc[i];
-    st.fin_len[img * k + i] = f_len[i];
-    st.fin_flag[img * k + i] = f_flag[i];
-    st.run_score[img * k + i] = new_score[i];
+    if (lane == 0) {
+      st.fin_score[img * k + i] = f_sc[i];
+      st.fin_len[img * k + i] = f_len[i];
+      st.fin_flag[img * k + i] = f_flag[i];
+      st.run_score[img * k + i] = new_score[i];
+    }
     fmin = fminf(fmin, f_sc[i]);
   }
 
@@ -368,7 +374,7 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
   const float best_possible = new_score[0] / div_heur;
   bool any = false;
   for (int i = 0; i < k; ++i) any = any || (best_possible > (f_flag[i] ? fmin : kNeg));
-  st.unsatisfied[img] = (unsat && any) ? 1 : 0;
+  if (lane == 0) st.unsatisfied[img] = (unsat && any) ? 1 : 0;
 }
 
 __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
@@ -394,13 +400,22 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
     if (a.embedding) {
       const float4* e = reinterpret_cast<const float4*>(a.embedding + (int64_t)tok * a.E);
       float4* d = reinterpret_cast<float4*>(a.x_emb + (int64_t)r * a.ld_x);
-      for (int i = tid; i < a.E / 4; i += blockDim.x) d[i] = e[i];
+      for (int i = tid; i < a.E / 4; i += blockDim.x) {
+        const float4 v = e[i];
+        d[i] = v;
+        split_store4(a.x_split, r, i * 4, v);
+      }
     }
   }
   for (int sidx = 0; sidx < a.n_state; ++sidx) {
     const float4* sp = reinterpret_cast<const float4*>(a.state_src[sidx] + (int64_t)src * a.ld_src[sidx]);
     float4* dp = reinterpret_cast<float4*>(a.state_dst[sidx] + (int64_t)r * a.ld_dst[sidx]);
-    for (int i = tid; i < a.width[sidx] / 4; i += blockDim.x) dp[i] = sp[i];
+    const int scol = a.x_split.hi ? a.state_split_col[sidx] : -1;
+    for (int i = tid; i < a.width[sidx] / 4; i += blockDim.x) {
+      const float4 v = sp[i];
+      dp[i] = v;
+      if (scol >= 0) split_store4(a.x_split, r, scol + i * 4, v);
+    }
   }
 }
 
@@ -491,7 +506,7 @@ int beam_step(const BeamState& st, int B, int k, int T, int V, int cur_len, int 
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "beam_step: num_beams %d not in [1,%d]", k,
                  kMaxRowsPerImage);
   if (B == 0) return CAPDEC_OK;
-  beam_step_kernel<<<ceil_div(B, 64), 64, 0, s>>>(st, B, k, T, V, cur_len, eos, len_div_finished, len_div_heuristic,
+  beam_step_kernel<<<ceil_div(B, 4), 128, 0, s>>>(st, B, k, T, V, cur_len, eos, len_div_finished, len_div_heuristic,
                                                   cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;

@@ -47,6 +47,8 @@ struct GatherArgs {
   const float* state_src[16]; float* state_dst[16]; int64_t ld_src[16]; int64_t ld_dst[16]; int width[16];
   int32_t* tok_out; int64_t ld_tok; int pos;
   int rows;
+  // optional split mirrors of X (the gate GEMM's operand): embedding at column 0, state i at column state_split_col[i]
+  SplitDst x_split; int state_split_col[16];   // state_split_col[i] < 0: state i is not part of X
 };
 int gather_rows(const GatherArgs& a, cudaStream_t s);
 
