@@ -51,5 +51,7 @@ struct MhaArgs {
   int B, L, H, heads, k;
 };
 int mha_attention(const MhaArgs& a, cudaStream_t s);
+// persistent TMA-streamed form (attn_mha_stream.cu) for dense [L,H] K/V tiles: 1 = took the call, 0 = left to the generic kernel
+int mha_attention_stream(const MhaArgs& a, cudaStream_t s);
 
 }  // namespace capdec

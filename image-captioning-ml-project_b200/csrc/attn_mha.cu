@@ -196,6 +196,8 @@ int mha_attention(const MhaArgs& a, cudaStream_t s) {
                  "mha_attention: head_dim must be a multiple of 4 (H=%d heads=%d)", a.H, a.heads);
   CAPDEC_REQUIRE(a.ld_q % 4 == 0 && a.ld_out % 4 == 0 && a.ld_kv % 4 == 0 && a.ld_kv >= a.H, CAPDEC_ERR_INVALID, "mha_attention: strides must be multiples of 4");
   if (a.B == 0) return CAPDEC_OK;
+  const int took = mha_attention_stream(a, s);   // persistent TMA-streamed kernel for dense K/V tiles
+  if (took != 0) return took > 0 ? CAPDEC_OK : took;
   switch (a.k) {
     case 1: return launch_kb<1>(a, s);
     case 2: return launch_kb<2>(a, s);

@@ -112,7 +112,7 @@ struct Session {
   // transformer arch
   float* tx = nullptr; float* tqkv = nullptr; float* tsa = nullptr; float* ty = nullptr; float* tqc = nullptr;
   float* tca = nullptr; float* tff = nullptr; float* tmem = nullptr;
-  std::vector<float*> tckv, tcache_k, tcache_v;
+  std::vector<float*> tck, tcv, tcache_k, tcache_v;   // hoisted cross-attention K / V (dense [B,L,H] each), self-attention cache
   int32_t* anc[2] = {nullptr, nullptr};
   int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
@@ -161,9 +161,9 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
     S.ty = ar.take<float>(R * H); S.tqc = ar.take<float>(R * H); S.tca = ar.take<float>(R * H);
     S.tff = ar.take<float>(R * F);
     if (!is_gpt2(h)) S.tmem = ar.take<float>((size_t)B * L * H);
-    S.tckv.resize(layers); S.tcache_k.resize(layers); S.tcache_v.resize(layers);
+    S.tck.resize(layers); S.tcv.resize(layers); S.tcache_k.resize(layers); S.tcache_v.resize(layers);
     for (int l = 0; l < layers; ++l) {
-      if (!is_gpt2(h)) S.tckv[l] = ar.take<float>((size_t)B * L * 2 * H);
+      if (!is_gpt2(h)) { S.tck[l] = ar.take<float>((size_t)B * L * H); S.tcv[l] = ar.take<float>((size_t)B * L * H); }
       S.tcache_k[l] = ar.take<float>(R * T * H);
       S.tcache_v[l] = ar.take<float>(R * T * H);
     }
@@ -510,7 +510,9 @@ int prologue_transformer(const capdec_handle* h, Session& S, const float* feats,
   for (int l = 0; l < h->cfg.num_layers; ++l) {
     const float* w = h->W(tl(l, "multihead_attn.in_proj_weight"));
     const float* b = h->W(tl(l, "multihead_attn.in_proj_bias"));
-    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)H * H, H, b + H, S.tckv[l], 2 * H, rows, 2 * H, H, EPI_STORE, s));
+    // K and V into separate dense [B,L,H] buffers (what the streaming attention kernel's bulk copies want)
+    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)H * H, H, b + H, S.tck[l], H, rows, H, H, EPI_STORE, s));
+    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)2 * H * H, H, b + 2 * H, S.tcv[l], H, rows, H, H, EPI_STORE, s));
   }
   S.anc_cur = -1;
   return CAPDEC_OK;
@@ -546,7 +548,7 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
                               S.tqc, H, rows, H, H, EPI_STORE, s)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       MhaArgs m{};
-      m.q = S.tqc; m.ld_q = H; m.kproj = S.tckv[l]; m.vproj = S.tckv[l] + H; m.ld_kv = 2 * H; m.mask = nullptr;
+      m.q = S.tqc; m.ld_q = H; m.kproj = S.tck[l]; m.vproj = S.tcv[l]; m.ld_kv = H; m.mask = nullptr;
       m.denom = (float)sqrt((double)(H / heads)); m.out = S.tca; m.ld_out = H; m.alpha = nullptr; m.ld_alpha = 0;
       m.B = S.B; m.L = S.L; m.H = H; m.heads = heads; m.k = S.k;
       CAPDEC_RETURN_IF(mha_attention(m, s)); }
