@@ -116,6 +116,9 @@ struct Session {
   int32_t* anc[2] = {nullptr, nullptr};
   int anc_cur = -1;   // -1: identity (no reorder yet / greedy / sampling)
   float* txn = nullptr; float* gprefix = nullptr; int n_prefix = 0;   // GPT-2: pre-LN output, image prefix K == V
+  // transformer family, tensor-core modes: hi/lo operand mirrors of the activations that feed GEMMs, written by the
+  // kernels that produce them (embedding / LayerNorm / self-attention / GELU epilogue) instead of by a split pass
+  SplitDst mx{}, msa{}, mff{};        // mirrors of tx (transformer) or txn (GPT-2), of tsa, of tff
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
   float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
   // legacy, tensor-core modes: the producers of the gate / vocabulary GEMM operands (attention context, state gather,
@@ -156,6 +159,18 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.n_prefix = ip ? (int)(ip->shape[0] / H) : 10;
       S.txn = ar.take<float>(R * H);
       S.gprefix = ar.take<float>((size_t)B * S.n_prefix * H);
+    }
+    S.mx = S.msa = S.mff = SplitDst{};
+    if (c.precision != CAPDEC_PREC_FP32 && H % 8 == 0 && F % 8 == 0 && !getenv("CAPDEC_NO_PRESPLIT")) {
+      const int kind = tc_kind(c.precision);
+      const size_t es = kind == KIND_BF16 ? 2 : 4;
+      const bool lo = tc_terms(c.precision) == 3;
+      auto mk = [&](size_t cols) {
+        SplitDst d{};
+        d.hi = ar.take<char>(R * cols * es); d.lo = lo ? ar.take<char>(R * cols * es) : nullptr; d.ld = (int64_t)cols; d.kind = kind;
+        return d;
+      };
+      S.mx = mk(H); S.msa = mk(H); S.mff = mk(F);
     }
     S.tx = ar.take<float>(R * H); S.tqkv = ar.take<float>(R * 3 * H); S.tsa = ar.take<float>(R * H);
     S.ty = ar.take<float>(R * H); S.tqc = ar.take<float>(R * H); S.tca = ar.take<float>(R * H);
@@ -247,14 +262,19 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
 }
 
 // ---- hoisted per-call projections ---------------------------------------------------------------------------
+// a_pre: A's hi/lo mirror written by A's producer (hi == nullptr: none, the GEMM splits A itself);
+// c_out: mirror to fill for the consumer of C (store-family and LSTM epilogues)
 int linear(const capdec_handle* h, const float* A, int64_t lda, const std::string& name, float* C, int64_t ldc, int M,
-           int epi, cudaStream_t s, float* C2 = nullptr, int64_t ldc2 = 0) {
+           int epi, cudaStream_t s, float* C2 = nullptr, int64_t ldc2 = 0, const SplitDst* a_pre = nullptr,
+           const SplitDst* c_out = nullptr) {
   const DevTensor* w = h->find(name + ".weight");
   const DevTensor* b = h->find(name + ".bias");
   CAPDEC_REQUIRE(w && w->shape.size() == 2, CAPDEC_ERR_STATE, "weight %s.weight missing", name.c_str());
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = w->p; g.ldw = w->shape[1]; g.bias = b ? b->p : nullptr;
   g.C = C; g.ldc = ldc; g.M = M; g.N = (int)w->shape[0]; g.K = (int)w->shape[1]; g.C2 = C2; g.ldc2 = ldc2;
+  if (a_pre && a_pre->hi) { g.A_hi = a_pre->hi; g.A_lo = a_pre->lo; g.ld_as = a_pre->ld; }
+  if (c_out && c_out->hi) g.c_split = *c_out;
   return gemm(h, h->cfg.precision, g, epi, s);
 }
 
@@ -266,6 +286,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = c.hidden_dim; g.bias = bias; g.M = rows; g.N = c.vocab_size; g.K = c.hidden_dim;
   if (S.presplit && is_legacy(h)) { g.A_hi = S.hs_hi; g.A_lo = S.hs_lo; g.ld_as = c.hidden_dim; }   // written by the LSTM epilogue
+  if (is_tf_family(h) && S.mx.hi) { g.A_hi = S.mx.hi; g.A_lo = S.mx.lo; g.ld_as = S.mx.ld; }        // written by the last LayerNorm
   if (logits == nullptr) {
     CAPDEC_REQUIRE(S.fuse_k > 0 && S.tk_part, CAPDEC_ERR_STATE, "vocab_project: no logits buffer and no fused top-k buffer");
     g.tk_part = S.tk_part; g.tk_k = S.fuse_k; g.tk_lse = S.tk_lse; g.tk_vocab = c.vocab_size;
@@ -495,9 +516,10 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
 std::string tl(int l, const char* name) { return "transformer_decoder.layers." + std::to_string(l) + "." + name; }
 
 int gemm_w(const capdec_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
-           int64_t ldc, int M, int N, int K, int epi, cudaStream_t s) {
+           int64_t ldc, int M, int N, int K, int epi, cudaStream_t s, const SplitDst* a_pre = nullptr) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  if (a_pre && a_pre->hi) { g.A_hi = a_pre->hi; g.A_lo = a_pre->lo; g.ld_as = a_pre->ld; }
   return gemm(h, h->cfg.precision, g, epi, s);
 }
 
@@ -526,26 +548,26 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
   CAPDEC_REQUIRE(t < pos->shape[0], CAPDEC_ERR_INVALID, "position %d exceeds position_encoding rows %lld", t, (long long)pos->shape[0]);
   const int F = (int)h->find(tl(0, "linear1.weight"))->shape[0];
   { StageScope sc(h, STAGE_GATHER, s);
-    CAPDEC_RETURN_IF(embed_pos(S.next_tok, h->W("embedding.weight"), pos->p + (size_t)t * H, S.tx, rows, H, s)); }
+    CAPDEC_RETURN_IF(embed_pos(S.next_tok, h->W("embedding.weight"), pos->p + (size_t)t * H, S.tx, rows, H, s, &S.mx)); }
   const float eps = 1e-5f;
   for (int l = 0; l < c.num_layers; ++l) {
     // self-attention block: x = norm1(x + out_proj(attn(in_proj(x))))   (post-LN, norm_first=False)
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(gemm_w(h, S.tx, H, h->W(tl(l, "self_attn.in_proj_weight")), H, h->W(tl(l, "self_attn.in_proj_bias")),
-                              S.tqkv, 3 * H, rows, 3 * H, H, EPI_STORE, s)); }
+                              S.tqkv, 3 * H, rows, 3 * H, H, EPI_STORE, s, &S.mx)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       SelfAttnArgs a{};
       a.qkv = S.tqkv; a.ld_qkv = 3 * H; a.cache_k = S.tcache_k[l]; a.cache_v = S.tcache_v[l];
       a.anc = S.anc_cur >= 0 ? S.anc[S.anc_cur] : nullptr; a.n_prefix = 0; a.rows_per_image = S.k;
-      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H;
+      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
-      CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s));
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm1.weight")), h->W(tl(l, "norm1.bias")), nullptr, S.tx, rows, H, eps, s));
+      CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm1.weight")), h->W(tl(l, "norm1.bias")), nullptr, S.tx, rows, H, eps, s, &S.mx));
       // cross-attention block over the hoisted K|V of the image regions: x = norm2(x + out_proj(attn(q(x), K, V)))
       CAPDEC_RETURN_IF(gemm_w(h, S.tx, H, h->W(tl(l, "multihead_attn.in_proj_weight")), H, h->W(tl(l, "multihead_attn.in_proj_bias")),
-                              S.tqc, H, rows, H, H, EPI_STORE, s)); }
+                              S.tqc, H, rows, H, H, EPI_STORE, s, &S.mx)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       MhaArgs m{};
       m.q = S.tqc; m.ld_q = H; m.kproj = S.tck[l]; m.vproj = S.tcv[l]; m.ld_kv = H; m.mask = nullptr;
@@ -554,12 +576,12 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
       CAPDEC_RETURN_IF(mha_attention(m, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tca, H, tl(l, "multihead_attn.out_proj"), S.ty, H, rows, EPI_STORE, s));
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm2.weight")), h->W(tl(l, "norm2.bias")), nullptr, S.tx, rows, H, eps, s)); }
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm2.weight")), h->W(tl(l, "norm2.bias")), nullptr, S.tx, rows, H, eps, s, &S.mx)); }
     // feed-forward block: x = norm3(x + linear2(gelu(linear1(x))))
     { StageScope sc(h, STAGE_GATE_GEMM, s);
-      CAPDEC_RETURN_IF(linear(h, S.tx, H, tl(l, "linear1"), S.tff, F, rows, EPI_GELU, s));
-      CAPDEC_RETURN_IF(linear(h, S.tff, F, tl(l, "linear2"), S.ty, H, rows, EPI_STORE, s));
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm3.weight")), h->W(tl(l, "norm3.bias")), nullptr, S.tx, rows, H, eps, s)); }
+      CAPDEC_RETURN_IF(linear(h, S.tx, H, tl(l, "linear1"), S.mff.hi ? nullptr : S.tff, F, rows, EPI_GELU, s, nullptr, 0, &S.mx, &S.mff));
+      CAPDEC_RETURN_IF(linear(h, S.tff, F, tl(l, "linear2"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.mff));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm3.weight")), h->W(tl(l, "norm3.bias")), nullptr, S.tx, rows, H, eps, s, &S.mx)); }
   }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   return vocab_project(h, S, S.tx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits, c.vocab_size, s);
@@ -612,26 +634,26 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
   const float* pending = nullptr;
   for (int l = 0; l < c.num_layers; ++l) {
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W(gl(l, "ln_1.weight")), h->W(gl(l, "ln_1.bias")), pending ? S.tx : nullptr, S.txn, rows, H, eps, s));
-      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "attn.c_attn"), S.tqkv, 3 * H, rows, EPI_STORE, s)); }
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W(gl(l, "ln_1.weight")), h->W(gl(l, "ln_1.bias")), pending ? S.tx : nullptr, S.txn, rows, H, eps, s, &S.mx));
+      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "attn.c_attn"), S.tqkv, 3 * H, rows, EPI_STORE, s, nullptr, 0, &S.mx)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       SelfAttnArgs a{};
       a.qkv = S.tqkv; a.ld_qkv = 3 * H; a.cache_k = S.tcache_k[l]; a.cache_v = S.tcache_v[l];
       a.anc = S.anc_cur >= 0 ? S.anc[S.anc_cur] : nullptr;
       a.prefix_k = S.gprefix; a.prefix_v = S.gprefix; a.n_prefix = P; a.rows_per_image = S.k;
-      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H;
+      a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
-      CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s));
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(gl(l, "ln_2.weight")), h->W(gl(l, "ln_2.bias")), S.tx, S.txn, rows, H, eps, s)); }
+      CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(gl(l, "ln_2.weight")), h->W(gl(l, "ln_2.bias")), S.tx, S.txn, rows, H, eps, s, &S.mx)); }
     { StageScope sc(h, STAGE_GATE_GEMM, s);
-      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "mlp.c_fc"), S.tff, F, rows, EPI_GELU_TANH, s));
-      CAPDEC_RETURN_IF(linear(h, S.tff, F, gl(l, "mlp.c_proj"), S.ty, H, rows, EPI_STORE, s)); }
+      CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "mlp.c_fc"), S.mff.hi ? nullptr : S.tff, F, rows, EPI_GELU_TANH, s, nullptr, 0, &S.mx, &S.mff));
+      CAPDEC_RETURN_IF(linear(h, S.tff, F, gl(l, "mlp.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.mff)); }
     pending = S.ty;
   }
   { StageScope sc(h, STAGE_SMALL_GEMM, s);
-    CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s)); }
+    CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s, &S.mx)); }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   // lm_head is tied to wte and has no bias
   return vocab_project(h, S, S.txn, H, h->W("model.lm_head.weight"), nullptr, rows, S.logits, c.vocab_size, s);

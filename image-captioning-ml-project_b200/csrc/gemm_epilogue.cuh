@@ -24,8 +24,9 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
         if (EPI == EPI_TANH) t = th(t);
         if (EPI == EPI_GELU) t = gelu_erf_(t);
         if (EPI == EPI_GELU_TANH) t = gelu_tanh_(t);
-        p.C[(int64_t)m * p.ldc + n + j] = t;
+        if (p.C) p.C[(int64_t)m * p.ldc + n + j] = t;
         if (p.C2) p.C2[(int64_t)m * p.ldc2 + n + j] = t;
+        split_store1(p.c_split, m, n + j, t);
       }
       return;
     }
@@ -43,8 +44,9 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
     if (EPI == EPI_TANH) { v0 = th(v0); v1 = th(v1); v2 = th(v2); v3 = th(v3); }
     if (EPI == EPI_GELU) { v0 = gelu_erf_(v0); v1 = gelu_erf_(v1); v2 = gelu_erf_(v2); v3 = gelu_erf_(v3); }
     if (EPI == EPI_GELU_TANH) { v0 = gelu_tanh_(v0); v1 = gelu_tanh_(v1); v2 = gelu_tanh_(v2); v3 = gelu_tanh_(v3); }
-    *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v0, v1, v2, v3);
+    if (p.C) *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v0, v1, v2, v3);
     if (p.C2) *reinterpret_cast<float4*>(p.C2 + (int64_t)m * p.ldc2 + n) = make_float4(v0, v1, v2, v3);
+    split_store4(p.c_split, m, n, make_float4(v0, v1, v2, v3));
   } else if (EPI == EPI_LSTM) {
     // torch.nn.LSTMCell: c' = sigmoid(f)*c + sigmoid(i)*tanh(g);  h' = sigmoid(o)*tanh(c')
     const int j = n >> 2;

@@ -478,6 +478,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               h2[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); h2[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
             }
             split_store8(p.c_split, m, j0, hv);
+          } else if (epi_is_store_family(EPI) && p.c_split.hi != nullptr && m < p.M && nb0 + 32 <= p.N &&
+                     (p.ldc & 3) == 0 && (p.c_split.ld & 7) == 0) {
+            // store-family epilogue whose output is (also) the next GEMM's operand: 8 columns at a time so each mirror
+            // store is 16 bytes; the fp32 copy is optional (C == nullptr when only the GEMM reads it)
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float4 b = pre_b ? bia[(j + u) >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float bb = ((j + u) & 3) == 0 ? b.x : ((j + u) & 3) == 1 ? b.y : ((j + u) & 3) == 2 ? b.z : b.w;
+                float tv = __uint_as_float(v[j + u]) + bb;
+                if (EPI == EPI_SIGMOID_TAIL && n0 + j + u >= p.n_split) tv = sigmoid_fast_(tv);
+                if (EPI == EPI_TANH) tv = tanh_fast_(tv);
+                if (EPI == EPI_GELU) tv = gelu_erf_(tv);
+                if (EPI == EPI_GELU_TANH) tv = gelu_tanh_(tv);
+                o[u] = tv;
+              }
+              if (p.C) {
+                float4* dst = reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n0 + j);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+              split_store8(p.c_split, m, n0 + j, o);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)

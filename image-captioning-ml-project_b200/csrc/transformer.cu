@@ -3,6 +3,8 @@
 // LayerNorm, single-position causal self-attention over a back-pointer-indirected KV cache, and the ancestor-table
 // update that replaces copying the cache on beam reorder.  The cross-attention over the hoisted per-layer K/V
 // projections of the image regions reuses mha_attention_kernel (attn_mha.cu); all dense layers go through gemm().
+#include <stdlib.h>
+
 #include "transformer.cuh"
 
 namespace capdec {
@@ -10,32 +12,37 @@ namespace {
 
 // x[r,:] = embedding[tok[r],:] + pos[:]
 __global__ void __launch_bounds__(128) embed_pos_kernel(const int32_t* __restrict__ tok, const float* __restrict__ emb,
-                                                        const float* __restrict__ pos, float* __restrict__ x, int H) {
+                                                        const float* __restrict__ pos, float* __restrict__ x, int H,
+                                                        const SplitDst split) {
   const int r = blockIdx.x;
   const float4* e = reinterpret_cast<const float4*>(emb + (int64_t)tok[r] * H);
   const float4* p = reinterpret_cast<const float4*>(pos);
   float4* o = reinterpret_cast<float4*>(x + (int64_t)r * H);
   for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
     const float4 a = e[i], b = p[i];
-    o[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    o[i] = v;
+    split_store4(split, r, i * 4, v);
   }
 }
 
-// s = x + y (y may be null); optionally store s; out = LayerNorm(s) * gamma + beta   (eps inside the sqrt, biased var)
+// s = x + y (y may be null); optionally store s; out = LayerNorm(s) * gamma + beta   (eps inside the sqrt, biased var).
+// 128-bit loads / stores; `split` (optional) also writes out as the hi/lo operand copies of the GEMM that consumes it.
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ sum_out, float* __restrict__ out, int H,
-                                                            float eps) {
-  extern __shared__ float srow[];
+                                                            float eps, const SplitDst split) {
+  extern __shared__ __align__(16) float srow[];
   __shared__ float s_red[8];
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const float* xr = x + (int64_t)r * H;
-  const float* yr = y ? y + (int64_t)r * H : nullptr;
+  const int r = blockIdx.x, tid = threadIdx.x, H4 = H >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)r * H);
+  const float4* yr = y ? reinterpret_cast<const float4*>(y + (int64_t)r * H) : nullptr;
   float part = 0.f;
-  for (int i = tid; i < H; i += 256) {
-    const float v = xr[i] + (yr ? yr[i] : 0.f);
-    srow[i] = v;
-    part += v;
+  for (int i = tid; i < H4; i += 256) {
+    float4 v = xr[i];
+    if (yr) { const float4 w = yr[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    reinterpret_cast<float4*>(srow)[i] = v;
+    part += (v.x + v.y) + (v.z + v.w);
   }
   part = warp_sum(part);
   if ((tid & 31) == 0) s_red[tid >> 5] = part;
@@ -45,17 +52,25 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   mean /= (float)H;
   __syncthreads();
   float var = 0.f;
-  for (int i = tid; i < H; i += 256) { const float d = srow[i] - mean; var += d * d; }
+  for (int i = tid; i < H4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(srow)[i];
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    var += (a * a + b * b) + (c * c + d * d);
+  }
   var = warp_sum(var);
   if ((tid & 31) == 0) s_red[tid >> 5] = var;
   __syncthreads();
   float v = 0.f;
   for (int w = 0; w < 8; ++w) v += s_red[w];
   const float rstd = rsqrtf(v / (float)H + eps);
-  for (int i = tid; i < H; i += 256) {
-    const float s = srow[i];
-    if (sum_out) sum_out[(int64_t)r * H + i] = s;
-    out[(int64_t)r * H + i] = (s - mean) * rstd * gamma[i] + beta[i];
+  for (int i = tid; i < H4; i += 256) {
+    const float4 sv = reinterpret_cast<const float4*>(srow)[i];
+    const float4 g = reinterpret_cast<const float4*>(gamma)[i], bt = reinterpret_cast<const float4*>(beta)[i];
+    if (sum_out) reinterpret_cast<float4*>(sum_out + (int64_t)r * H)[i] = sv;
+    const float4 o = make_float4((sv.x - mean) * rstd * g.x + bt.x, (sv.y - mean) * rstd * g.y + bt.y,
+                                 (sv.z - mean) * rstd * g.z + bt.z, (sv.w - mean) * rstd * g.w + bt.w);
+    reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;
+    split_store4(split, r, i * 4, o);
   }
 }
 
@@ -118,7 +133,99 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int e = lane + 32 * j;
-    if (e < d) a.out[(int64_t)r * a.ld_out + hd * d + e] = acc[j] * inv;
+    if (e < d) {
+      a.out[(int64_t)r * a.ld_out + hd * d + e] = acc[j] * inv;
+      split_store1(a.out_split, r, hd * d + e, acc[j] * inv);
+    }
+  }
+}
+
+// Two-pass form for up to 128 keys (every config of the path: prefix 10 + max_len <= 50), one warp per (row, head).
+// Pass 1: lane = key -- every lane computes one COMPLETE q.k dot with 128-bit loads of its key's head slice (q is
+// broadcast from shared memory), so there is no per-key warp reduction; the softmax runs across the lanes.
+// Pass 2: lane = output element -- the weighted values accumulate with coalesced loads, weights come by shuffle.
+template <int NK>   // keys handled per lane: n_keys <= 32 * NK
+__global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
+  extern __shared__ __align__(16) float s_q[];   // [H] query of this row
+  const int r = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = a.H, d = H / a.heads, d4 = d >> 2, T = a.T, t = a.t;
+  const float* qkv = a.qkv + (int64_t)r * a.ld_qkv;
+  float* kc = a.cache_k + ((int64_t)r * T + t) * H;
+  float* vc = a.cache_v + ((int64_t)r * T + t) * H;
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+    reinterpret_cast<float4*>(s_q)[i] = reinterpret_cast<const float4*>(qkv)[i];
+    reinterpret_cast<float4*>(kc)[i] = reinterpret_cast<const float4*>(qkv + H)[i];
+    reinterpret_cast<float4*>(vc)[i] = reinterpret_cast<const float4*>(qkv + 2 * H)[i];
+  }
+  __syncthreads();
+  const int hd = warp;
+  if (hd >= a.heads) return;
+  const int img = r / a.rows_per_image;
+  const int n_keys = a.n_prefix + t + 1;
+  auto key_ptr = [&](int p, const float* prefix, const float* cache) -> const float* {
+    if (p < a.n_prefix) return prefix + ((int64_t)img * a.n_prefix + p) * H + hd * d;
+    const int pos = p - a.n_prefix;
+    const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
+    return cache + ((int64_t)prow * T + pos) * H + hd * d;
+  };
+  // ---- pass 1: scores, lane = key
+  const float4* q4 = reinterpret_cast<const float4*>(s_q + hd * d);
+  float sc[NK];
+#pragma unroll
+  for (int i = 0; i < NK; ++i) {
+    const int p = lane + 32 * i;
+    sc[i] = -INFINITY;
+    if (p < n_keys) {
+      const float4* k4 = reinterpret_cast<const float4*>(key_ptr(p, a.prefix_k, a.cache_k));
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      for (int e = 0; e < d4; ++e) {
+        const float4 kv = k4[e], qv = q4[e];
+        d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+      }
+      sc[i] = ((d0 + d1) + (d2 + d3)) * a.scale;
+    }
+  }
+  // ---- softmax across the lanes
+  float m = sc[0];
+#pragma unroll
+  for (int i = 1; i < NK; ++i) m = fmaxf(m, sc[i]);
+  m = warp_max(m);
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < NK; ++i) { sc[i] = expf(sc[i] - m); l += sc[i]; }   // exp(-inf) = 0 for the unused slots
+  l = warp_sum(l);
+  const float inv = 1.f / l;
+  // ---- pass 2: weighted values, lane = output element
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p0 = 0; p0 < n_keys; p0 += 4) {
+    const float* vp[4];
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = min(p0 + u, n_keys - 1);
+      vp[u] = key_ptr(p, a.prefix_v, a.cache_v);
+      float wv = 0.f;
+#pragma unroll
+      for (int i = 0; i < NK; ++i) { const float cand = __shfl_sync(0xffffffffu, sc[i], p & 31); if (i == (p >> 5)) wv = cand; }
+      w[u] = p0 + u < n_keys ? wv : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = lane + 32 * j;
+      if (e < d) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[j] = fmaf(w[u], vp[u][e], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = lane + 32 * j;
+    if (e < d) {
+      a.out[(int64_t)r * a.ld_out + hd * d + e] = acc[j] * inv;
+      split_store1(a.out_split, r, hd * d + e, acc[j] * inv);
+    }
   }
 }
 
@@ -135,17 +242,20 @@ __global__ void reorder_ancestors_kernel(const int32_t* __restrict__ src, const 
 
 }  // namespace
 
-int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s) {
+int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s,
+              const SplitDst* split) {
   if (rows == 0) return CAPDEC_OK;
-  embed_pos_kernel<<<rows, 128, 0, s>>>(tok, emb, pos_row, x, H);
+  embed_pos_kernel<<<rows, 128, 0, s>>>(tok, emb, pos_row, x, H, split ? *split : SplitDst{});
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
 
 int add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float* sum_out, float* out,
-                  int rows, int H, float eps, cudaStream_t s) {
+                  int rows, int H, float eps, cudaStream_t s, const SplitDst* split) {
   if (rows == 0) return CAPDEC_OK;
-  add_layernorm_kernel<<<rows, 256, (size_t)H * sizeof(float), s>>>(x, y, gamma, beta, sum_out, out, H, eps);
+  CAPDEC_REQUIRE(H % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "add_layernorm: H must be a multiple of 4");
+  add_layernorm_kernel<<<rows, 256, (size_t)H * sizeof(float), s>>>(x, y, gamma, beta, sum_out, out, H, eps,
+                                                                    split ? *split : SplitDst{});
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -155,6 +265,16 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
                  "self_attn_decode: heads=%d head_dim=%d unsupported (head_dim <= 128, heads <= 32)", a.heads,
                  a.heads ? a.H / a.heads : 0);
   if (a.rows == 0) return CAPDEC_OK;
+  const int n_keys = a.n_prefix + a.t + 1;
+  static const bool old_form = getenv("CAPDEC_SELFATTN_ONLINE") != nullptr;
+  if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && a.H * sizeof(float) <= 48 * 1024) {
+    const size_t smem = (size_t)a.H * sizeof(float);
+    if (n_keys <= 32)      self_attn_decode2_kernel<1><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    else if (n_keys <= 64) self_attn_decode2_kernel<2><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    else                   self_attn_decode2_kernel<4><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    CAPDEC_LAUNCH_CHECK();
+    return CAPDEC_OK;
+  }
   self_attn_decode_kernel<<<a.rows, 32 * a.heads, 0, s>>>(a);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;

@@ -12,12 +12,14 @@ struct SelfAttnArgs {
   int rows_per_image;
   float scale;                          // 1/sqrt(head_dim)
   float* out; int64_t ld_out;           // [R, H]
+  SplitDst out_split;                   // optional: out also as the split operand of the projection GEMM that follows
   int rows, H, heads, T, t;
 };
 
-int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s);
+int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s,
+              const SplitDst* split = nullptr);
 int add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float* sum_out, float* out,
-                  int rows, int H, float eps, cudaStream_t s);
+                  int rows, int H, float eps, cudaStream_t s, const SplitDst* split = nullptr);
 int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s);
 int reorder_ancestors(const int32_t* src, const int32_t* anc_old, int32_t* anc_new, int rows, int T, int t_done,
                       cudaStream_t s);
