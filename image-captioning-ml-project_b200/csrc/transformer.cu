@@ -141,15 +141,16 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 }
 
 // Two-pass form for up to 128 keys (every config of the path: prefix 10 + max_len <= 50), one warp per (row, head).
-// Pass 1: lane = key -- every lane computes one COMPLETE q.k dot with 128-bit loads of its key's head slice (q is
-// broadcast from shared memory), so there is no per-key warp reduction; the softmax runs across the lanes.
-// Pass 2: lane = output element -- the weighted values accumulate with coalesced loads, weights come by shuffle.
-template <int NK>   // keys handled per lane: n_keys <= 32 * NK
+// Pass 1: lane = key -- every lane resolves the address of ITS key once (prefix row or ancestor-indirected cache row)
+// and computes one COMPLETE q.k dot with 128-bit loads of the key's head slice (q is broadcast from shared memory), so
+// there is no per-key warp reduction; the softmax runs across the lanes.
+// Pass 2: lane = output element -- key p's value pointer and weight come from lane p by shuffle, the loads are coalesced.
+template <int NK, int D4T>   // keys per lane (n_keys <= 32 * NK); head_dim / 4 when known at compile time (0 = runtime)
 __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   extern __shared__ __align__(16) float s_q[];   // [H] query of this row
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = a.H, d = H / a.heads, d4 = d >> 2, T = a.T, t = a.t;
+  const int H = a.H, d = H / a.heads, d4 = D4T > 0 ? D4T : (d >> 2), T = a.T, t = a.t;
   const float* qkv = a.qkv + (int64_t)r * a.ld_qkv;
   float* kc = a.cache_k + ((int64_t)r * T + t) * H;
   float* vc = a.cache_v + ((int64_t)r * T + t) * H;
@@ -163,25 +164,40 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   if (hd >= a.heads) return;
   const int img = r / a.rows_per_image;
   const int n_keys = a.n_prefix + t + 1;
-  auto key_ptr = [&](int p, const float* prefix, const float* cache) -> const float* {
-    if (p < a.n_prefix) return prefix + ((int64_t)img * a.n_prefix + p) * H + hd * d;
-    const int pos = p - a.n_prefix;
-    const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
-    return cache + ((int64_t)prow * T + pos) * H + hd * d;
-  };
   // ---- pass 1: scores, lane = key
   const float4* q4 = reinterpret_cast<const float4*>(s_q + hd * d);
   float sc[NK];
+  const float* vptr[NK];
 #pragma unroll
   for (int i = 0; i < NK; ++i) {
     const int p = lane + 32 * i;
     sc[i] = -INFINITY;
+    vptr[i] = a.cache_v;
     if (p < n_keys) {
-      const float4* k4 = reinterpret_cast<const float4*>(key_ptr(p, a.prefix_k, a.cache_k));
+      const float* kptr;
+      if (p < a.n_prefix) {
+        const int64_t off = ((int64_t)img * a.n_prefix + p) * H + hd * d;
+        kptr = a.prefix_k + off; vptr[i] = a.prefix_v + off;
+      } else {
+        const int pos = p - a.n_prefix;
+        const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
+        const int64_t off = ((int64_t)prow * T + pos) * H + hd * d;
+        kptr = a.cache_k + off; vptr[i] = a.cache_v + off;
+      }
+      const float4* k4 = reinterpret_cast<const float4*>(kptr);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-      for (int e = 0; e < d4; ++e) {
-        const float4 kv = k4[e], qv = q4[e];
-        d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+#pragma unroll
+      for (int e = 0; e < (D4T > 0 ? D4T : 1); ++e) {
+        if (D4T > 0) {
+          const float4 kv = k4[e], qv = q4[e];
+          d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+        }
+      }
+      if (D4T == 0) {
+        for (int e = 0; e < d4; ++e) {
+          const float4 kv = k4[e], qv = q4[e];
+          d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+        }
       }
       sc[i] = ((d0 + d1) + (d2 + d3)) * a.scale;
     }
@@ -196,27 +212,30 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   for (int i = 0; i < NK; ++i) { sc[i] = expf(sc[i] - m); l += sc[i]; }   // exp(-inf) = 0 for the unused slots
   l = warp_sum(l);
   const float inv = 1.f / l;
-  // ---- pass 2: weighted values, lane = output element
+  // ---- pass 2: weighted values, lane = output element (up to 4 strided elements of the head dimension, d <= 128)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int p0 = 0; p0 < n_keys; p0 += 4) {
-    const float* vp[4];
-    float w[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = min(p0 + u, n_keys - 1);
-      vp[u] = key_ptr(p, a.prefix_v, a.cache_v);
-      float wv = 0.f;
+  for (int i = 0; i < NK; ++i) {
+    const int n_here = min(32, n_keys - 32 * i);
+    for (int p0 = 0; p0 < n_here; p0 += 4) {   // 4 keys per round: 8 independent loads in flight per lane
+      float w[4];
+      const float* vp[4];
 #pragma unroll
-      for (int i = 0; i < NK; ++i) { const float cand = __shfl_sync(0xffffffffu, sc[i], p & 31); if (i == (p >> 5)) wv = cand; }
-      w[u] = p0 + u < n_keys ? wv : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = lane + 32 * j;
-      if (e < d) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[j] = fmaf(w[u], vp[u][e], acc[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int pl = min(p0 + u, n_here - 1);
+        const float wv = __shfl_sync(0xffffffffu, sc[i], pl);
+        vp[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)vptr[i], pl));
+        w[u] = p0 + u < n_here ? wv : 0.f;
       }
+      float x[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int e = lane + 32 * j; x[u][j] = e < d ? vp[u][e] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[u], x[u][j], acc[j]);
     }
   }
 #pragma unroll
@@ -269,9 +288,15 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
   static const bool old_form = getenv("CAPDEC_SELFATTN_ONLINE") != nullptr;
   if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && a.H * sizeof(float) <= 48 * 1024) {
     const size_t smem = (size_t)a.H * sizeof(float);
-    if (n_keys <= 32)      self_attn_decode2_kernel<1><<<a.rows, 32 * a.heads, smem, s>>>(a);
-    else if (n_keys <= 64) self_attn_decode2_kernel<2><<<a.rows, 32 * a.heads, smem, s>>>(a);
-    else                   self_attn_decode2_kernel<4><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    const int d4 = a.H / a.heads / 4;
+#define CAPDEC_SA_LAUNCH(NKV)                                                                               \
+    if (d4 == 16)      self_attn_decode2_kernel<NKV, 16><<<a.rows, 32 * a.heads, smem, s>>>(a);            \
+    else if (d4 == 24) self_attn_decode2_kernel<NKV, 24><<<a.rows, 32 * a.heads, smem, s>>>(a);            \
+    else               self_attn_decode2_kernel<NKV, 0><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    if (n_keys <= 32)      { CAPDEC_SA_LAUNCH(1) }
+    else if (n_keys <= 64) { CAPDEC_SA_LAUNCH(2) }
+    else                   { CAPDEC_SA_LAUNCH(4) }
+#undef CAPDEC_SA_LAUNCH
     CAPDEC_LAUNCH_CHECK();
     return CAPDEC_OK;
   }
