@@ -274,7 +274,9 @@ def main():
         peak, peak_src = measured_peaks()
         att_ms, att_n = stage["attention"]
         per_launch_ms = att_ms / max(att_n, 1)
-        achieved = ATTN_BYTES_PER_IMAGE_STEP * B / (per_launch_ms * 1e-3) / 1e9 if att_n else None
+        # the bf16 mode streams bf16 tiles (half the algorithmic bytes); every other mode streams the fp32 tiles
+        attn_bytes = ATTN_BYTES_PER_IMAGE_STEP // 2 if args.precision == "bf16" else ATTN_BYTES_PER_IMAGE_STEP
+        achieved = attn_bytes * B / (per_launch_ms * 1e-3) / 1e9 if att_n else None
         traffic = None
         tf = os.path.join(ROOT, "profiles", "attention_traffic.json")
         if os.path.isfile(tf):
@@ -291,10 +293,10 @@ def main():
                        "l2_policy": "inputs (6.6 GB/GPU) larger than L2, no flush"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"kernel": "additive_attention_stream_kernel<5,relu,2>", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "additive_attention_stream_kernel<5,relu,2,%s>" % ("bf16" if args.precision == "bf16" else "f32"), "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ATTN_BYTES_PER_IMAGE_STEP * B,
+                         "traffic": traffic if args.precision != "bf16" else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": attn_bytes * B,
                          "avg_launch_ms": per_launch_ms, "launches": att_n},
             "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},
             "stage_share": {k: round(v[0] / total_stage_ms, 4) for k, v in stage.items()},

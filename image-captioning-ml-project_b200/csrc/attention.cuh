@@ -23,6 +23,8 @@ struct AddAttnArgs {
   float w_bias, temperature;
   const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr
   const float* feats;                   // [B,L,D]
+  int tile_bf16;                        // 1: att1 and feats point at bf16 tiles of the same shapes (the bf16 precision mode
+                                        // streams half the bytes; streaming kernel only)
   const float* gate; int64_t ld_gate;   // [R,D] or nullptr
   float* ctx; int64_t ld_ctx;           // [R,D]  (may be nullptr when ctx_split carries the only consumer's copy)
   SplitDst ctx_split; int ctx_split_col; // optional: ctx also/only as the split GEMM operand, at column ctx_split_col
@@ -33,6 +35,8 @@ int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s);
 // persistent TMA-streamed form (attn_stream.cu): returns 1 if it took the call, 0 if the shape is left to the generic
 // kernel in attn_additive.cu, < 0 on error
 int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s);
+// whether the streaming kernel covers a shape (callers that want bf16 tiles must know before they lay out the workspace)
+bool additive_attention_stream_supports(int A, int D, int L, int k, bool tile_bf16);
 
 // Multi-head dot-product attention on hoisted per-image K/V projections, all k rows of an image per CTA:
 //   s[b,h,l] = q[row_b,h,:] . K[img,l,h,:] / denom      (masked -> -1e9)

@@ -71,8 +71,20 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) { return ACT == ACT_RELU ? fmaxf(x, 0.f) : tanhf(x); }
 
-template <int KB, int ACT, int NC>
+// 4 consecutive elements (index i4 counts groups of 4) of a shared-memory tile row holding fp32 or bf16 data
+template <int BF>
+__device__ __forceinline__ float4 tile_ld4(const void* row, int i4) {
+  if (BF) {
+    const uint2 u = reinterpret_cast<const uint2*>(row)[i4];
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                       __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  }
+  return reinterpret_cast<const float4*>(row)[i4];
+}
+
+template <int KB, int ACT, int NC, int BF>
 __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(const AddAttnArgs p, const StreamLayout y) {
+  constexpr size_t ES = BF ? 2 : 4;   // bytes per tile element
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ringA = smem + y.off_ringA;
   uint8_t* ringF = smem + y.off_ringF;
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     // ================================ feats producer ================================
     if (lane == 0) {
       uint32_t itF = 0;
-      const size_t rowF = (size_t)D * sizeof(float);
+      const size_t rowF = (size_t)D * ES;
       for (int i = 0; i < n_img; ++i) {
         const int img = blockIdx.x + i * gridDim.x;
         for (int c = 0; c < y.nF; ++c, ++itF) {
@@ -113,7 +125,8 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           const int rows = min(y.rowsF, L - c * y.rowsF);
           const uint32_t bytes = (uint32_t)(rows * rowF);
           mbar_expect_tx(&fullF[s], bytes);
-          bulk_load(ringF + (size_t)s * y.stageF, p.feats + ((size_t)img * L + (size_t)c * y.rowsF) * D, bytes, &fullF[s]);
+          bulk_load(ringF + (size_t)s * y.stageF,
+                    reinterpret_cast<const char*>(p.feats) + ((size_t)img * L + (size_t)c * y.rowsF) * rowF, bytes, &fullF[s]);
         }
       }
     }
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     // ================================ att1 producer ================================
     if (lane == 0) {
       uint32_t itA = 0;
-      const size_t rowA = (size_t)A * sizeof(float);
+      const size_t rowA = (size_t)A * ES;
       for (int i = 0; i < n_img; ++i) {
         const int img = blockIdx.x + i * gridDim.x;
         for (int c = 0; c < y.nA; ++c, ++itA) {
@@ -130,7 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           const int rows = min(y.rowsA, L - c * y.rowsA);
           const uint32_t bytes = (uint32_t)(rows * rowA);
           mbar_expect_tx(&fullA[s], bytes);
-          bulk_load(ringA + (size_t)s * y.stageA, p.att1 + ((size_t)img * L + (size_t)c * y.rowsA) * A, bytes, &fullA[s]);
+          bulk_load(ringA + (size_t)s * y.stageA,
+                    reinterpret_cast<const char*>(p.att1) + ((size_t)img * L + (size_t)c * y.rowsA) * rowA, bytes, &fullA[s]);
         }
       }
     }
@@ -160,16 +174,16 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
         const int s = itA % kStagesA;
         mbar_wait(&fullA[s], (itA / kStagesA) & 1);
         const int rows = min(y.rowsA, L - c * y.rowsA);
-        const float* tile = reinterpret_cast<const float*>(ringA + (size_t)s * y.stageA);
+        const uint8_t* tile = ringA + (size_t)s * y.stageA;
         for (int r = sw * 2; r < rows; r += kScoreWarps * 2) {
           const int r1 = min(r + 1, rows - 1);
-          const float4* x0p = reinterpret_cast<const float4*>(tile + (size_t)r * A);
-          const float4* x1p = reinterpret_cast<const float4*>(tile + (size_t)r1 * A);
+          const void* x0p = tile + (size_t)r * A * ES;
+          const void* x1p = tile + (size_t)r1 * A * ES;
           float acc0[KB], acc1[KB];
 #pragma unroll
           for (int b = 0; b < KB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
           for (int a4 = lane; a4 < A4; a4 += 32) {
-            const float4 x0 = x0p[a4], x1 = x1p[a4];
+            const float4 x0 = tile_ld4<BF>(x0p, a4), x1 = tile_ld4<BF>(x1p, a4);
             const float4 wv = reinterpret_cast<const float4*>(s_w)[a4];
 #pragma unroll
             for (int b = 0; b < KB; ++b) {
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
         const int s = itF % kStagesF;
         mbar_wait(&fullF[s], (itF / kStagesF) & 1);
         const int rows = min(y.rowsF, L - c * y.rowsF);
-        const float4* tile = reinterpret_cast<const float4*>(ringF + (size_t)s * y.stageF);
+        const uint8_t* tile = ringF + (size_t)s * y.stageF;
         if (active) {
           for (int r = g; r < rows; r += y.G) {
             const int l = c * y.rowsF + r;
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
               const int col = c0 + j * kCtxThreads;
-              x[j] = col < D4 ? tile[(size_t)r * D4 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[j] = col < D4 ? tile_ld4<BF>(tile + (size_t)r * D * ES, col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int b = 0; b < KB; ++b) {
@@ -326,11 +340,12 @@ int sm_count() {
 // Shared-memory plan; returns false when the shape does not fit this kernel (the caller uses the generic kernel).
 bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   const int A4 = a.A / 4, D4 = a.D / 4;
-  if (a.A % 4 || a.D % 4 || D4 > 2 * kCtxThreads || a.L < 1) return false;
+  const size_t es = a.tile_bf16 ? 2 : 4;
+  if (a.A % 8 || a.D % 8 || D4 > 2 * kCtxThreads || a.L < 1) return false;   // rows are multiples of 16 bytes in either tile type
   if ((((uintptr_t)a.att1 | (uintptr_t)a.feats | (uintptr_t)a.att2 | (uintptr_t)a.w) & 15) != 0) return false;
   int G = 1;
   if (D4 <= kCtxThreads / 2) { while (D4 * G * 2 <= kCtxThreads) G *= 2; }
-  const size_t rowA = (size_t)a.A * 4, rowF = (size_t)a.D * 4;
+  const size_t rowA = (size_t)a.A * es, rowF = (size_t)a.D * es;
   const int Lp = (a.L + 3) & ~3;
   size_t fixed = 0;
   auto take = [&](size_t bytes) { const size_t o = fixed; fixed = (fixed + bytes + 127) & ~(size_t)127; return (uint32_t)o; };
@@ -372,20 +387,33 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
   static const int cap = getenv("CAPDEC_ATTN_MAX_CTAS") ? atoi(getenv("CAPDEC_ATTN_MAX_CTAS")) : 0;   // experiments: SM partitioning
   int grid = a.B < sm_count() ? a.B : sm_count();
   if (cap > 0 && grid > cap) grid = cap;
-#define CAPDEC_STREAM_LAUNCH(ACTV, NCV)                                                                                   \
+#define CAPDEC_STREAM_LAUNCH(ACTV, NCV, BFV)                                                                              \
   {                                                                                                                       \
-    auto kern = additive_attention_stream_kernel<KB, ACTV, NCV>;                                                          \
+    auto kern = additive_attention_stream_kernel<KB, ACTV, NCV, BFV>;                                                     \
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));             \
     kern<<<grid, kThreads, y.total, s>>>(a, y);                                                                           \
   }
-  if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2) }
-  else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2) }
+  if (a.tile_bf16) {
+    if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }
+    else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 1) }
+  } else {
+    if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 0) }
+    else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 0) }
+  }
 #undef CAPDEC_STREAM_LAUNCH
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
 
 }  // namespace
+
+bool additive_attention_stream_supports(int A, int D, int L, int k, bool tile_bf16) {
+  if (getenv("CAPDEC_ATTN_GENERIC") != nullptr || k < 1 || k > kMaxRowsPerImage) return false;
+  AddAttnArgs a{};
+  a.A = A; a.D = D; a.L = L; a.k = k; a.tile_bf16 = tile_bf16 ? 1 : 0;
+  StreamLayout y{};
+  return plan(a, k <= 6 ? k : 8, &y);
+}
 
 // returns 1 when the streaming kernel took the call, 0 when the shape is left to the generic kernel, < 0 on error
 int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s) {

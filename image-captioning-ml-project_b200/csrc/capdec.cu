@@ -124,6 +124,9 @@ struct Session {
   // legacy, tensor-core modes: the producers of the gate / vocabulary GEMM operands (attention context, state gather,
   // LSTM epilogue) write the hi/lo operand copies themselves, so no split pass runs inside the step loop
   void* xs_hi = nullptr; void* xs_lo = nullptr; void* hs_hi = nullptr; void* hs_lo = nullptr; bool presplit = false;
+  // legacy, bf16 mode: the region tiles the attention kernel streams every step are kept in bf16 (half the bytes):
+  // feats_h [B,L,D] is also the att1 GEMM's operand, att1_h [B,L,A] comes straight out of that GEMM's epilogue
+  void* feats_h = nullptr; void* att1_h = nullptr;
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
@@ -235,8 +238,13 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.hs_hi = ar.take<char>(R * H * es);
       S.hs_lo = lo ? ar.take<char>(R * H * es) : nullptr;
       S.presplit = true;
+      if (c.precision == CAPDEC_PREC_BF16 && A % 8 == 0 && D % 8 == 0 && !getenv("CAPDEC_NO_BF16_TILES") &&
+          additive_attention_stream_supports(A, D, L, k, true)) {
+        S.feats_h = ar.take<char>((size_t)B * L * D * 2);
+        S.att1_h = ar.take<char>((size_t)B * L * A * 2);
+      }
     }
-    S.att1 = ar.take<float>((size_t)B * L * A);
+    if (!S.att1_h) S.att1 = ar.take<float>((size_t)B * L * A);
     S.meanb = ar.take<float>((size_t)B * D);
     S.init = ar.take<float>((size_t)B * 2 * H);
     S.hproj = ar.take<float>(R * (A + D));
@@ -314,7 +322,15 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
   // att1 = enc_att(enc)  (models/decoder.py:152, hoisted)
-  CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s));
+  if (S.att1_h) {
+    // bf16 mode: one conversion pass makes the bf16 feature tiles (GEMM operand AND what attention streams every step);
+    // the GEMM's epilogue emits att1 directly as bf16 tiles
+    CAPDEC_RETURN_IF(tc_split(c.precision, feats, D, S.B * S.L, D, S.feats_h, nullptr, s));
+    const SplitDst a_pre{S.feats_h, nullptr, D, KIND_BF16}, c_out{S.att1_h, nullptr, A, KIND_BF16};
+    CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", nullptr, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &a_pre, &c_out));
+  } else {
+    CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s));
+  }
   // h0, c0 = h_lin(mean), c_lin(mean)  (:137-139)
   CAPDEC_RETURN_IF(mean_regions(feats, S.B, S.L, D, S.meanb, s));
   GemmArgs g{};
@@ -444,8 +460,10 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   // scores -> softmax -> gated context, written straight into the LSTM operand (:154-161)
   AddAttnArgs a{};
   a.row_src = reuse ? S.row_src : nullptr;
-  a.att1 = S.att1; a.att2 = S.hproj; a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
-  a.temperature = 1.f; a.mask = nullptr; a.feats = feats; a.gate = S.hproj + A; a.ld_gate = A + D;
+  a.att1 = S.att1; a.att2 = S.hproj;
+  if (S.att1_h) { a.att1 = reinterpret_cast<const float*>(S.att1_h); a.tile_bf16 = 1; } a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
+  a.temperature = 1.f; a.mask = nullptr; a.feats = S.att1_h ? reinterpret_cast<const float*>(S.feats_h) : feats;
+  a.gate = S.hproj + A; a.ld_gate = A + D;
   a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;
   a.B = images; a.L = S.L; a.A = A; a.D = D; a.k = S.k;
   const int kind = tc_kind(c.precision);
