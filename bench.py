@@ -138,7 +138,8 @@ def main():
     ap.add_argument("--impl", default="capdec", choices=["capdec", "reference"])
     ap.add_argument("--images", type=int, default=env_int("CAPDEC_BENCH_IMAGES", 4096), help="images per GPU")
     ap.add_argument("--precision", default=os.environ.get("CAPDEC_BENCH_PRECISION", "bf16x3"))
-    ap.add_argument("--chunk", type=int, default=env_int("CAPDEC_BENCH_CHUNK", 512), help="e2e H2D pipeline chunk (images)")
+    ap.add_argument("--chunk", type=int, default=env_int("CAPDEC_BENCH_CHUNK", 0),
+                    help="e2e H2D pipeline chunk in images (0 = the library default, two images per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-modes", action="store_true")
@@ -243,7 +244,8 @@ def main():
         same = bool(torch.equal(host_out["tokens"], out["tokens"].cpu()))
         e2e = {"value": B * world / (e2e_ms / 1000.0), "unit": "images/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(feats_host.numel() * 4),
-               "d2h_bytes_per_step": int(B * MAXLEN * 4 + B * 8), "chunk_images": args.chunk,
+               "d2h_bytes_per_step": int(B * MAXLEN * 4 + B * 8),
+               "chunk_images": args.chunk if args.chunk > 0 else 2 * torch.cuda.get_device_properties(dev).multi_processor_count,
                "matches_device_path": same}
 
     # ---- the other tensor-core modes on the same workload (reported beside the headline, N=1 only)

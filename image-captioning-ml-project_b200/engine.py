@@ -167,7 +167,7 @@ class Engine:
         return ctx, w
 
     def decode_beam_host(self, features_host, pooled_host, num_beams, max_length, length_penalty=1.0,
-                         chunk_images=512, out=None):
+                         chunk_images=0, out=None):
         """End-to-end path: host (pinned) buffers in, host buffers out, copies inside the call."""
         assert features_host.device.type == "cpu" and features_host.dtype == torch.float32 and features_host.is_contiguous()
         B, L = features_host.shape[0], features_host.shape[1]

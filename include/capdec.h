@@ -162,7 +162,8 @@ int capdec_attention_forward(capdec_handle* h, const float* query_dev, const flo
  * Same as capdec_decode_beam but every buffer is HOST memory (pinned recommended): the call
  * allocates device staging on first use, streams the features host->device in image chunks
  * overlapped with the decode of the previous chunk, copies tokens/lengths/scores back and
- * synchronises before returning.  This is the call bench.py times for the `e2e` figure. */
+ * synchronises before returning.  chunk_images <= 0 selects the default (two images per SM).  This is the call
+ * bench.py times for the `e2e` figure. */
 int capdec_decode_beam_host(capdec_handle* h, const float* features_host, const float* pooled_host,
                             int32_t num_images, int32_t num_regions, int32_t num_beams,
                             int32_t max_length, float length_penalty, int32_t chunk_images,

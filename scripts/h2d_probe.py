@@ -24,7 +24,7 @@ model = model.to(dev)
 eng = model._engine(dev)
 out = {"tokens": torch.empty(B, 20, dtype=torch.int32).pin_memory(), "lengths": torch.empty(B, dtype=torch.int32).pin_memory(),
        "scores": torch.empty(B, dtype=torch.float32).pin_memory()}
-for chunk in (128, 256, 512, 1024):
+for chunk in [int(x) for x in os.environ.get("CHUNKS", "296,444,512,592,740").split(",")]:
     for _ in range(2):
         eng.decode_beam_host(host, None, 5, 20, chunk_images=chunk, out=out)
     torch.cuda.synchronize()
