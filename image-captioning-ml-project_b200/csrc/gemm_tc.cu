@@ -1,17 +1,19 @@
-// tcgen05 GEMM for the dense contractions of the decode step (CAPDEC_PREC_TF32X3):
-//     C[M,N] = A[M,K] * W[N,K]^T + bias,  fused epilogues as in gemm_epilogue.cuh
-// fp32-equivalent accuracy on the 5th-gen tensor cores by the 3-term TF32 split
-//     a = a_hi + a_lo,  w = w_hi + w_lo   (hi = cvt.rna.tf32(x), lo = x - hi, exact in fp32)
-//     a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi       (the dropped lo*lo term is ~2^-22 relative)
-// accumulated in fp32 in TMEM.  tcgen05 has no IEEE-fp32 MMA; this is the split-accumulate form
-// SURVEY.md section 7 names for the fp32 mode.
+// tcgen05 GEMM for the dense contractions of the decode step (all tensor-core precision modes):
+//     C[M,N] = A[M,K] * W[N,K]^T + bias,  fused epilogues as in gemm_epilogue.cuh + the chunk-level ones below
+// tcgen05 has no IEEE-fp32 MMA, so fp32-grade accuracy comes from a 3-term operand split
+//     a = a_hi + a_lo,  w = w_hi + w_lo,    a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi   (lo*lo dropped)
+// accumulated in fp32 in TMEM, either on kind::tf32 (hi = cvt.rna.tf32, lo = exact residual; CAPDEC_PREC_TF32X3) or
+// on kind::f16 with bf16 operands (hi = bf16_rn(x), lo = bf16_rn(x - hi); CAPDEC_PREC_BF16X3, same three MMAs at
+// twice the rate).  CAPDEC_PREC_TF32 / CAPDEC_PREC_BF16 are the single-term forms.
 //
-// Kernel: one 128 x BN output tile per CTA, K streamed in 32-float (128-byte, SWIZZLE_128B) blocks.
+// Kernel (persistent, one CTA or one CTA PAIR per 128/256 x 256 output tile, K streamed in 128-byte SWIZZLE_128B blocks):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A_hi/A_lo/W_hi/W_lo tiles, mbarrier tx
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8),
-//               tcgen05.commit releases shared-memory stages and publishes the accumulator
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M = 128 or 256 with cta_group::2, N = 256),
+//               tcgen05.commit releases shared-memory stages and publishes the (double-buffered) accumulator
 //   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global; warp w reads TMEM
 //               lane quadrant w % 4 and column half (w - 2) / 4 of the tile, so every scheduler has two epilogue warps
+// A operands may arrive pre-split (GemmArgs::A_hi/A_lo, written by the kernel that produced them); otherwise
+// split_kernel makes the copies.  Weights are split once per handle.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <limits.h>
