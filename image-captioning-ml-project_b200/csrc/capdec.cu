@@ -481,6 +481,13 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   if (S.presplit) {
     l.A_hi = S.xs_hi; l.A_lo = S.xs_lo; l.ld_as = S.ldX[0];
     l.c_split = SplitDst{S.hs_hi, S.hs_lo, H, kind};   // new h as the vocabulary GEMM's operand
+    if (h->emb_gates) {
+      // the embedding columns of [emb | ctx | h] are served by the per-token table: K shrinks from E+D+H to D+H
+      const size_t es = kind == KIND_BF16 ? 2 : 4;
+      l.A = S.X[0] + E; l.W = h->w_gates[0] + E; l.K = D + H;
+      l.A_hi = (const char*)S.xs_hi + (size_t)E * es; l.A_lo = S.xs_lo ? (const char*)S.xs_lo + (size_t)E * es : nullptr;
+      l.row_table = h->emb_gates; l.row_index = S.next_tok; l.ld_table = 4 * H;
+    }
   }
   { StageScope sc(h, STAGE_GATE_GEMM, s); CAPDEC_RETURN_IF(gemm(h, c.precision, l, EPI_LSTM, s)); }
   // fc(h)  (:171; dropout is the identity in eval)
@@ -710,6 +717,7 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
   }
   g.n_state = n;
   if (S.presplit && is_legacy(h)) {
+    if (h->emb_gates) g.embedding = nullptr;   // the gate GEMM reads the token's row of emb_gates instead of X[:, :E]
     g.x_split = SplitDst{S.xs_hi, S.xs_lo, S.ldX[0], tc_kind(c.precision)};
     for (int i = 0; i < 16; ++i) g.state_split_col[i] = -1;
     if (with_state) g.state_split_col[0] = E + D;   // state 0 = new h of the single legacy layer -> X[:, E+D:]
@@ -870,7 +878,7 @@ int capdec_finalize(capdec_handle* h, void* stream) {
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear(); h->w_gates.clear(); h->b_gates.clear(); h->gate_in.clear();
   h->w_hproj = h->b_hproj = h->w_init = h->b_init = h->w_aoa = h->b_aoa = nullptr;
-  h->w_vocab_cat = h->b_vocab_cat = nullptr; h->vocab_cat_n = 0;
+  h->w_vocab_cat = h->b_vocab_cat = nullptr; h->vocab_cat_n = 0; h->emb_gates = nullptr;
 
   if (is_gpt2(h)) {
     // src/models/decoders.py:513-561 + transformers GPT2LMHeadModel parameter names; Conv1D weights are bound
@@ -942,6 +950,13 @@ int capdec_finalize(capdec_handle* h, void* stream) {
     CAPDEC_RETURN_IF(scatter_rows(h->w_hproj + A * H, H, 1, 0, 0, h->W("f_beta.weight"), H, (int)D, (int)H, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj, 1, 1, 0, 0, h->W("dec_att.bias"), 1, (int)A, 1, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj + A, 1, 1, 0, 0, h->W("f_beta.bias"), 1, (int)D, 1, false, s));
+    if (c.precision != CAPDEC_PREC_FP32 && !getenv("CAPDEC_NO_EMB_TABLE")) {
+      CAPDEC_RETURN_IF(dev_alloc(h, &h->emb_gates, (size_t)V * 4 * H));
+      GemmArgs g{};
+      g.A = h->W("embedding.weight"); g.lda = E; g.W = h->w_gates[0]; g.ldw = E + D + H; g.bias = nullptr;
+      g.C = h->emb_gates; g.ldc = 4 * H; g.M = (int)V; g.N = (int)(4 * H); g.K = (int)E;
+      CAPDEC_RETURN_IF(gemm_ffma(g, EPI_STORE, s));
+    }
     if (c.precision != CAPDEC_PREC_FP32 && !getenv("CAPDEC_NO_HPROJ_TAIL")) {
       const int64_t Vp = (V + 255) / 256 * 256, Nc = Vp + A + D;
       CAPDEC_RETURN_IF(dev_alloc(h, &h->w_vocab_cat, (size_t)Nc * H));

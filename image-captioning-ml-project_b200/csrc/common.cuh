@@ -192,6 +192,9 @@ struct GemmArgs {
   float* c_out; int64_t ldcout;     // EPI_LSTM: new cell state [M,H]
   float* C2; int64_t ldc2;          // optional second copy of the primary output (nullptr = none)
   const void* A_hi; const void* A_lo; int64_t ld_as;   // tensor-core path: A already split by its producer (row stride ld_as elements)
+  // EPI_LSTM: per-row additive term of the gate pre-activations, looked up by row: gates[m, :] += row_table[row_index[m], :]
+  // (the embedding part of the LSTM input folded into a [V, 4H] table: the GEMM's K loses the embedding columns)
+  const float* row_table; const int32_t* row_index; int64_t ld_table;
   SplitDst c_split;                 // store-family / EPI_LSTM epilogues: also write the output as the split operand of its consumer GEMM
   float* tk_part; int tk_k;         // EPI_TOPK: candidate records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
   float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(tk_vocab), 2]

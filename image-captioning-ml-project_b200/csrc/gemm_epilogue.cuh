@@ -49,6 +49,10 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
     split_store4(p.c_split, m, n, make_float4(v0, v1, v2, v3));
   } else if (EPI == EPI_LSTM) {
     // torch.nn.LSTMCell: c' = sigmoid(f)*c + sigmoid(i)*tanh(g);  h' = sigmoid(o)*tanh(c')
+    if (p.row_table) {
+      const float4 tb = *reinterpret_cast<const float4*>(p.row_table + (int64_t)p.row_index[m] * p.ld_table + n);
+      v0 += tb.x; v1 += tb.y; v2 += tb.z; v3 += tb.w;
+    }
     const int j = n >> 2;
     const float cp = p.c_in[(int64_t)m * p.ldcin + j];
     const float c2 = sig(v1) * cp + sig(v0) * th(v2);

@@ -463,6 +463,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             const float4 ci0 = *reinterpret_cast<const float4*>(p.c_in + (int64_t)m * p.ldcin + j0);
             const float4 ci1 = *reinterpret_cast<const float4*>(p.c_in + (int64_t)m * p.ldcin + j0 + 4);
             const float cp[8] = {ci0.x, ci0.y, ci0.z, ci0.w, ci1.x, ci1.y, ci1.z, ci1.w};
+            if (p.row_table) {   // embedding contribution of this row's token, pre-multiplied into gate space
+              const float4* tb = reinterpret_cast<const float4*>(p.row_table + (int64_t)p.row_index[m] * p.ld_table + n0);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float4 tv4 = __ldg(tb + u);
+                bia[u].x += tv4.x; bia[u].y += tv4.y; bia[u].z += tv4.z; bia[u].w += tv4.w;
+              }
+            }
             float hv[8], cv[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {

@@ -31,6 +31,9 @@ struct capdec_handle {
   // legacy, tensor-core beam/greedy path: [fc ; 0-pad to a 256 multiple ; dec_att ; f_beta] so that the vocabulary GEMM of
   // step t also emits [dec_att | sigmoid(f_beta)] of the new hidden state for step t+1 (same A operand)
   float* w_vocab_cat = nullptr; float* b_vocab_cat = nullptr; int vocab_cat_n = 0;
+  // legacy, tensor-core modes: emb_gates[v, n] = sum_e embedding[v, e] * W_ih[n, e] in the interleaved gate order (exact fp32):
+  // the embedding columns leave the gate GEMM's K, the LSTM epilogue adds the row of the step's token instead
+  float* emb_gates = nullptr;
   float* w_init = nullptr;  float* b_init = nullptr;   // legacy [2H,D]; lstm arch [2*H*layers, H] = [init_h ; init_c]
   // aoa: [info ; gate] rows interleaved n = 2*j + {info, gate}
   float* w_aoa = nullptr;   float* b_aoa = nullptr;
