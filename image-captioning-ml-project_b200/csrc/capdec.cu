@@ -127,6 +127,7 @@ struct Session {
   // legacy, bf16 mode: the region tiles the attention kernel streams every step are kept in bf16 (half the bytes):
   // feats_h [B,L,D] is also the att1 GEMM's operand, att1_h [B,L,A] comes straight out of that GEMM's epilogue
   void* feats_h = nullptr; void* att1_h = nullptr;
+  void* feats_l = nullptr;               // split modes: lo copy of the features (hi in feats_h); both feed the hoisted enc_att GEMM
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
@@ -242,6 +243,10 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
           additive_attention_stream_supports(A, D, L, k, true)) {
         S.feats_h = ar.take<char>((size_t)B * L * D * 2);
         S.att1_h = ar.take<char>((size_t)B * L * A * 2);
+      } else if (D % 8 == 0 && !getenv("CAPDEC_NO_MEAN_SPLIT")) {
+        // operand copies of the features for the hoisted enc_att GEMM, written by the same pass that takes the region mean
+        S.feats_h = ar.take<char>((size_t)B * L * D * es);
+        S.feats_l = lo ? ar.take<char>((size_t)B * L * D * es) : nullptr;
       }
     }
     if (!S.att1_h) S.att1 = ar.take<float>((size_t)B * L * A);
@@ -322,17 +327,23 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
   // att1 = enc_att(enc)  (models/decoder.py:152, hoisted)
-  if (S.att1_h) {
-    // bf16 mode: one conversion pass makes the bf16 feature tiles (GEMM operand AND what attention streams every step);
-    // the GEMM's epilogue emits att1 directly as bf16 tiles
-    CAPDEC_RETURN_IF(tc_split(c.precision, feats, D, S.B * S.L, D, S.feats_h, nullptr, s));
-    const SplitDst a_pre{S.feats_h, nullptr, D, KIND_BF16}, c_out{S.att1_h, nullptr, A, KIND_BF16};
-    CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", nullptr, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &a_pre, &c_out));
+  const int kind = tc_kind(c.precision);
+  if (S.feats_h) {
+    // one pass over the features: region mean (for h0 / c0, :137-139) + the hi/lo operand copies.  In the bf16 mode the
+    // hi copy is also what the attention kernel streams every step and the GEMM's epilogue emits att1 directly as bf16.
+    const SplitDst fsplit{S.feats_h, S.feats_l, D, kind};
+    CAPDEC_RETURN_IF(mean_regions_split(feats, S.B, S.L, D, S.meanb, fsplit, s));
+    if (S.att1_h) {
+      const SplitDst c_out{S.att1_h, nullptr, A, KIND_BF16};
+      CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", nullptr, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &fsplit, &c_out));
+    } else {
+      CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &fsplit));
+    }
   } else {
     CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s));
+    // h0, c0 = h_lin(mean), c_lin(mean)  (:137-139)
+    CAPDEC_RETURN_IF(mean_regions(feats, S.B, S.L, D, S.meanb, s));
   }
-  // h0, c0 = h_lin(mean), c_lin(mean)  (:137-139)
-  CAPDEC_RETURN_IF(mean_regions(feats, S.B, S.L, D, S.meanb, s));
   GemmArgs g{};
   g.A = S.meanb; g.lda = D; g.W = h->w_init; g.ldw = D; g.bias = h->b_init; g.C = S.init; g.ldc = 2 * H;
   g.M = S.B; g.N = 2 * H; g.K = D;

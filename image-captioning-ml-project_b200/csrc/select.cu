@@ -434,6 +434,32 @@ __global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restri
   reinterpret_cast<float4*>(out + (int64_t)b * D)[c] = make_float4(acc.x / fl, acc.y / fl, acc.z / fl, acc.w / fl);
 }
 
+// mean over regions fused with the operand split of the same tile: one pass over feats [B,L,D] produces the region mean
+// (h0 / c0 input, models/decoder.py:137) AND the hi/lo copies the hoisted enc_att GEMM (and, in the bf16 mode, the
+// attention kernel) read, instead of one pass for the mean and another for the split
+__global__ void __launch_bounds__(256) mean_split_kernel(const float* __restrict__ feats, int L, int D,
+                                                         float* __restrict__ out, const SplitDst split) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
+  if (c >= D / 4) return;
+  const float4* p = reinterpret_cast<const float4*>(feats + (int64_t)b * L * D) + c;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ldg_stream(p + (int64_t)min(l0 + u, L - 1) * (D / 4));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (l0 + u < L) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        split_store4(split, (int64_t)b * L + l0 + u, c * 4, v[u]);
+      }
+    }
+  }
+  const float fl = (float)L;
+  reinterpret_cast<float4*>(out + (int64_t)b * D)[c] = make_float4(acc.x / fl, acc.y / fl, acc.z / fl, acc.w / fl);
+}
+
 __global__ void __launch_bounds__(128) expand_rows_kernel(const float* __restrict__ src, int64_t ld_src,
                                                           float* __restrict__ dst, int64_t ld_dst, int k, int width) {
   const int r = blockIdx.x;
@@ -533,6 +559,15 @@ int mean_regions(const float* feats, int B, int L, int D, float* out, cudaStream
   if (B == 0) return CAPDEC_OK;
   dim3 grid(ceil_div(D / 4, 256), B);
   mean_regions_kernel<<<grid, 256, 0, s>>>(feats, L, D, out);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int mean_regions_split(const float* feats, int B, int L, int D, float* out, const SplitDst& split, cudaStream_t s) {
+  CAPDEC_REQUIRE(D % 8 == 0 && split.ld % 8 == 0, CAPDEC_ERR_UNSUPPORTED, "mean_regions_split: D must be a multiple of 8");
+  if (B == 0) return CAPDEC_OK;
+  dim3 grid(ceil_div(D / 4, 256), B);
+  mean_split_kernel<<<grid, 256, 0, s>>>(feats, L, D, out, split);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }

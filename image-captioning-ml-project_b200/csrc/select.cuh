@@ -54,6 +54,8 @@ int gather_rows(const GatherArgs& a, cudaStream_t s);
 
 // mean over regions: out[b,:] = mean_l feats[b,l,:]
 int mean_regions(const float* feats, int B, int L, int D, float* out, cudaStream_t s);
+// the same mean, fused with writing the hi/lo operand copies of feats ([B*L, D], row pitch split.ld) in one pass
+int mean_regions_split(const float* feats, int B, int L, int D, float* out, const SplitDst& split, cudaStream_t s);
 // dst[r, :] = src[r / k, :]  (expand per-image rows to per-beam rows), width % 4 == 0
 int expand_rows(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int k, int width, cudaStream_t s);
 int fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t s);
