@@ -703,10 +703,9 @@ int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8
   return step_lstm(h, S, feats, mask, alpha, ld_alpha, s);
 }
 
-// commit the step: reorder state by back-pointer, embed the chosen tokens, optionally record them
-int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
-           bool with_state, cudaStream_t s, int t_done = -1) {
-  if (is_tf_family(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
+// the step's commit as gather arguments: reorder state by back-pointer, embed the chosen tokens, optionally record them
+void build_gather(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
+                  bool with_state, GatherArgs* out) {
   S.row_src = src;
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim;
@@ -733,6 +732,14 @@ int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_
     for (int i = 0; i < 16; ++i) g.state_split_col[i] = -1;
     if (with_state) g.state_split_col[0] = E + D;   // state 0 = new h of the single legacy layer -> X[:, E+D:]
   }
+  *out = g;
+}
+
+int commit(const capdec_handle* h, Session& S, const int32_t* src, int32_t* tok_out, int64_t ld_tok, int pos,
+           bool with_state, cudaStream_t s, int t_done = -1) {
+  if (is_tf_family(h)) return commit_transformer(h, S, with_state ? src : nullptr, tok_out, ld_tok, pos, t_done, s);
+  GatherArgs g{};
+  build_gather(h, S, src, tok_out, ld_tok, pos, with_state, &g);
   StageScope sc(h, STAGE_GATHER, s);
   return gather_rows(g, s);
 }
@@ -1082,17 +1089,31 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
   const int k2 = 2 * k;
   for (int cur_len = 1; cur_len < T; ++cur_len) {
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, cur_len - 1, s));
-    { StageScope sc(h, STAGE_SELECT, s);
-      CAPDEC_RETURN_IF(select_topk(h, S, k2, S.cand_lp, S.cand_idx, s)); }
     // prompt length is 1 (BOS): finished score / (cur_len+1-1)^lp ; heuristic uses ((cur_len+1)-1)^lp
     const float div_fin = (float)pow((double)cur_len, (double)length_penalty);
     const float div_heur = div_fin;
     const size_t o = (size_t)(cur_len - 1) * B * k2;
+    const bool more = cur_len + 1 < T;
+    // Opt-in (CAPDEC_FUSED_SELECT=1): measured on B200 at 4096 images the single per-image kernel takes 3.8 ms per decode
+    // against 2.9 ms for the three specialised kernels (its phases serialise inside a CTA), so the default keeps them apart.
+    static const bool fused_select = getenv("CAPDEC_FUSED_SELECT") != nullptr;
+    if (S.fuse_k > 0 && !is_tf_family(h) && fused_select) {
+      // candidate merge + beam bookkeeping + state reorder / embedding gather of an image in one CTA
+      GatherArgs ga{};
+      if (more) build_gather(h, S, S.src_row, nullptr, 0, -1, true, &ga);
+      StageScope sc(h, STAGE_BEAM, s);
+      CAPDEC_RETURN_IF(select_fused(S.tk_part, S.tk_lse, c.vocab_size, S.tk_ntotal, S.fuse_k, S.beam, B, k, T, cur_len,
+                                    c.eos_token_id, div_fin, div_heur, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
+                                    dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, more ? &ga : nullptr, s));
+      continue;
+    }
+    { StageScope sc(h, STAGE_SELECT, s);
+      CAPDEC_RETURN_IF(select_topk(h, S, k2, S.cand_lp, S.cand_idx, s)); }
     { StageScope sc(h, STAGE_BEAM, s);
       CAPDEC_RETURN_IF(beam_step(S.beam, B, k, T, c.vocab_size, cur_len, c.eos_token_id, div_fin, div_heur, S.cand_lp,
                                  S.cand_idx, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
                                  dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, s)); }
-    if (cur_len + 1 < T) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s, cur_len - 1));
+    if (more) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s, cur_len - 1));
   }
   CAPDEC_RETURN_IF(beam_finalize(S.beam, (T - 1) & 1, B, k, T, out_tok, out_len, out_score, s));
   return CAPDEC_OK;

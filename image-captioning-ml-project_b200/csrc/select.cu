@@ -107,29 +107,29 @@ __global__ void __launch_bounds__(kThreads) lse_topk_kernel(const float* __restr
 // shared memory; each of the K rounds is a warp arg-max over the lanes' best list heads (ties -> lower vocabulary
 // index, as torch.topk / the unfused kernel).  Slots the GEMM did not write carry the 0xFF fill (index -1) and are skipped.
 constexpr int kMergeMaxRecords = 1024;
-__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ part, const float* __restrict__ lse_part,
-                                                         int n_lse, int vocab, int n_rec, int PS, int TKB,
-                                                         int rows, int K, float* __restrict__ out_lp,
-                                                         int32_t* __restrict__ out_idx, float* __restrict__ out_lse) {
-  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 4 + warp;
-  if (row >= rows) return;
-  const float* pr = part + (int64_t)row * n_rec * PS;
-  uint8_t* pos = s_pos[warp];
+struct MergeArgs {
+  const float* part; const float* lse_part;
+  int n_lse, vocab, n_rec, PS, TKB, rows, K;
+};
+// one warp: merge the records of `row`; writes K sorted (log-prob, index) pairs through out_lp / out_idx (any address space)
+__device__ __forceinline__ void merge_row(const MergeArgs& a, int row, int lane, uint8_t* pos, float* out_lp, int32_t* out_idx,
+                                          float* out_lse) {
+  const int n_rec = a.n_rec, PS = a.PS, TKB = a.TKB;
+  const float* pr = a.part + (int64_t)row * n_rec * PS;
   // log-sum-exp from the per-(tile half) partials, in a fixed order: lane-strided sequential sums, then the shuffle tree
-  const float2* lp2 = reinterpret_cast<const float2*>(lse_part) + (int64_t)row * n_lse;
+  const float2* lp2 = reinterpret_cast<const float2*>(a.lse_part) + (int64_t)row * a.n_lse;
   float M = -INFINITY;
-  for (int t = lane; t < n_lse; t += 32)
-    if (t * 128 < vocab) M = fmaxf(M, lp2[t].x);
+  for (int t = lane; t < a.n_lse; t += 32)
+    if (t * 128 < a.vocab) M = fmaxf(M, lp2[t].x);
   M = warp_max(M);
   float S = 0.f;
-  for (int t = lane; t < n_lse; t += 32)
-    if (t * 128 < vocab) { const float2 v = lp2[t]; S += v.y * expf(v.x - M); }
+  for (int t = lane; t < a.n_lse; t += 32)
+    if (t * 128 < a.vocab) { const float2 v = lp2[t]; S += v.y * expf(v.x - M); }
   S = warp_sum(S);
   for (int t = lane; t < n_rec; t += 32) pos[t] = 0;
+  __syncwarp();
   const float logS = logf(S);
-  if (lane == 0 && out_lse) out_lse[row] = M + logS;
+  if (lane == 0 && out_lse) *out_lse = M + logS;
 
   // lane-local best head, recomputed only by the lane whose head was taken
   auto scan = [&](float& bv, int& bi, int& bt) {
@@ -144,20 +144,29 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
   };
   float bv; int bi, bt;
   scan(bv, bi, bt);
-  for (int r = 0; r < K; ++r) {
+  for (int r = 0; r < a.K; ++r) {
     float wv = bv;
     int wi = bi;
     warp_argmax(wv, wi);
     const bool valid = wi != INT_MAX;
     if (lane == 0) {
-      out_lp[(int64_t)row * K + r] = valid ? (wv - M) - logS : -INFINITY;
-      out_idx[(int64_t)row * K + r] = valid ? wi : -1;
+      out_lp[r] = valid ? (wv - M) - logS : -INFINITY;
+      out_idx[r] = valid ? wi : -1;
     }
     if (valid && bi == wi) {   // vocabulary indices are unique, so exactly one lane advances
       pos[bt] += 1;
       scan(bv, bi, bt);
     }
   }
+}
+
+__global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a, float* __restrict__ out_lp,
+                                                         int32_t* __restrict__ out_idx, float* __restrict__ out_lse) {
+  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= a.rows) return;
+  merge_row(a, row, lane, s_pos[warp], out_lp + (int64_t)row * a.K, out_idx + (int64_t)row * a.K, out_lse ? out_lse + row : nullptr);
 }
 
 // One CTA per row: inverse-CDF draw in vocabulary index order (double prefix sums), or argmax for the greedy slot.
@@ -252,15 +261,13 @@ __global__ void beam_init_kernel(BeamState st, int B, int k, int T, int bos, int
   st.unsatisfied[img] = 1;
 }
 
-__global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int cur_len, int eos, float div_fin,
-                                 float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
-                                 int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
-                                 int32_t* dbg_tok, int32_t* dbg_beam) {
-  // one WARP per image: every lane evaluates the (tiny) selection logic redundantly on the same inputs, the token
-  // sequences are copied lane-parallel, lane 0 writes the scalars
-  const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (img >= B) return;
+// one WARP per image: every lane evaluates the (tiny) selection logic redundantly on the same inputs, the token
+// sequences are copied lane-parallel, lane 0 writes the scalars.  cand_lp / cand_idx: the image's k sorted lists of 2k
+// candidates, cand[(b * 2k) + j] (global or shared memory).
+__device__ __forceinline__ void beam_step_image(const BeamState& st, int img, int lane, int k, int T, int cur_len, int eos,
+                                                float div_fin, float div_heur, const float* cand_lp, const int32_t* cand_idx,
+                                                int32_t* next_tok, int32_t* src_row, float* dbg_lp, int32_t* dbg_tok,
+                                                int32_t* dbg_beam) {
   constexpr int KM = kMaxRowsPerImage, K2 = kMaxTopK;
   const int k2 = 2 * k;
   const int par = (cur_len - 1) & 1;  // read buffers [par], write [par ^ 1]
@@ -280,7 +287,7 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
     int bb = -1, bt = 0;
     for (int b = 0; b < k; ++b) {
       if (ptr[b] >= k2) continue;
-      const int64_t o = ((int64_t)img * k + b) * k2 + ptr[b];
+      const int o = b * k2 + ptr[b];
       const int tok = cand_idx[o];
       if (tok < 0) continue;
       const float v = cand_lp[o] + score[b];
@@ -377,6 +384,17 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
   if (lane == 0) st.unsatisfied[img] = (unsat && any) ? 1 : 0;
 }
 
+__global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int cur_len, int eos, float div_fin,
+                                 float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
+                                 int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
+                                 int32_t* dbg_tok, int32_t* dbg_beam) {
+  const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (img >= B) return;
+  beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, cand_lp + (int64_t)img * k * 2 * k,
+                  cand_idx + (int64_t)img * k * 2 * k, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+}
+
 __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
                                      float* out_score) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,9 +408,7 @@ __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int
 }
 
 // ---- gathers ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
-  const int r = blockIdx.x;
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void gather_row(const GatherArgs& a, int r, int tid, int nthreads) {
   const int src = a.src ? a.src[r] : r;
   if (a.tok) {
     const int tok = a.tok[r];
@@ -400,7 +416,7 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
     if (a.embedding) {
       const float4* e = reinterpret_cast<const float4*>(a.embedding + (int64_t)tok * a.E);
       float4* d = reinterpret_cast<float4*>(a.x_emb + (int64_t)r * a.ld_x);
-      for (int i = tid; i < a.E / 4; i += blockDim.x) {
+      for (int i = tid; i < a.E / 4; i += nthreads) {
         const float4 v = e[i];
         d[i] = v;
         split_store4(a.x_split, r, i * 4, v);
@@ -411,12 +427,37 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
     const float4* sp = reinterpret_cast<const float4*>(a.state_src[sidx] + (int64_t)src * a.ld_src[sidx]);
     float4* dp = reinterpret_cast<float4*>(a.state_dst[sidx] + (int64_t)r * a.ld_dst[sidx]);
     const int scol = a.x_split.hi ? a.state_split_col[sidx] : -1;
-    for (int i = tid; i < a.width[sidx] / 4; i += blockDim.x) {
+    for (int i = tid; i < a.width[sidx] / 4; i += nthreads) {
       const float4 v = sp[i];
       dp[i] = v;
       if (scol >= 0) split_store4(a.x_split, r, scol + i * 4, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) { gather_row(a, blockIdx.x, threadIdx.x, blockDim.x); }
+
+// Per-image fusion of the three bookkeeping kernels of a beam step (fused top-k path): the image's k rows are merged
+// from the vocabulary GEMM's records into k sorted candidate lists in shared memory (one warp per row), warp 0 runs
+// the HF beam step on them, then the whole CTA gathers the image's new rows (state reorder by back-pointer + embedding).
+// Beams reorder only inside an image, so no other CTA's results are needed.
+__global__ void __launch_bounds__(128) select_fused_kernel(const MergeArgs ma, const BeamState st, int k, int T, int cur_len,
+                                                           int eos, float div_fin, float div_heur, int32_t* next_tok,
+                                                           int32_t* src_row, float* dbg_lp, int32_t* dbg_tok,
+                                                           int32_t* dbg_beam, const GatherArgs ga, int do_gather) {
+  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
+  __shared__ float s_lp[kMaxRowsPerImage * kMaxTopK];
+  __shared__ int32_t s_idx[kMaxRowsPerImage * kMaxTopK];
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k2 = 2 * k;
+  for (int b = warp; b < k; b += 4) merge_row(ma, img * k + b, lane, s_pos[warp], s_lp + b * k2, s_idx + b * k2, nullptr);
+  __syncthreads();
+  if (warp == 0)
+    beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, s_lp, s_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+  if (!do_gather) return;
+  __threadfence_block();
+  __syncthreads();   // next_tok / src_row of this image's rows are visible to the whole CTA
+  for (int b = 0; b < k; ++b) gather_row(ga, img * k + b, threadIdx.x, blockDim.x);
 }
 
 __global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restrict__ feats, int L, int D,
@@ -499,8 +540,8 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
   CAPDEC_REQUIRE(tk_supported(vocab, part_k) && n_rec <= kMergeMaxRecords && topk >= 1 && topk <= tk_bucket(part_k), CAPDEC_ERR_INVALID,
                  "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
   if (rows == 0) return CAPDEC_OK;
-  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows,
-                                                       topk, out_lp, out_idx, out_lse);
+  const MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, topk};
+  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(ma, out_lp, out_idx, out_lse);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -542,6 +583,22 @@ int beam_finalize(const BeamState& st, int parity, int B, int k, int T, int32_t*
                   float* out_score, cudaStream_t s) {
   if (B == 0) return CAPDEC_OK;
   beam_finalize_kernel<<<ceil_div(B * T, 256), 256, 0, s>>>(st, parity, B, k, T, out_tok, out_len, out_score);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int select_fused(const float* part, const float* lse_part, int vocab, int n_total, int part_k, const BeamState& st, int B, int k,
+                 int T, int cur_len, int eos, float div_fin, float div_heur, int32_t* next_tok, int32_t* src_row,
+                 float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, const GatherArgs* ga, cudaStream_t s) {
+  const int rows = B * k, n_rec = tk_records(rows, n_total);
+  CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage && 2 * k <= tk_bucket(part_k) && n_rec <= kMergeMaxRecords, CAPDEC_ERR_INVALID,
+                 "select_fused: num_beams %d / record layout unsupported", k);
+  if (B == 0) return CAPDEC_OK;
+  const MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, 2 * k};
+  GatherArgs g{};
+  if (ga) g = *ga;
+  select_fused_kernel<<<B, 128, 0, s>>>(ma, st, k, T, cur_len, eos, div_fin, div_heur, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam,
+                                        g, ga ? 1 : 0);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
