@@ -291,6 +291,22 @@ def test_legacy_beam_with_eos_finishing(cuda):
         assert (fill == 2).all()        # HF fills with eos when pad_token_id == 0 (generation/utils.py:3187)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("B,k,T,V", [(1, 1, 2, 40), (3, 8, 6, 500), (2, 5, 5, 8), (5, 2, 3, 4), (148 * 2 + 1, 3, 4, 300)])
+def test_legacy_beam_edge_shapes(cuda, precision, B, k, T, V):
+    """Edge shapes of the beam path against the oracle: a single image / single beam / shortest max_length, the
+    maximum beam width (8 rows per image), vocabularies SMALLER than the 2k candidates a step asks for (the candidate
+    lists are padded with -inf / -1 exactly like the unfused kernel), and a batch that is not a multiple of anything
+    (one more image than two rounds of the persistent attention grid)."""
+    m, sd = legacy_weights(V, 3)
+    m.precision = precision
+    enc = legacy_features(B, seed=17)
+    ref = obeam.beam_search(olegacy.LegacyStepper(sd, enc, k), B, k, T, record_steps=True)
+    out = m.to(cuda).beam_search(enc.to(cuda), beam_size=k, max_length=T, trace=True)
+    _compare_beam(out, ref, B, k, f"legacy edge B={B} k={k} T={T} V={V} {precision}", min_identical=0.97)
+    assert torch.equal(out["lengths"].cpu().long(), ref["lengths"]) or precision != "fp32"
+
+
 def test_legacy_greedy_and_sample_vs_oracle(cuda):
     B, T, V = 10, 12, 3000
     m, sd = legacy_weights(V, 2)
