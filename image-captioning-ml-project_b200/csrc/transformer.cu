@@ -147,60 +147,81 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 // Pass 2: lane = output element -- key p's value pointer and weight come from lane p by shuffle, the loads are coalesced.
 template <int NK, int D4T>   // keys per lane (n_keys <= 32 * NK); head_dim / 4 when known at compile time (0 = runtime)
 __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
-  extern __shared__ __align__(16) float s_q[];   // [H] query of this row
+  extern __shared__ __align__(16) float s_q[];   // [H] query of this row, then [heads][128] scores
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = a.H, d = H / a.heads, d4 = D4T > 0 ? D4T : (d >> 2), T = a.T, t = a.t;
+  float* s_sc = s_q + H;
   const float* qkv = a.qkv + (int64_t)r * a.ld_qkv;
   float* kc = a.cache_k + ((int64_t)r * T + t) * H;
   float* vc = a.cache_v + ((int64_t)r * T + t) * H;
+  // every lane resolves the address of its key(s) first: the ancestor-table lookup does not depend on this step's q/k/v,
+  // so its latency overlaps the q/k/v staging below
+  const int hd = warp;
+  const int img = r / a.rows_per_image;
+  const int n_keys = a.n_prefix + t + 1;
+  const float* kptr[NK];
+  const float* vptr[NK];
+#pragma unroll
+  for (int i = 0; i < NK; ++i) {
+    const int p = lane + 32 * i;
+    kptr[i] = a.cache_k; vptr[i] = a.cache_v;
+    if (p < n_keys && hd < a.heads) {
+      if (p < a.n_prefix) {
+        const int64_t off = ((int64_t)img * a.n_prefix + p) * H + hd * d;
+        kptr[i] = a.prefix_k + off; vptr[i] = a.prefix_v + off;
+      } else {
+        const int pos = p - a.n_prefix;
+        const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
+        const int64_t off = ((int64_t)prow * T + pos) * H + hd * d;
+        kptr[i] = a.cache_k + off; vptr[i] = a.cache_v + off;
+      }
+    }
+  }
   for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
     reinterpret_cast<float4*>(s_q)[i] = reinterpret_cast<const float4*>(qkv)[i];
     reinterpret_cast<float4*>(kc)[i] = reinterpret_cast<const float4*>(qkv + H)[i];
     reinterpret_cast<float4*>(vc)[i] = reinterpret_cast<const float4*>(qkv + 2 * H)[i];
   }
   __syncthreads();
-  const int hd = warp;
   if (hd >= a.heads) return;
-  const int img = r / a.rows_per_image;
-  const int n_keys = a.n_prefix + t + 1;
-  // ---- pass 1: scores, lane = key
+  // ---- pass 1: scores.  A group of GL lanes (8 / 16 / 32 >= head_dim / 4) reads one key's head slice with one coalesced
+  // 128-bit load per lane, so a warp handles 32 / GL keys per round and the dot needs log2(GL) shuffle steps; the
+  // key's address comes from the lane that resolved it.  Scores pass through shared memory to land in lane = key.
   const float4* q4 = reinterpret_cast<const float4*>(s_q + hd * d);
+  float* my_sc = s_sc + warp * 128;
+  const int GL = d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
+  const int kpr = 32 / GL, sub = lane % GL, grp = lane / GL;
+  const float4 qv = sub < d4 ? q4[sub] : make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int UR = 8;
+  for (int p0 = 0; p0 < n_keys; p0 += UR * kpr) {   // UR rounds at a time: their key loads are all in flight together
+    int pk[UR];
+    float4 kv[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      pk[u] = p0 + u * kpr + grp;
+      const int p = min(pk[u], n_keys - 1);
+      const float* kp = nullptr;
+#pragma unroll
+      for (int i = 0; i < NK; ++i) {
+        const float* cand = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)kptr[i], p & 31));
+        if (i == (p >> 5)) kp = cand;
+      }
+      kv[u] = sub < d4 ? reinterpret_cast<const float4*>(kp)[sub] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      float part = fmaf(qv.x, kv[u].x, fmaf(qv.y, kv[u].y, fmaf(qv.z, kv[u].z, qv.w * kv[u].w)));
+      for (int o = GL >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (sub == 0 && pk[u] < n_keys) my_sc[pk[u]] = part * a.scale;
+    }
+  }
+  __syncwarp();
   float sc[NK];
-  const float* vptr[NK];
 #pragma unroll
   for (int i = 0; i < NK; ++i) {
     const int p = lane + 32 * i;
-    sc[i] = -INFINITY;
-    vptr[i] = a.cache_v;
-    if (p < n_keys) {
-      const float* kptr;
-      if (p < a.n_prefix) {
-        const int64_t off = ((int64_t)img * a.n_prefix + p) * H + hd * d;
-        kptr = a.prefix_k + off; vptr[i] = a.prefix_v + off;
-      } else {
-        const int pos = p - a.n_prefix;
-        const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
-        const int64_t off = ((int64_t)prow * T + pos) * H + hd * d;
-        kptr = a.cache_k + off; vptr[i] = a.cache_v + off;
-      }
-      const float4* k4 = reinterpret_cast<const float4*>(kptr);
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-      for (int e = 0; e < (D4T > 0 ? D4T : 1); ++e) {
-        if (D4T > 0) {
-          const float4 kv = k4[e], qv = q4[e];
-          d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
-        }
-      }
-      if (D4T == 0) {
-        for (int e = 0; e < d4; ++e) {
-          const float4 kv = k4[e], qv = q4[e];
-          d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
-        }
-      }
-      sc[i] = ((d0 + d1) + (d2 + d3)) * a.scale;
-    }
+    sc[i] = p < n_keys ? my_sc[p] : -INFINITY;
   }
   // ---- softmax across the lanes
   float m = sc[0];
@@ -217,23 +238,23 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
 #pragma unroll
   for (int i = 0; i < NK; ++i) {
     const int n_here = min(32, n_keys - 32 * i);
-    for (int p0 = 0; p0 < n_here; p0 += 4) {   // 4 keys per round: 8 independent loads in flight per lane
-      float w[4];
-      const float* vp[4];
+    for (int p0 = 0; p0 < n_here; p0 += 8) {   // 8 keys per round: up to 16-32 independent loads in flight per lane
+      float w[8];
+      const float* vp[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int pl = min(p0 + u, n_here - 1);
         const float wv = __shfl_sync(0xffffffffu, sc[i], pl);
         vp[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)vptr[i], pl));
         w[u] = p0 + u < n_here ? wv : 0.f;
       }
-      float x[4][4];
+      float x[8][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int e = lane + 32 * j; x[u][j] = e < d ? vp[u][e] : 0.f; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[u], x[u][j], acc[j]);
     }
@@ -286,8 +307,8 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
   if (a.rows == 0) return CAPDEC_OK;
   const int n_keys = a.n_prefix + a.t + 1;
   static const bool old_form = getenv("CAPDEC_SELFATTN_ONLINE") != nullptr;
-  if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && a.H * sizeof(float) <= 48 * 1024) {
-    const size_t smem = (size_t)a.H * sizeof(float);
+  if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
+    const size_t smem = ((size_t)a.H + (size_t)a.heads * 128) * sizeof(float);
     const int d4 = a.H / a.heads / 4;
 #define CAPDEC_SA_LAUNCH(NKV)                                                                               \
     if (d4 == 16)      self_attn_decode2_kernel<NKV, 16><<<a.rows, 32 * a.heads, smem, s>>>(a);            \
