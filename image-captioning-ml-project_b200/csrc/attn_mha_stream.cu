@@ -69,6 +69,7 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 
 template <int KB, int NC>
 __global__ void __launch_bounds__(kThreads, 1) mha_attention_stream_kernel(const MhaArgs p, const MhaLayout y) {
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ringK = smem + y.off_ringK;
   uint8_t* ringV = smem + y.off_ringV;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) mha_attention_stream_kernel(const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ V producer ================================
@@ -349,11 +351,11 @@ int launch_stream(const MhaArgs& a, const MhaLayout& y, cudaStream_t s) {
   if (nc == 1) {
     auto kern = mha_attention_stream_kernel<KB, 1>;
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));
-    kern<<<grid, kThreads, y.total, s>>>(a, y);
+    CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));
   } else {
     auto kern = mha_attention_stream_kernel<KB, 2>;
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));
-    kern<<<grid, kThreads, y.total, s>>>(a, y);
+    CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));
   }
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;

@@ -85,6 +85,7 @@ __device__ __forceinline__ float4 tile_ld4(const void* row, int i4) {
 template <int KB, int ACT, int NC, int BF>
 __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(const AddAttnArgs p, const StreamLayout y) {
   constexpr size_t ES = BF ? 2 : 4;   // bytes per tile element
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ringA = smem + y.off_ringA;
   uint8_t* ringF = smem + y.off_ringF;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ feats producer ================================
@@ -391,7 +393,7 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
   {                                                                                                                       \
     auto kern = additive_attention_stream_kernel<KB, ACTV, NCV, BFV>;                                                     \
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));             \
-    kern<<<grid, kThreads, y.total, s>>>(a, y);                                                                           \
+    CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));                                                                           \
   }
   if (a.tile_bf16) {
     if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }

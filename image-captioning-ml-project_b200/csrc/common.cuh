@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/capdec.h"
@@ -51,6 +52,33 @@ extern int64_t g_launch_count;
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------
+// The decode loop is a chain of dependent kernels on one stream.  Kernels launched through launch_k(..., pdl = true)
+// may become resident while their predecessor is still draining (every kernel calls pdl_trigger() first thing) and do
+// their own set-up (barrier init, TMEM allocation, descriptor prefetch); pdl_wait() then blocks until the predecessor
+// has completed and its writes are visible.  No global memory is touched before pdl_wait().  CAPDEC_NO_PDL=1 turns the
+// launch attribute off (the device-side calls are then no-ops).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = getenv("CAPDEC_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  int n = 0;
+  if (pdl && pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

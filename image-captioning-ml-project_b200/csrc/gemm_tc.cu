@@ -163,6 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; rank 0 issues the MMAs
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
@@ -208,6 +209,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers initialised + TMEM allocated in BOTH CTAs of the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up above overlapped the predecessor's tail; its outputs (our operands) are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair: own 128 rows of A, own BN/CG rows of W) =====
@@ -550,6 +552,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 template <int KIND>
 __global__ void split_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, int Kp, void* __restrict__ hi,
                              void* __restrict__ lo) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 columns
   const int c4 = Kp >> 2;
   if (i >= (int64_t)rows * c4) return;
@@ -586,8 +590,9 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t ld, int rows, 
 int split_operand(int kind, const float* x, int64_t ld, int rows, int cols, int Kp, void* hi, void* lo, cudaStream_t s) {
   const int64_t n = (int64_t)rows * (Kp / 4);
   if (n == 0) return CAPDEC_OK;
-  if (kind == KIND_BF16) split_kernel<KIND_BF16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, Kp, hi, lo);
-  else                   split_kernel<KIND_TF32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ld, rows, cols, Kp, hi, lo);
+  const dim3 grid((unsigned)((n + 255) / 256));
+  if (kind == KIND_BF16) CAPDEC_CHECK_CUDA(launch_k(split_kernel<KIND_BF16>, grid, dim3(256), 0, s, true, x, ld, rows, cols, Kp, hi, lo));
+  else                   CAPDEC_CHECK_CUDA(launch_k(split_kernel<KIND_TF32>, grid, dim3(256), 0, s, true, x, ld, rows, cols, Kp, hi, lo));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -686,10 +691,12 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const int groups = num_tiles < max_groups ? num_tiles : max_groups;                                           \
     cudaLaunchConfig_t cfg = {};                                                                                  \
     cfg.gridDim = dim3(groups * CG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
-    cudaLaunchAttribute at[1];                                                                                    \
+    cudaLaunchAttribute at[2];                                                                                    \
     at[0].id = cudaLaunchAttributeClusterDimension;                                                               \
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
-    cfg.attrs = at; cfg.numAttrs = 1;                                                                             \
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                \
+    at[1].val.programmaticStreamSerializationAllowed = 1;                                                         \
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;                                                         \
     CAPDEC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, g));                                 \
   }
 #define CAPDEC_TC_CASE(E) case E: CAPDEC_TC_LAUNCH(E, 0) break;

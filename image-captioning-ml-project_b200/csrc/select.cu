@@ -162,6 +162,8 @@ __device__ __forceinline__ void merge_row(const MergeArgs& a, int row, int lane,
 
 __global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a, float* __restrict__ out_lp,
                                                          int32_t* __restrict__ out_idx, float* __restrict__ out_lse) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ uint8_t s_pos[4][kMergeMaxRecords];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 4 + warp;
@@ -388,6 +390,8 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
                                  float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
                                  int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
                                  int32_t* dbg_tok, int32_t* dbg_beam) {
+  pdl_trigger();
+  pdl_wait();
   const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (img >= B) return;
@@ -435,7 +439,11 @@ __device__ __forceinline__ void gather_row(const GatherArgs& a, int r, int tid, 
   }
 }
 
-__global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) { gather_row(a, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  gather_row(a, blockIdx.x, threadIdx.x, blockDim.x);
+}
 
 // Per-image fusion of the three bookkeeping kernels of a beam step (fused top-k path): the image's k rows are merged
 // from the vocabulary GEMM's records into k sorted candidate lists in shared memory (one warp per row), warp 0 runs
@@ -541,7 +549,7 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
                  "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
   if (rows == 0) return CAPDEC_OK;
   const MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, topk};
-  topk_merge_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(ma, out_lp, out_idx, out_lse);
+  CAPDEC_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(ceil_div(rows, 4)), dim3(128), 0, s, true, ma, out_lp, out_idx, out_lse));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -573,8 +581,8 @@ int beam_step(const BeamState& st, int B, int k, int T, int V, int cur_len, int 
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "beam_step: num_beams %d not in [1,%d]", k,
                  kMaxRowsPerImage);
   if (B == 0) return CAPDEC_OK;
-  beam_step_kernel<<<ceil_div(B, 4), 128, 0, s>>>(st, B, k, T, V, cur_len, eos, len_div_finished, len_div_heuristic,
-                                                  cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+  CAPDEC_CHECK_CUDA(launch_k(beam_step_kernel, dim3(ceil_div(B, 4)), dim3(128), 0, s, true, st, B, k, T, V, cur_len, eos,
+                             len_div_finished, len_div_heuristic, cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -606,7 +614,7 @@ int select_fused(const float* part, const float* lse_part, int vocab, int n_tota
 int gather_rows(const GatherArgs& a, cudaStream_t s) {
   CAPDEC_REQUIRE(a.n_state <= 16, CAPDEC_ERR_INVALID, "gather_rows: too many state tensors");
   if (a.rows == 0) return CAPDEC_OK;
-  gather_rows_kernel<<<a.rows, 128, 0, s>>>(a);
+  CAPDEC_CHECK_CUDA(launch_k(gather_rows_kernel, dim3(a.rows), dim3(128), 0, s, true, a));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }

@@ -14,6 +14,8 @@ namespace {
 __global__ void __launch_bounds__(128) embed_pos_kernel(const int32_t* __restrict__ tok, const float* __restrict__ emb,
                                                         const float* __restrict__ pos, float* __restrict__ x, int H,
                                                         const SplitDst split) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const float4* e = reinterpret_cast<const float4*>(emb + (int64_t)tok[r] * H);
   const float4* p = reinterpret_cast<const float4*>(pos);
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ sum_out, float* __restrict__ out, int H,
                                                             float eps, const SplitDst split) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float srow[];
   __shared__ float s_red[8];
   const int r = blockIdx.x, tid = threadIdx.x, H4 = H >> 2;
@@ -147,6 +151,8 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 // Pass 2: lane = output element -- key p's value pointer and weight come from lane p by shuffle, the loads are coalesced.
 template <int NK, int D4T>   // keys per lane (n_keys <= 32 * NK); head_dim / 4 when known at compile time (0 = runtime)
 __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float s_q[];   // [H] query of this row, then [heads][128] scores
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -285,7 +291,7 @@ __global__ void reorder_ancestors_kernel(const int32_t* __restrict__ src, const 
 int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s,
               const SplitDst* split) {
   if (rows == 0) return CAPDEC_OK;
-  embed_pos_kernel<<<rows, 128, 0, s>>>(tok, emb, pos_row, x, H, split ? *split : SplitDst{});
+  CAPDEC_CHECK_CUDA(launch_k(embed_pos_kernel, dim3(rows), dim3(128), 0, s, true, tok, emb, pos_row, x, H, split ? *split : SplitDst{}));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -294,8 +300,8 @@ int add_layernorm(const float* x, const float* y, const float* gamma, const floa
                   int rows, int H, float eps, cudaStream_t s, const SplitDst* split) {
   if (rows == 0) return CAPDEC_OK;
   CAPDEC_REQUIRE(H % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "add_layernorm: H must be a multiple of 4");
-  add_layernorm_kernel<<<rows, 256, (size_t)H * sizeof(float), s>>>(x, y, gamma, beta, sum_out, out, H, eps,
-                                                                    split ? *split : SplitDst{});
+  CAPDEC_CHECK_CUDA(launch_k(add_layernorm_kernel, dim3(rows), dim3(256), (size_t)H * sizeof(float), s, true, x, y, gamma, beta,
+                             sum_out, out, H, eps, split ? *split : SplitDst{}));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -311,9 +317,9 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
     const size_t smem = ((size_t)a.H + (size_t)a.heads * 128) * sizeof(float);
     const int d4 = a.H / a.heads / 4;
 #define CAPDEC_SA_LAUNCH(NKV)                                                                               \
-    if (d4 == 16)      self_attn_decode2_kernel<NKV, 16><<<a.rows, 32 * a.heads, smem, s>>>(a);            \
-    else if (d4 == 24) self_attn_decode2_kernel<NKV, 24><<<a.rows, 32 * a.heads, smem, s>>>(a);            \
-    else               self_attn_decode2_kernel<NKV, 0><<<a.rows, 32 * a.heads, smem, s>>>(a);
+    if (d4 == 16)      CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 16>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));  \
+    else if (d4 == 24) CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 24>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));  \
+    else               CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 0>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));
     if (n_keys <= 32)      { CAPDEC_SA_LAUNCH(1) }
     else if (n_keys <= 64) { CAPDEC_SA_LAUNCH(2) }
     else                   { CAPDEC_SA_LAUNCH(4) }
