@@ -206,6 +206,7 @@ enum Epilogue : int {
 static inline int tk_bucket(int k) { return k <= 1 ? 1 : k <= 6 ? 6 : k <= 10 ? 10 : 16; }   // compiled list lengths
 static inline int tk_stride(int k) { return (2 + 2 * tk_bucket(k) + 3) & ~3; }              // floats per record
 int tk_records(int M, int N);                                                              // records per row (gemm_tc.cu)
+void tk_schedule(int M, int N, int* n_tiles, int* quota, int* block_rows);                 // the launch's tile schedule
 static inline int tk_lse_pairs(int vocab) { return 2 * ((vocab + 255) / 256); }                // 128-column halves of 256-column tiles
 static inline bool tk_supported(int vocab, int k) { return k >= 1 && k <= 16 && vocab >= 1; }
 

@@ -752,14 +752,19 @@ int tc_split(int precision, const float* x, int64_t ld, int rows, int cols, void
   return split_operand(tc_kind(precision), x, ld, rows, cols, cols, hi, tc_terms(precision) == 3 ? lo : nullptr, s);
 }
 
-// records per row the EPI_TOPK epilogue writes for an [M,N] problem: 2 column halves x (runs a row block can span)
-int tk_records(int M, int N) {
-  if (M <= 0) return 2;
-  const int cg = tc_cta_group(M);
-  const int n_tiles = ceil_div(N, 256), num_tiles = n_tiles * ceil_div(M, BM * cg);
+// The EPI_TOPK launch's tile schedule for an [M,N] problem (the merge kernel derives from it which record slots of a row
+// block were written): n tiles per row block, tiles per CTA group (contiguous runs), rows per block.
+void tk_schedule(int M, int N, int* n_tiles_out, int* quota_out, int* block_rows_out) {
+  const int cg = tc_cta_group(M > 0 ? M : 1);
+  const int n_tiles = ceil_div(N, 256), num_tiles = n_tiles * ceil_div(M > 0 ? M : 1, BM * cg);
   const int max_groups = tc_max_groups(cg);
   const int groups = num_tiles < max_groups ? num_tiles : max_groups;
-  const int quota = ceil_div(num_tiles, groups);
+  *n_tiles_out = n_tiles; *quota_out = ceil_div(num_tiles, groups); *block_rows_out = BM * cg;
+}
+// records per row the EPI_TOPK epilogue may write: 2 column halves x (runs a row block can span)
+int tk_records(int M, int N) {
+  int n_tiles, quota, br;
+  tk_schedule(M, N, &n_tiles, &quota, &br);
   return 2 * (ceil_div(n_tiles, quota) + 1);
 }
 
@@ -824,8 +829,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     CAPDEC_REQUIRE(a.tk_vocab >= 1 && a.tk_vocab <= a.N && (tail <= 0 || (tail % 4 == 0 && a.C && a.ldc % 4 == 0)), CAPDEC_ERR_INVALID,
                    "gemm: EPI_TOPK tail block must start at a 256-column boundary behind the vocabulary and be a multiple of 4 wide");
     CAPDEC_REQUIRE(a.M <= m_chunk, CAPDEC_ERR_UNSUPPORTED, "gemm: EPI_TOPK with %d rows exceeds the single-launch limit %d", a.M, m_chunk);
-    // slots a launch does not write (row blocks that fall into a single run) must read as empty: index -1
-    CAPDEC_CHECK_CUDA(cudaMemsetAsync(a.tk_part, 0xFF, (size_t)a.M * tk_records(a.M, a.N) * tk_stride(a.tk_k) * sizeof(float), s));
+    // (record slots a row block does not use stay unwritten; topk_merge derives the used slots from tk_schedule)
   }
   CUtensorMap map_w_hi, map_w_lo;
   CAPDEC_RETURN_IF(make_map(&map_w_hi, kind, w_hi, a.N, Kp, Kp, bn / cg));

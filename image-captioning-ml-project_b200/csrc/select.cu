@@ -105,17 +105,21 @@ __global__ void __launch_bounds__(kThreads) lse_topk_kernel(const float* __restr
 // Combine the partial records of the fused vocabulary GEMM (EPI_TOPK, gemm_tc.cu) into the row's log-sum-exp and
 // sorted top-K:  one warp per row; lane l owns records l, l+32, ... and keeps a read position per owned record in
 // shared memory; each of the K rounds is a warp arg-max over the lanes' best list heads (ties -> lower vocabulary
-// index, as torch.topk / the unfused kernel).  Slots the GEMM did not write carry the 0xFF fill (index -1) and are skipped.
+// index, as torch.topk / the unfused kernel).  Which slots the GEMM wrote follows from its tile schedule (MergeArgs).
 constexpr int kMergeMaxRecords = 1024;
 struct MergeArgs {
   const float* part; const float* lse_part;
   int n_lse, vocab, n_rec, PS, TKB, rows, K;
+  int n_tiles, quota, block_rows;   // the producing GEMM's schedule: tiles per row block, tiles per CTA-group run, rows per block
 };
 // one warp: merge the records of `row`; writes K sorted (log-prob, index) pairs through out_lp / out_idx (any address space)
 __device__ __forceinline__ void merge_row(const MergeArgs& a, int row, int lane, uint8_t* pos, float* out_lp, int32_t* out_idx,
                                           float* out_lse) {
-  const int n_rec = a.n_rec, PS = a.PS, TKB = a.TKB;
-  const float* pr = a.part + (int64_t)row * n_rec * PS;
+  const int PS = a.PS, TKB = a.TKB;
+  const float* pr = a.part + (int64_t)row * a.n_rec * PS;
+  // slots this row's block actually wrote: one per CTA-group run that intersects its n tiles (x 2 column halves)
+  const int blk = row / a.block_rows;
+  const int n_rec = 2 * ((((blk + 1) * a.n_tiles - 1) / a.quota) - ((blk * a.n_tiles) / a.quota) + 1);
   // log-sum-exp from the per-(tile half) partials, in a fixed order: lane-strided sequential sums, then the shuffle tree
   const float2* lp2 = reinterpret_cast<const float2*>(a.lse_part) + (int64_t)row * a.n_lse;
   float M = -INFINITY;
@@ -548,7 +552,8 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
   CAPDEC_REQUIRE(tk_supported(vocab, part_k) && n_rec <= kMergeMaxRecords && topk >= 1 && topk <= tk_bucket(part_k), CAPDEC_ERR_INVALID,
                  "topk_merge: topk %d exceeds the partial list length %d (vocab %d)", topk, tk_bucket(part_k), vocab);
   if (rows == 0) return CAPDEC_OK;
-  const MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, topk};
+  MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, topk, 0, 0, 0};
+  tk_schedule(rows, n_total, &ma.n_tiles, &ma.quota, &ma.block_rows);
   CAPDEC_CHECK_CUDA(launch_k(topk_merge_kernel, dim3(ceil_div(rows, 4)), dim3(128), 0, s, true, ma, out_lp, out_idx, out_lse));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
@@ -602,7 +607,8 @@ int select_fused(const float* part, const float* lse_part, int vocab, int n_tota
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage && 2 * k <= tk_bucket(part_k) && n_rec <= kMergeMaxRecords, CAPDEC_ERR_INVALID,
                  "select_fused: num_beams %d / record layout unsupported", k);
   if (B == 0) return CAPDEC_OK;
-  const MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, 2 * k};
+  MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, 2 * k, 0, 0, 0};
+  tk_schedule(rows, n_total, &ma.n_tiles, &ma.quota, &ma.block_rows);
   GatherArgs g{};
   if (ga) g = *ga;
   select_fused_kernel<<<B, 128, 0, s>>>(ma, st, k, T, cur_len, eos, div_fin, div_heur, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam,
