@@ -163,6 +163,9 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # the JSON line must be the only thing on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch.distributed as dist
     import capdec_b200 as cd
     from tests.helpers import legacy_weights
@@ -170,6 +173,19 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # keep this rank's threads (and, by first touch, its pinned feature buffer) on the CPUs NUMA-local to its GPU, so
+        # the ranks' host->device streams do not all cross the same memory controller / socket link
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
