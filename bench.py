@@ -163,9 +163,11 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    # the JSON line must be the only thing on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # the JSON line must be the only thing on stdout, but NCCL prints its version banner there: route fd 1 to stderr for
+    # the whole run and write the result line to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     import capdec_b200 as cd
     from tests.helpers import legacy_weights
@@ -357,7 +359,8 @@ def main():
             rec["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"{n} images x beam {BEAM} x {STEPS_PER_DECODE} steps, {dt:.1f} s, torch "
                                              f"{torch.__version__} fp32, {torch.get_num_threads()} threads"}
-        print(json.dumps(rec))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(rec) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
