@@ -6,7 +6,9 @@ namespace capdec {
 
 constexpr int kMaxRowsPerImage = 8;  // beams / samples of one image that share its feature tiles in one CTA
 
-enum AddAct : int { ACT_RELU = 0, ACT_TANH = 1 };
+// ACT_TANH_FAST: tanh as 1 - 2/(1 + e^{2x}) on the MUFU pipe (~1e-6 absolute error), used by the tensor-core precision modes:
+// with exact tanhf the 196 x H x k evaluations per image-step make the soft-attention kernel ALU-bound at 4x its HBM time
+enum AddAct : int { ACT_RELU = 0, ACT_TANH = 1, ACT_TANH_FAST = 2 };
 
 // Additive attention over one image's region tiles, all `k` rows (beams) of the image at once:
 //   e[b,l]   = (w . act(att1[img,l,:] + att2[row_b,:]) + w_bias) / temperature   (masked -> -1e9)

@@ -14,7 +14,7 @@ constexpr int kRowsPerIter = 4;  // region rows handled together by a warp in th
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
-  return ACT == ACT_RELU ? fmaxf(x, 0.f) : tanhf(x);
+  return ACT == ACT_RELU ? fmaxf(x, 0.f) : ACT == ACT_TANH_FAST ? tanh_fast_(x) : tanhf(x);
 }
 
 template <int KB, int ACT>
@@ -195,7 +195,8 @@ int launch_kb(const AddAttnArgs& a, int act, cudaStream_t s) {
   while (D4 * G * 2 <= kThreads) G *= 2;
   size_t smem = sizeof(float) * ((size_t)KB * a.A + a.A + (size_t)KB * Lp + (size_t)(G - 1) * KB * a.D);
   CAPDEC_REQUIRE(smem <= 200 * 1024, CAPDEC_ERR_UNSUPPORTED, "additive_attention: shared memory %zu B too large", smem);
-  auto kern = act == ACT_RELU ? additive_attention_kernel<KB, ACT_RELU> : additive_attention_kernel<KB, ACT_TANH>;
+  auto kern = act == ACT_RELU ? additive_attention_kernel<KB, ACT_RELU>
+            : act == ACT_TANH_FAST ? additive_attention_kernel<KB, ACT_TANH_FAST> : additive_attention_kernel<KB, ACT_TANH>;
   if (smem > 48 * 1024) CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<a.B, kThreads, smem, s>>>(a);
   CAPDEC_LAUNCH_CHECK();

@@ -68,8 +68,13 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+constexpr float kTwoLog2e = 2.8853900817779268f;   // e^{2x} = 2^{kTwoLog2e x}
+constexpr float kTanhRange = 21.f;                 // e^{+-42}: the product of two such factors stays a normal fp32
+
 template <int ACT>
-__device__ __forceinline__ float act_fn(float x) { return ACT == ACT_RELU ? fmaxf(x, 0.f) : tanhf(x); }
+__device__ __forceinline__ float act_fn(float x) {
+  return ACT == ACT_RELU ? fmaxf(x, 0.f) : ACT == ACT_TANH_FAST ? tanh_fast_(x) : tanhf(x);
+}
 
 // 4 consecutive elements (index i4 counts groups of 4) of a shared-memory tile row holding fp32 or bf16 data
 template <int BF>
@@ -99,6 +104,8 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   uint64_t* emptyF = fullF + kStagesF;
   uint64_t* e_full = emptyF + kStagesF;
   uint64_t* e_empty = e_full + kEBuf;
+  int* s_flag = reinterpret_cast<int*>(e_empty + kEBuf);         // [2] "an att2 value of this image is out of range"
+  float* s_wsum = reinterpret_cast<float*>(s_flag + 2);          // sum_a w[a]                (both ACT_TANH_FAST only)
 
   const int A = p.A, L = p.L, D = p.D, k = p.k, Lp = y.Lp;
   const int A4 = A >> 2, D4 = D >> 2;
@@ -110,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     for (int s = 0; s < kStagesF; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], kCtxWarps); }
     for (int s = 0; s < kEBuf; ++s) { mbar_init(&e_full[s], kScoreWarps); mbar_init(&e_empty[s], kCtxWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_flag[0] = s_flag[1] = 0;
   }
   __syncthreads();
   pdl_wait();
@@ -154,6 +162,12 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     // ================================ score warps ================================
     const int sw = warp - 2, t = threadIdx.x - 64;
     for (int i = t; i < A4; i += kScoreThreads) reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(p.w)[i];
+    if (ACT == ACT_TANH_FAST && sw == 0) {   // (p.w is a weight: not written by the preceding kernels)
+      float ws = 0.f;
+      for (int a = lane; a < A; a += 32) ws += p.w[a];
+      ws = warp_sum(ws);
+      if (lane == 0) *s_wsum = ws;
+    }
     uint32_t itA = 0;
     for (int i = 0; i < n_img; ++i) {
       const int img = blockIdx.x + i * gridDim.x;
@@ -167,9 +181,18 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           const int64_t rs = p.row_src ? p.row_src[row0 + b] : row0 + b;
           v = *reinterpret_cast<const float4*>(p.att2 + rs * p.ld_att2 + a4 * 4);
         }
+        if (ACT == ACT_TANH_FAST) {
+          // product form (see the score loop): the staged value is e^{2q}; out-of-range rows send the image down the
+          // direct path instead
+          if (fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > kTanhRange) s_flag[i & 1] = 1;
+          v.x = ex2_approx_(kTwoLog2e * v.x); v.y = ex2_approx_(kTwoLog2e * v.y);
+          v.z = ex2_approx_(kTwoLog2e * v.z); v.w = ex2_approx_(kTwoLog2e * v.w);
+        }
         reinterpret_cast<float4*>(q2)[j] = v;
       }
       named_barrier(1, kScoreThreads);
+      const bool qbig = ACT == ACT_TANH_FAST && s_flag[i & 1] != 0;
+      if (ACT == ACT_TANH_FAST && t == 0) s_flag[(i + 1) & 1] = 0;   // its last readers (image i-1) are behind this barrier
       mbar_wait(&e_empty[buf], (((uint32_t)i / kEBuf) & 1) ^ 1);   // the context warps are done with this alpha buffer
       float* e = s_e + (size_t)buf * KB * Lp;
       for (int c = 0; c < y.nA; ++c, ++itA) {
@@ -187,31 +210,91 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           for (int a4 = lane; a4 < A4; a4 += 32) {
             const float4 x0 = tile_ld4<BF>(x0p, a4), x1 = tile_ld4<BF>(x1p, a4);
             const float4 wv = reinterpret_cast<const float4*>(s_w)[a4];
+            if constexpr (ACT == ACT_TANH_FAST) {
+              // tanh(x + q) = 1 - 2 r,  r = 1 / (1 + e^{2x} e^{2q}):  e^{2x} once per tile element (shared by the k beams),
+              // e^{2q} once per beam row (staged above), so each (element, beam) costs ONE MUFU op (the reciprocal)
+              // instead of two.  acc accumulates sum_a w_a r_a; the score is sum(w) - 2 acc.  |x|, |q| <= 21 keeps the
+              // product inside fp32 range; anything larger (never seen from a trained projection) takes the direct form.
+              const float mx = fmaxf(fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x0.z), fabsf(x0.w))),
+                                     fmaxf(fmaxf(fabsf(x1.x), fabsf(x1.y)), fmaxf(fabsf(x1.z), fabsf(x1.w))));
+              if (!qbig && mx <= kTanhRange) {
+                const float4 E0 = make_float4(ex2_approx_(kTwoLog2e * x0.x), ex2_approx_(kTwoLog2e * x0.y),
+                                              ex2_approx_(kTwoLog2e * x0.z), ex2_approx_(kTwoLog2e * x0.w));
+                const float4 E1 = make_float4(ex2_approx_(kTwoLog2e * x1.x), ex2_approx_(kTwoLog2e * x1.y),
+                                              ex2_approx_(kTwoLog2e * x1.z), ex2_approx_(kTwoLog2e * x1.w));
 #pragma unroll
-            for (int b = 0; b < KB; ++b) {
-              const float4 q = reinterpret_cast<const float4*>(q2)[b * A4 + a4];
-              float u = acc0[b], v = acc1[b];
-              u = fmaf(wv.x, act_fn<ACT>(x0.x + q.x), u); v = fmaf(wv.x, act_fn<ACT>(x1.x + q.x), v);
-              u = fmaf(wv.y, act_fn<ACT>(x0.y + q.y), u); v = fmaf(wv.y, act_fn<ACT>(x1.y + q.y), v);
-              u = fmaf(wv.z, act_fn<ACT>(x0.z + q.z), u); v = fmaf(wv.z, act_fn<ACT>(x1.z + q.z), v);
-              u = fmaf(wv.w, act_fn<ACT>(x0.w + q.w), u); v = fmaf(wv.w, act_fn<ACT>(x1.w + q.w), v);
-              acc0[b] = u; acc1[b] = v;
-            }
-          }
-          const int l0 = c * y.rowsA + r;
+                for (int b = 0; b < KB; ++b) {
+                  const float4 q = reinterpret_cast<const float4*>(q2)[b * A4 + a4];
+                  float u = acc0[b], v = acc1[b];
+                  u = fmaf(wv.x, rcp_approx_(fmaf(E0.x, q.x, 1.f)), u); v = fmaf(wv.x, rcp_approx_(fmaf(E1.x, q.x, 1.f)), v);
+                  u = fmaf(wv.y, rcp_approx_(fmaf(E0.y, q.y, 1.f)), u); v = fmaf(wv.y, rcp_approx_(fmaf(E1.y, q.y, 1.f)), v);
+                  u = fmaf(wv.z, rcp_approx_(fmaf(E0.z, q.z, 1.f)), u); v = fmaf(wv.z, rcp_approx_(fmaf(E1.z, q.z, 1.f)), v);
+                  u = fmaf(wv.w, rcp_approx_(fmaf(E0.w, q.w, 1.f)), u); v = fmaf(wv.w, rcp_approx_(fmaf(E1.w, q.w, 1.f)), v);
+                  acc0[b] = u; acc1[b] = v;
+                }
+              } else {
+                for (int b = 0; b < k; ++b) {
+                  const int64_t rs = p.row_src ? p.row_src[row0 + b] : row0 + b;
+                  const float4 q = *reinterpret_cast<const float4*>(p.att2 + rs * p.ld_att2 + a4 * 4);
+                  const float xs0[4] = {x0.x, x0.y, x0.z, x0.w}, xs1[4] = {x1.x, x1.y, x1.z, x1.w};
+                  const float qs[4] = {q.x, q.y, q.z, q.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w};
+                  float u = 0.f, v = 0.f;
 #pragma unroll
-          for (int b = 0; b < KB; ++b) {
-            const float v0 = warp_sum(acc0[b]), v1 = warp_sum(acc1[b]);
-            if (lane == 0) {
-              float e0 = (v0 + p.w_bias) / p.temperature;
-              if (p.mask && p.mask[(int64_t)img * L + l0]) e0 = -1.0e9f;
-              e[b * Lp + l0] = e0;
-              if (r + 1 < rows) {
-                float e1 = (v1 + p.w_bias) / p.temperature;
-                if (p.mask && p.mask[(int64_t)img * L + l0 + 1]) e1 = -1.0e9f;
-                e[b * Lp + l0 + 1] = e1;
+                  for (int j = 0; j < 4; ++j) {
+                    u = fmaf(ws[j], rcp_approx_(1.f + ex2_approx_(kTwoLog2e * (xs0[j] + qs[j]))), u);
+                    v = fmaf(ws[j], rcp_approx_(1.f + ex2_approx_(kTwoLog2e * (xs1[j] + qs[j]))), v);
+                  }
+#pragma unroll
+                  for (int bb = 0; bb < KB; ++bb)
+                    if (bb == b) { acc0[bb] += u; acc1[bb] += v; }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int b = 0; b < KB; ++b) {
+                const float4 q = reinterpret_cast<const float4*>(q2)[b * A4 + a4];
+                float u = acc0[b], v = acc1[b];
+                u = fmaf(wv.x, act_fn<ACT>(x0.x + q.x), u); v = fmaf(wv.x, act_fn<ACT>(x1.x + q.x), v);
+                u = fmaf(wv.y, act_fn<ACT>(x0.y + q.y), u); v = fmaf(wv.y, act_fn<ACT>(x1.y + q.y), v);
+                u = fmaf(wv.z, act_fn<ACT>(x0.z + q.z), u); v = fmaf(wv.z, act_fn<ACT>(x1.z + q.z), v);
+                u = fmaf(wv.w, act_fn<ACT>(x0.w + q.w), u); v = fmaf(wv.w, act_fn<ACT>(x1.w + q.w), v);
+                acc0[b] = u; acc1[b] = v;
               }
             }
+          }
+          // 2 KB partial sums per lane -> one total per (row, beam): a transposing butterfly (each exchange halves the
+          // values a lane still carries) needs N - 1 + log2(32 / N) shuffles instead of 5 per value, and leaves the
+          // totals in different lanes, which store them in parallel.  Bias, temperature and mask are applied by the
+          // softmax pass below, spread over all lanes.
+          constexpr int N = KB <= 1 ? 2 : KB <= 2 ? 4 : KB <= 4 ? 8 : KB <= 8 ? 16 : 32;
+          static_assert(2 * KB <= 32, "beam bucket too wide for the score reduction");
+          float red[N];
+#pragma unroll
+          for (int j = 0; j < N / 2; ++j) { red[j] = j < KB ? acc0[j] : 0.f; red[N / 2 + j] = j < KB ? acc1[j] : 0.f; }
+          int n = N;
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) {
+            if (n > 1) {
+              const bool up = (lane & m) != 0;
+#pragma unroll
+              for (int j = 0; j < N / 2; ++j) {
+                if (j < n / 2) {
+                  const float send = up ? red[j] : red[j + n / 2];
+                  const float keep = up ? red[j + n / 2] : red[j];
+                  red[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+              }
+              n >>= 1;
+            } else {
+              red[0] += __shfl_xor_sync(0xffffffffu, red[0], m);
+            }
+          }
+          constexpr int kIdxShift = N == 32 ? 0 : N == 16 ? 1 : N == 8 ? 2 : N == 4 ? 3 : 4;
+          const int idx = lane >> kIdxShift, rsel = idx / (N / 2), b = idx - rsel * (N / 2);
+          if ((lane & ((1 << kIdxShift) - 1)) == 0 && b < KB && r + rsel < rows) {
+            float v = red[0];
+            if (ACT == ACT_TANH_FAST) v = fmaf(-2.f, v, *s_wsum);
+            e[b * Lp + c * y.rowsA + r + rsel] = v;
           }
         }
         __syncwarp();
@@ -221,7 +304,12 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       for (int b = sw; b < k; b += kScoreWarps) {
         float* eb = e + b * Lp;
         float m = -INFINITY;
-        for (int l = lane; l < L; l += 32) m = fmaxf(m, eb[l]);
+        for (int l = lane; l < L; l += 32) {
+          float v = (eb[l] + p.w_bias) / p.temperature;
+          if (p.mask && p.mask[(int64_t)img * L + l]) v = -1.0e9f;
+          eb[l] = v;
+          m = fmaxf(m, v);
+        }
         m = warp_max(m);
         float sum = 0.f;
         for (int l = lane; l < L; l += 32) {
@@ -355,7 +443,7 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   y->off_w = take((size_t)a.A * 4);
   y->off_e = take((size_t)kEBuf * KB * Lp * 4);
   y->off_red = take(G > 1 ? (size_t)(G - 1) * KB * a.D * 4 : 16);
-  y->off_bar = take((size_t)(2 * kStagesA + 2 * kStagesF + 2 * kEBuf) * 8);
+  y->off_bar = take((size_t)(2 * kStagesA + 2 * kStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
   const size_t budget = 220 * 1024;
   if (fixed + kStagesA * rowA + kStagesF * rowF > budget) return false;
   // att1 ring: one full pass of the score warps (2 rows each) per stage when it fits; the feats ring gets the rest
@@ -396,11 +484,13 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
     CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));                                                                           \
   }
   if (a.tile_bf16) {
-    if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }
-    else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 1) }
+    if (act == ACT_RELU)           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }
+    else if (act == ACT_TANH_FAST) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 2, 1) }
+    else                           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 1) }
   } else {
-    if (act == ACT_RELU) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 0) }
-    else                 { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 0) }
+    if (act == ACT_RELU)           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 0) }
+    else if (act == ACT_TANH_FAST) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 2, 0) }
+    else                           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 0) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 0) }
   }
 #undef CAPDEC_STREAM_LAUNCH
   CAPDEC_LAUNCH_CHECK();

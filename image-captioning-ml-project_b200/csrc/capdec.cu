@@ -434,7 +434,9 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
     a.w_bias = h->energy_bias; a.temperature = c.temperature; a.mask = mask; a.feats = feats;
     a.gate = nullptr; a.ctx = base_dst; a.ld_ctx = ld_base; a.alpha = alpha; a.ld_alpha = ld_alpha;
     a.B = images; a.L = S.L; a.A = H; a.D = H; a.k = k;
-    { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, ACT_TANH, s)); }
+    // exact tanhf in the fp32 mode; the MUFU form (1e-6) in the tensor-core modes, whose GEMM noise is 100x larger
+    const int act = (c.precision == CAPDEC_PREC_FP32 || getenv("CAPDEC_EXACT_TANH")) ? ACT_TANH : ACT_TANH_FAST;
+    { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, act, s)); }
   }
 
   StageScope sc_tail(h, STAGE_SMALL_GEMM, s);

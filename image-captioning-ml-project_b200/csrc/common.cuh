@@ -94,8 +94,13 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 // MUFU-based forms for the tensor-core epilogues (ex2.approx + rcp: ~1e-6 relative / 2e-7 absolute error, far below the
 // MMA accumulation noise of those modes); the exact-fp32 GEMM keeps expf / IEEE division
-__device__ __forceinline__ float sigmoid_fast_(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast_(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+// (rcp.approx is the bare MUFU.RCP; __frcp_rn expands to a Newton fix-up plus a slow-path call and is 3x the instructions)
+__device__ __forceinline__ float rcp_approx_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoid_fast_(float x) { return rcp_approx_(1.f + ex2_approx_(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast_(float x) {
+  return fmaf(-2.f, rcp_approx_(1.f + ex2_approx_(2.8853900817779268f * x)), 1.f);
+}
 __device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_tanh_(float x) {   // transformers.activations.NewGELUActivation
   return 0.5f * x * (1.f + tanhf(0.79788456080286535588f * (x + 0.044715f * x * x * x)));

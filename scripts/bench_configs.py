@@ -49,6 +49,14 @@ if "c1" in which:
         ms, nl = timeit(lambda: m.beam_search(enc, beam_size=3, max_length=20))
         out[f"c1_legacy_beam3_64img_{prec}"] = {"ms": ms, "images_per_s": 64 / ms * 1e3, "launches": nl,
                                                  "stage_ms": stage(m, lambda: m.beam_search(enc, beam_size=3, max_length=20))}
+if "c2src" in which:
+    from tests.helpers import lstm_decoder
+    for kind, heads in (("soft", 8), ("aoa", 8)):
+        m, _ = lstm_decoder(kind, H=512, layers=1, heads=heads, V=10000); m.precision = "bf16x3"; m = m.to(dev)
+        ef = {"features": rnd((4096, 196, 512), 3), "pooled_features": rnd((4096, 512), 4)}
+        ms, nl = timeit(lambda: m.generate(ef, 20, num_beams=5))
+        out[f"c2src_lstm_{kind}_beam5_4096img_bf16x3"] = {"ms": ms, "images_per_s": 4096 / ms * 1e3, "launches": nl,
+                                                          "stage_ms": stage(m, lambda: m.generate(ef, 20, num_beams=5))}
 if "c3" in which:
     m, _ = transformer_decoder(H=768, layers=6, heads=8, V=10000, max_length=50); m.precision = "bf16x3"; m = m.to(dev)
     ef = {"features": rnd((2048, 196, 768), 5)}

@@ -146,6 +146,41 @@ def test_attention_forward_matches_oracle(cuda, kind, heads, H, L, rpi, masked, 
     assert torch.allclose(ctx.cpu(), ref_ctx, atol=2e-5), (ctx.cpu() - ref_ctx).abs().max()
 
 
+@pytest.mark.parametrize("scale", [1.0, 6.0, 40.0])
+@pytest.mark.parametrize("H,L,rpi", [(512, 196, 5), (128, 37, 3)])
+def test_soft_attention_product_form_tanh(cuda, scale, H, L, rpi):
+    """The tensor-core modes evaluate tanh(att1 + att2) as 1 - 2/(1 + e^{2 att1} e^{2 att2}) (one MUFU op per element and
+    beam; attn_stream.cu).  It has to agree with the exact form for ordinary activations AND for |pre-activation| far
+    outside the range where the product is representable (scale 40: |x| up to ~150 -> the kernel's direct-form path)."""
+    torch.manual_seed(21)
+    mod = cd.build_attention(cd.AttentionConfig(attention_type=cd.AttentionType("soft"), num_heads=1, hidden_dim=H)).eval()
+    sd = {"attention." + k: v.detach().clone() for k, v in mod.state_dict().items()}
+    B = 6
+    g = torch.Generator().manual_seed(22)
+    q, feats = torch.randn(B * rpi, H, generator=g) * scale, torch.randn(B, L, H, generator=g) * scale
+    if scale > 10:   # opposite-signed huge terms whose SUM is moderate: clamping either factor alone would be wrong
+        q[:, : H // 2] = 0
+    img = torch.arange(B).repeat_interleave(rpi)
+    ref_ctx, ref_w = oatt.attend("soft", sd, "attention.", q, feats, 1, img, None, 1.0, None, None)
+    mod = mod.to(cuda)
+    mod.precision = "bf16x3"
+    f = feats.to(cuda)
+    ctx, w = mod(q.to(cuda), f, f, None, rows_per_image=rpi)
+    # the projections themselves run as 3-term bf16 GEMMs here (~1e-5 relative on O(scale) pre-activations)
+    tol = 2e-5 * max(1.0, scale * scale)
+    assert torch.allclose(w.cpu(), ref_w, atol=tol), (w.cpu() - ref_w).abs().max()
+    assert torch.allclose(ctx.cpu(), ref_ctx, atol=20 * tol * scale, rtol=1e-3), (ctx.cpu() - ref_ctx).abs().max()
+    assert torch.isfinite(ctx).all() and torch.isfinite(w).all()
+    # same GEMMs, exact tanhf in the score loop: isolates the activation's own error
+    os.environ["CAPDEC_EXACT_TANH"] = "1"
+    try:
+        ctx_x, w_x = mod(q.to(cuda), f, f, None, rows_per_image=rpi)
+    finally:
+        del os.environ["CAPDEC_EXACT_TANH"]
+    assert torch.allclose(w, w_x, atol=3e-6, rtol=2e-5), (w - w_x).abs().max()
+    assert torch.allclose(ctx, ctx_x, atol=2e-5 * scale, rtol=1e-4), (ctx - ctx_x).abs().max()
+
+
 # ------------------------------------------------------------------------------------------------ legacy path
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_legacy_teacher_forced_vs_oracle_and_golden(cuda, precision):
