@@ -40,15 +40,55 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 50 ms while the timed region runs."""
+    """SM clock + throttle reasons of this rank's GPU, sampled in-process through NVML every 20 ms while the timed
+    region runs (nvidia-smi takes longer to start on an 8-GPU box than a short timed region lasts; it is only the
+    fallback when pynvml is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h, self.stop = index, [], None, None, None, threading.Event()
+        self.sm, self.mx, self.reasons = [], None, set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown))
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names:
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            if self.stop.wait(0.02):
+                break
 
     def __enter__(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -63,11 +103,18 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc:
+        if self.nv is not None:
+            self.stop.set()
+            self.t.join(timeout=2)
+        elif self.proc:
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        if self.nv is not None:
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -77,7 +124,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -348,6 +395,16 @@ def main():
                                "frac": v_ach / tpeak if v_ach else None, "shape": [R, Nv, 512], "mma_terms": terms,
                                "note": "vocabulary padded to 256 + the [dec_att|f_beta] tail; fused log-softmax/top-k epilogue"},
                 "peak_source": tsrc}
+            # beam reorder (gather_rows_kernel): per row read new h and c (2 x 4H bytes), write h into the gate operand
+            # as fp32 and as its hi/lo bf16 pair, write c  -> 5 x 4H bytes per row; it runs out of L2 as much as out of
+            # HBM (its sources were written by the kernel before it), so "frac" can exceed 1 against the HBM peak
+            ga_ms, ga_n = stage["gather"]
+            if ga_n:
+                ga_bytes = R * 5 * 4 * 512
+                ga_ach = ga_bytes / (ga_ms / ga_n * 1e-3) / 1e9
+                rec["stage_roofline"]["reorder"] = {"kernel": "gather_rows_kernel", "bound": "hbm", "achieved": ga_ach, "peak": peak,
+                                                    "unit": "GB/s", "frac": ga_ach / peak, "algorithmic_bytes_per_launch": ga_bytes,
+                                                    "avg_launch_ms": ga_ms / ga_n}
         if e2e:
             rec["e2e"] = e2e
         if other_modes:
