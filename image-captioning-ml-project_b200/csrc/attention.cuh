@@ -25,8 +25,11 @@ struct AddAttnArgs {
   float w_bias, temperature;
   const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr
   const float* feats;                   // [B,L,D]
-  int tile_bf16;                        // 1: att1 and feats point at bf16 tiles of the same shapes (the bf16 precision mode
-                                        // streams half the bytes; streaming kernel only)
+  int tile_bf16;                        // tile format (streaming kernel only).  0: fp32.  1: att1 and feats point at bf16 tiles of
+                                        // the same shapes (bf16 mode: half the bytes).  2: "p24" planes (common.cuh; bf16x3 mode:
+                                        // three quarters of the bytes): att1 / feats point at the 16-bit planes,
+  const uint8_t* att1_b8;               //    att1_b8 / feats_b8 at the byte planes
+  const uint8_t* feats_b8;
   const float* gate; int64_t ld_gate;   // [R,D] or nullptr
   float* ctx; int64_t ld_ctx;           // [R,D]  (may be nullptr when ctx_split carries the only consumer's copy)
   SplitDst ctx_split; int ctx_split_col; // optional: ctx also/only as the split GEMM operand, at column ctx_split_col
@@ -38,7 +41,7 @@ int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s);
 // kernel in attn_additive.cu, < 0 on error
 int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s);
 // whether the streaming kernel covers a shape (callers that want bf16 tiles must know before they lay out the workspace)
-bool additive_attention_stream_supports(int A, int D, int L, int k, bool tile_bf16);
+bool additive_attention_stream_supports(int A, int D, int L, int k, int tile_fmt);
 
 // Multi-head dot-product attention on hoisted per-image K/V projections, all k rows of an image per CTA:
 //   s[b,h,l] = q[row_b,h,:] . K[img,l,h,:] / denom      (masked -> -1e9)

@@ -27,15 +27,17 @@ namespace {
 constexpr int kScoreWarps = 8, kCtxWarps = 8;
 constexpr int kScoreThreads = 32 * kScoreWarps, kCtxThreads = 32 * kCtxWarps;
 constexpr int kThreads = 64 + kScoreThreads + kCtxThreads;   // 576
-constexpr int kStagesA = 2, kStagesF = 4;
+constexpr int kMaxStagesA = 4, kStagesF = 4;                 // att1 ring: StreamLayout::stA stages (2; CAPDEC_ATTN_STAGES_A overrides: 3 and 4 measured slower, they shrink the feats ring)
 constexpr int kEBuf = 3;                                     // alpha buffers: scores of image i+1 while context reads image i
 constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct StreamLayout {
   int rowsA, rowsF, nA, nF;            // rows per ring stage, stages per image
   uint32_t stageA, stageF;             // bytes per stage
+  uint32_t b8A, b8F;                   // p24 tiles: offset of the byte plane inside a stage
   uint32_t off_ringA, off_ringF, off_att2, off_w, off_e, off_red, off_bar, total;
   int Lp, G;                           // padded L; context row groups (threads split rows when D/4 <= 128)
+  int stA;                             // att1 ring stages
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,7 +80,8 @@ __device__ __forceinline__ float act_fn(float x) {
 
 // 4 consecutive elements (index i4 counts groups of 4) of a shared-memory tile row holding fp32 or bf16 data
 template <int BF>
-__device__ __forceinline__ float4 tile_ld4(const void* row, int i4) {
+__device__ __forceinline__ float4 tile_ld4(const void* row, int i4, const void* row_b8 = nullptr) {
+  if (BF == 2) return p24_decode4_(reinterpret_cast<const uint2*>(row)[i4], reinterpret_cast<const uint32_t*>(row_b8)[i4]);
   if (BF) {
     const uint2 u = reinterpret_cast<const uint2*>(row)[i4];
     return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
@@ -89,18 +92,20 @@ __device__ __forceinline__ float4 tile_ld4(const void* row, int i4) {
 
 template <int KB, int ACT, int NC, int BF>
 __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(const AddAttnArgs p, const StreamLayout y) {
-  constexpr size_t ES = BF ? 2 : 4;   // bytes per tile element
+  constexpr size_t ES = BF ? 2 : 4;   // bytes per element of the (first) tile plane; BF == 2 adds a byte plane behind it
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ringA = smem + y.off_ringA;
   uint8_t* ringF = smem + y.off_ringF;
   float* s_att2 = reinterpret_cast<float*>(smem + y.off_att2);   // [2][KB][A]
   float* s_w = reinterpret_cast<float*>(smem + y.off_w);         // [A]
-  float* s_e = reinterpret_cast<float*>(smem + y.off_e);         // [kEBuf][KB][Lp]
+  float* s_e = reinterpret_cast<float*>(smem + y.off_e);         // [kEBuf][Lp][KBP]: the beams of a region are adjacent
+  constexpr int KBP = KB <= 4 ? 4 : 8;
   float* s_red = reinterpret_cast<float*>(smem + y.off_red);     // [G-1][KB][D]
   uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + y.off_bar);
-  uint64_t* emptyA = fullA + kStagesA;
-  uint64_t* fullF = emptyA + kStagesA;
+  uint64_t* emptyA = fullA + kMaxStagesA;
+  uint64_t* fullF = emptyA + kMaxStagesA;
+  const int kStagesA = y.stA;
   uint64_t* emptyF = fullF + kStagesF;
   uint64_t* e_full = emptyF + kStagesF;
   uint64_t* e_empty = e_full + kEBuf;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   const int n_img = ((int)blockIdx.x < p.B) ? (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStagesA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], kScoreWarps); }
+    for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], kScoreWarps); }
     for (int s = 0; s < kStagesF; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], kCtxWarps); }
     for (int s = 0; s < kEBuf; ++s) { mbar_init(&e_full[s], kScoreWarps); mbar_init(&e_empty[s], kCtxWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -134,9 +139,12 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           mbar_wait(&emptyF[s], ((itF / kStagesF) & 1) ^ 1);
           const int rows = min(y.rowsF, L - c * y.rowsF);
           const uint32_t bytes = (uint32_t)(rows * rowF);
-          mbar_expect_tx(&fullF[s], bytes);
+          mbar_expect_tx(&fullF[s], BF == 2 ? bytes + bytes / 2 : bytes);
           bulk_load(ringF + (size_t)s * y.stageF,
                     reinterpret_cast<const char*>(p.feats) + ((size_t)img * L + (size_t)c * y.rowsF) * rowF, bytes, &fullF[s]);
+          if (BF == 2)
+            bulk_load(ringF + (size_t)s * y.stageF + y.b8F, p.feats_b8 + ((size_t)img * L + (size_t)c * y.rowsF) * D, bytes / 2,
+                      &fullF[s]);
         }
       }
     }
@@ -152,9 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           mbar_wait(&emptyA[s], ((itA / kStagesA) & 1) ^ 1);
           const int rows = min(y.rowsA, L - c * y.rowsA);
           const uint32_t bytes = (uint32_t)(rows * rowA);
-          mbar_expect_tx(&fullA[s], bytes);
+          mbar_expect_tx(&fullA[s], BF == 2 ? bytes + bytes / 2 : bytes);
           bulk_load(ringA + (size_t)s * y.stageA,
                     reinterpret_cast<const char*>(p.att1) + ((size_t)img * L + (size_t)c * y.rowsA) * rowA, bytes, &fullA[s]);
+          if (BF == 2)
+            bulk_load(ringA + (size_t)s * y.stageA + y.b8A, p.att1_b8 + ((size_t)img * L + (size_t)c * y.rowsA) * A, bytes / 2,
+                      &fullA[s]);
         }
       }
     }
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       const bool qbig = ACT == ACT_TANH_FAST && s_flag[i & 1] != 0;
       if (ACT == ACT_TANH_FAST && t == 0) s_flag[(i + 1) & 1] = 0;   // its last readers (image i-1) are behind this barrier
       mbar_wait(&e_empty[buf], (((uint32_t)i / kEBuf) & 1) ^ 1);   // the context warps are done with this alpha buffer
-      float* e = s_e + (size_t)buf * KB * Lp;
+      float* e = s_e + (size_t)buf * KBP * Lp;
       for (int c = 0; c < y.nA; ++c, ++itA) {
         const int s = itA % kStagesA;
         mbar_wait(&fullA[s], (itA / kStagesA) & 1);
@@ -204,11 +215,14 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           const int r1 = min(r + 1, rows - 1);
           const void* x0p = tile + (size_t)r * A * ES;
           const void* x1p = tile + (size_t)r1 * A * ES;
+          const void* x0b = tile + y.b8A + (size_t)r * A;     // (BF == 2 only)
+          const void* x1b = tile + y.b8A + (size_t)r1 * A;
           float acc0[KB], acc1[KB];
+          float2 pacc0[KB], pacc1[KB];   // (packed relu path only)
 #pragma unroll
-          for (int b = 0; b < KB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+          for (int b = 0; b < KB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; pacc0[b] = pacc1[b] = make_float2(0.f, 0.f); }
           for (int a4 = lane; a4 < A4; a4 += 32) {
-            const float4 x0 = tile_ld4<BF>(x0p, a4), x1 = tile_ld4<BF>(x1p, a4);
+            const float4 x0 = tile_ld4<BF>(x0p, a4, x0b), x1 = tile_ld4<BF>(x1p, a4, x1b);
             const float4 wv = reinterpret_cast<const float4*>(s_w)[a4];
             if constexpr (ACT == ACT_TANH_FAST) {
               // tanh(x + q) = 1 - 2 r,  r = 1 / (1 + e^{2x} e^{2q}):  e^{2x} once per tile element (shared by the k beams),
@@ -249,6 +263,22 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
                     if (bb == b) { acc0[bb] += u; acc1[bb] += v; }
                 }
               }
+            } else if constexpr (ACT == ACT_RELU && BF != 0) {
+              // tolerance-based modes: packed add / fma (FADD2, FFMA2), two interleaved partial sums per accumulator
+#pragma unroll
+              for (int b = 0; b < KB; ++b) {
+                const float4 q = reinterpret_cast<const float4*>(q2)[b * A4 + a4];
+                float2 s0 = __fadd2_rn(make_float2(x0.x, x0.y), make_float2(q.x, q.y));
+                float2 s1 = __fadd2_rn(make_float2(x0.z, x0.w), make_float2(q.z, q.w));
+                float2 t0 = __fadd2_rn(make_float2(x1.x, x1.y), make_float2(q.x, q.y));
+                float2 t1 = __fadd2_rn(make_float2(x1.z, x1.w), make_float2(q.z, q.w));
+                s0.x = fmaxf(s0.x, 0.f); s0.y = fmaxf(s0.y, 0.f); s1.x = fmaxf(s1.x, 0.f); s1.y = fmaxf(s1.y, 0.f);
+                t0.x = fmaxf(t0.x, 0.f); t0.y = fmaxf(t0.y, 0.f); t1.x = fmaxf(t1.x, 0.f); t1.y = fmaxf(t1.y, 0.f);
+                pacc0[b] = __ffma2_rn(make_float2(wv.x, wv.y), s0, pacc0[b]);
+                pacc0[b] = __ffma2_rn(make_float2(wv.z, wv.w), s1, pacc0[b]);
+                pacc1[b] = __ffma2_rn(make_float2(wv.x, wv.y), t0, pacc1[b]);
+                pacc1[b] = __ffma2_rn(make_float2(wv.z, wv.w), t1, pacc1[b]);
+              }
             } else {
 #pragma unroll
               for (int b = 0; b < KB; ++b) {
@@ -268,6 +298,10 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           // softmax pass below, spread over all lanes.
           constexpr int N = KB <= 1 ? 2 : KB <= 2 ? 4 : KB <= 4 ? 8 : KB <= 8 ? 16 : 32;
           static_assert(2 * KB <= 32, "beam bucket too wide for the score reduction");
+          if constexpr (ACT == ACT_RELU && BF != 0) {
+#pragma unroll
+            for (int b = 0; b < KB; ++b) { acc0[b] = pacc0[b].x + pacc0[b].y; acc1[b] = pacc1[b].x + pacc1[b].y; }
+          }
           float red[N];
 #pragma unroll
           for (int j = 0; j < N / 2; ++j) { red[j] = j < KB ? acc0[j] : 0.f; red[N / 2 + j] = j < KB ? acc1[j] : 0.f; }
@@ -294,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           if ((lane & ((1 << kIdxShift) - 1)) == 0 && b < KB && r + rsel < rows) {
             float v = red[0];
             if (ACT == ACT_TANH_FAST) v = fmaf(-2.f, v, *s_wsum);
-            e[b * Lp + c * y.rowsA + r + rsel] = v;
+            e[(c * y.rowsA + r + rsel) * KBP + b] = v;
           }
         }
         __syncwarp();
@@ -302,27 +336,27 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       }
       named_barrier(1, kScoreThreads);   // every score of the image is in shared memory
       for (int b = sw; b < k; b += kScoreWarps) {
-        float* eb = e + b * Lp;
+        float* eb = e + b;   // element l at eb[l * KBP]
         float m = -INFINITY;
         for (int l = lane; l < L; l += 32) {
-          float v = (eb[l] + p.w_bias) / p.temperature;
+          float v = (eb[l * KBP] + p.w_bias) / p.temperature;
           if (p.mask && p.mask[(int64_t)img * L + l]) v = -1.0e9f;
-          eb[l] = v;
+          eb[l * KBP] = v;
           m = fmaxf(m, v);
         }
         m = warp_max(m);
         float sum = 0.f;
         for (int l = lane; l < L; l += 32) {
-          const float v = expf(eb[l] - m);
-          eb[l] = v;
+          const float v = expf(eb[l * KBP] - m);
+          eb[l * KBP] = v;
           sum += v;
         }
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
         float* aout = p.alpha ? p.alpha + (row0 + b) * p.ld_alpha : nullptr;
         for (int l = lane; l < L; l += 32) {
-          const float v = eb[l] * inv;
-          eb[l] = v;
+          const float v = eb[l * KBP] * inv;
+          eb[l * KBP] = v;
           if (aout) aout[l] = v;
         }
       }
@@ -335,41 +369,75 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     const int Dw = D4 < kCtxThreads ? D4 : kCtxThreads;   // float4 columns covered per pass
     const int g = t / Dw, c0 = t - g * Dw;
     const bool active = g < y.G;
+    // per-thread constants of the row loop: byte offsets of this thread's columns inside a tile row (columns past D/4 are
+    // clamped: they compute a duplicate that is never stored), row strides
+    uint32_t offH[NC], offB[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int col = min(c0 + j * kCtxThreads, D4 - 1);
+      offH[j] = (uint32_t)col * (BF ? 8u : 16u); offB[j] = (uint32_t)col * 4u;
+    }
+    const uint32_t rowH = (uint32_t)D * (uint32_t)ES;
+    const uint32_t stepH = (uint32_t)y.G * rowH, stepB = (uint32_t)y.G * (uint32_t)D, stepE = (uint32_t)y.G * KBP;
     uint32_t itF = 0;
     for (int i = 0; i < n_img; ++i) {
       const int img = blockIdx.x + i * gridDim.x;
       const int64_t row0 = (int64_t)img * k;
       const int buf = i % kEBuf;
       mbar_wait(&e_full[buf], ((uint32_t)i / kEBuf) & 1);
-      const float* e = s_e + (size_t)buf * KB * Lp;
-      float4 acc[NC][KB];
+      const float* e = s_e + (size_t)buf * KBP * Lp;
+      // packed fp32x2 FMAs (FFMA2, sm_100): the same IEEE fma per element, half the issue slots
+      float2 acc[NC][KB][2];
 #pragma unroll
       for (int j = 0; j < NC; ++j)
 #pragma unroll
-        for (int b = 0; b < KB; ++b) acc[j][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < KB; ++b) acc[j][b][0] = acc[j][b][1] = make_float2(0.f, 0.f);
       for (int c = 0; c < y.nF; ++c, ++itF) {
         const int s = itF % kStagesF;
         mbar_wait(&fullF[s], (itF / kStagesF) & 1);
         const int rows = min(y.rowsF, L - c * y.rowsF);
         const uint8_t* tile = ringF + (size_t)s * y.stageF;
         if (active) {
-          for (int r = g; r < rows; r += y.G) {
-            const int l = c * y.rowsF + r;
-            float4 x[NC];
+          // rows g, g + G, ... of the chunk, two per iteration (the loads of both rows are in flight before the first
+          // FMA needs them); all addresses advance by per-thread constants
+          const uint8_t* ph = tile + (size_t)g * rowH;
+          const uint8_t* pb = tile + y.b8F + (size_t)g * D;
+          const float* ep = e + (size_t)(c * y.rowsF + g) * KBP;
+          int n = (rows - g + y.G - 1) / y.G;
+          auto load = [&](float4 (&x)[NC], const uint8_t* h, const uint8_t* q8) {
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
-              const int col = c0 + j * kCtxThreads;
-              x[j] = col < D4 ? tile_ld4<BF>(tile + (size_t)r * D * ES, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (BF == 2) x[j] = p24_decode4_(*reinterpret_cast<const uint2*>(h + offH[j]), *reinterpret_cast<const uint32_t*>(q8 + offB[j]));
+              else if (BF == 1) x[j] = tile_ld4<1>(h + offH[j], 0);
+              else x[j] = *reinterpret_cast<const float4*>(h + offH[j]);
             }
+          };
+          auto fma_row = [&](const float4 (&x)[NC], const float* al) {
+            float w[KBP];
+            *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(al);
+            if (KBP == 8) *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(al + 4);
 #pragma unroll
             for (int b = 0; b < KB; ++b) {
-              const float al = e[b * Lp + l];
+              const float2 a2 = make_float2(w[b], w[b]);
 #pragma unroll
               for (int j = 0; j < NC; ++j) {
-                acc[j][b].x = fmaf(al, x[j].x, acc[j][b].x); acc[j][b].y = fmaf(al, x[j].y, acc[j][b].y);
-                acc[j][b].z = fmaf(al, x[j].z, acc[j][b].z); acc[j][b].w = fmaf(al, x[j].w, acc[j][b].w);
+                acc[j][b][0] = __ffma2_rn(a2, make_float2(x[j].x, x[j].y), acc[j][b][0]);
+                acc[j][b][1] = __ffma2_rn(a2, make_float2(x[j].z, x[j].w), acc[j][b][1]);
               }
             }
+          };
+          for (; n >= 2; n -= 2) {
+            float4 x[NC], xb[NC];
+            load(x, ph, pb);
+            load(xb, ph + stepH, pb + stepB);
+            fma_row(x, ep);
+            fma_row(xb, ep + stepE);
+            ph += 2 * stepH; pb += 2 * stepB; ep += 2 * stepE;
+          }
+          if (n == 1) {
+            float4 x[NC];
+            load(x, ph, pb);
+            fma_row(x, ep);
           }
         }
         __syncwarp();
@@ -378,7 +446,9 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       if (y.G > 1) {   // (NC == 1 here) fold the row groups through shared memory
         if (active && g > 0) {
 #pragma unroll
-          for (int b = 0; b < KB; ++b) reinterpret_cast<float4*>(s_red)[((size_t)(g - 1) * KB + b) * D4 + c0] = acc[0][b];
+          for (int b = 0; b < KB; ++b)
+            reinterpret_cast<float4*>(s_red)[((size_t)(g - 1) * KB + b) * D4 + c0] =
+                make_float4(acc[0][b][0].x, acc[0][b][0].y, acc[0][b][1].x, acc[0][b][1].y);
         }
         named_barrier(2, kCtxThreads);
         if (active && g == 0) {
@@ -386,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
           for (int b = 0; b < KB; ++b)
             for (int gg = 1; gg < y.G; ++gg) {
               const float4 v = reinterpret_cast<const float4*>(s_red)[((size_t)(gg - 1) * KB + b) * D4 + c0];
-              acc[0][b].x += v.x; acc[0][b].y += v.y; acc[0][b].z += v.z; acc[0][b].w += v.w;
+              acc[0][b][0].x += v.x; acc[0][b][0].y += v.y; acc[0][b][1].x += v.z; acc[0][b][1].y += v.w;
             }
         }
         named_barrier(2, kCtxThreads);   // s_red may be overwritten by the next image only after everyone has read it
@@ -399,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
 #pragma unroll
           for (int b = 0; b < KB; ++b) {
             if (b >= k) continue;
-            float4 v = acc[j][b];
+            float4 v = make_float4(acc[j][b][0].x, acc[j][b][0].y, acc[j][b][1].x, acc[j][b][1].y);
             if (p.gate) {
               const int64_t rs = p.row_src ? p.row_src[row0 + b] : row0 + b;
               const float4 gt = *reinterpret_cast<const float4*>(p.gate + rs * p.ld_gate + col * 4);
@@ -430,7 +500,8 @@ int sm_count() {
 // Shared-memory plan; returns false when the shape does not fit this kernel (the caller uses the generic kernel).
 bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   const int A4 = a.A / 4, D4 = a.D / 4;
-  const size_t es = a.tile_bf16 ? 2 : 4;
+  const size_t es = a.tile_bf16 == 2 ? 3 : a.tile_bf16 ? 2 : 4;   // bytes per tile element over all planes
+  if (a.tile_bf16 == 2 && (a.A % 16 || a.D % 16)) return false;   // byte-plane rows must stay 16-byte multiples
   if (a.A % 8 || a.D % 8 || D4 > 2 * kCtxThreads || a.L < 1) return false;   // rows are multiples of 16 bytes in either tile type
   if ((((uintptr_t)a.att1 | (uintptr_t)a.feats | (uintptr_t)a.att2 | (uintptr_t)a.w) & 15) != 0) return false;
   int G = 1;
@@ -441,10 +512,13 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   auto take = [&](size_t bytes) { const size_t o = fixed; fixed = (fixed + bytes + 127) & ~(size_t)127; return (uint32_t)o; };
   y->off_att2 = take((size_t)2 * KB * a.A * 4);
   y->off_w = take((size_t)a.A * 4);
-  y->off_e = take((size_t)kEBuf * KB * Lp * 4);
+  y->off_e = take((size_t)kEBuf * (KB <= 4 ? 4 : 8) * Lp * 4);
   y->off_red = take(G > 1 ? (size_t)(G - 1) * KB * a.D * 4 : 16);
-  y->off_bar = take((size_t)(2 * kStagesA + 2 * kStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
+  y->off_bar = take((size_t)(2 * kMaxStagesA + 2 * kStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
   const size_t budget = 220 * 1024;
+  static const int stA_env = getenv("CAPDEC_ATTN_STAGES_A") ? atoi(getenv("CAPDEC_ATTN_STAGES_A")) : 0;
+  const int kStagesA = stA_env >= 2 && stA_env <= kMaxStagesA ? stA_env : 2;
+  y->stA = kStagesA;
   if (fixed + kStagesA * rowA + kStagesF * rowF > budget) return false;
   // att1 ring: one full pass of the score warps (2 rows each) per stage when it fits; the feats ring gets the rest
   const size_t left = budget - fixed;
@@ -463,6 +537,7 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   y->nA = (a.L + rowsA - 1) / rowsA; y->nF = (a.L + rowsF - 1) / rowsF;
   y->stageA = (uint32_t)(((size_t)rowsA * rowA + 127) & ~(size_t)127);
   y->stageF = (uint32_t)(((size_t)rowsF * rowF + 127) & ~(size_t)127);
+  y->b8A = (uint32_t)rowsA * a.A * 2; y->b8F = (uint32_t)rowsF * a.D * 2;
   y->off_ringA = take((size_t)kStagesA * y->stageA);
   y->off_ringF = take((size_t)kStagesF * y->stageF);
   y->total = (uint32_t)fixed;
@@ -483,7 +558,10 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));             \
     CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));                                                                           \
   }
-  if (a.tile_bf16) {
+  if (a.tile_bf16 == 2) {
+    CAPDEC_REQUIRE(act == ACT_RELU && a.att1_b8 && a.feats_b8, CAPDEC_ERR_UNSUPPORTED, "p24 tiles: relu attention with both byte planes only");
+    if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 2) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 2)
+  } else if (a.tile_bf16) {
     if (act == ACT_RELU)           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }
     else if (act == ACT_TANH_FAST) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 2, 1) }
     else                           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 1) }
@@ -499,10 +577,10 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
 
 }  // namespace
 
-bool additive_attention_stream_supports(int A, int D, int L, int k, bool tile_bf16) {
+bool additive_attention_stream_supports(int A, int D, int L, int k, int tile_fmt) {
   if (getenv("CAPDEC_ATTN_GENERIC") != nullptr || k < 1 || k > kMaxRowsPerImage) return false;
   AddAttnArgs a{};
-  a.A = A; a.D = D; a.L = L; a.k = k; a.tile_bf16 = tile_bf16 ? 1 : 0;
+  a.A = A; a.D = D; a.L = L; a.k = k; a.tile_bf16 = tile_fmt;
   StreamLayout y{};
   return plan(a, k <= 6 ? k : 8, &y);
 }

@@ -128,6 +128,9 @@ struct Session {
   // feats_h [B,L,D] is also the att1 GEMM's operand, att1_h [B,L,A] comes straight out of that GEMM's epilogue
   void* feats_h = nullptr; void* att1_h = nullptr;
   void* feats_l = nullptr;               // split modes: lo copy of the features (hi in feats_h); both feed the hoisted enc_att GEMM
+  // bf16x3 mode, "p24" tiles (common.cuh): feats_h / att1_h are the 16-bit planes (feats_h still the GEMM's hi operand),
+  // these the byte planes; the attention kernel streams 3 bytes per element instead of 4
+  uint8_t* feats_b8 = nullptr; uint8_t* att1_b8 = nullptr;
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
@@ -247,6 +250,11 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
         // operand copies of the features for the hoisted enc_att GEMM, written by the same pass that takes the region mean
         S.feats_h = ar.take<char>((size_t)B * L * D * es);
         S.feats_l = lo ? ar.take<char>((size_t)B * L * D * es) : nullptr;
+        if (c.precision == CAPDEC_PREC_BF16X3 && !getenv("CAPDEC_NO_P24_TILES") && additive_attention_stream_supports(A, D, L, k, 2)) {
+          S.feats_b8 = ar.take<uint8_t>((size_t)B * L * D);
+          S.att1_h = ar.take<char>((size_t)B * L * A * 2);
+          S.att1_b8 = ar.take<uint8_t>((size_t)B * L * A);
+        }
       }
     }
     if (!S.att1_h) S.att1 = ar.take<float>((size_t)B * L * A);
@@ -331,10 +339,10 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
   if (S.feats_h) {
     // one pass over the features: region mean (for h0 / c0, :137-139) + the hi/lo operand copies.  In the bf16 mode the
     // hi copy is also what the attention kernel streams every step and the GEMM's epilogue emits att1 directly as bf16.
-    const SplitDst fsplit{S.feats_h, S.feats_l, D, kind};
+    const SplitDst fsplit{S.feats_h, S.feats_l, D, kind, S.feats_b8};
     CAPDEC_RETURN_IF(mean_regions_split(feats, S.B, S.L, D, S.meanb, fsplit, s));
     if (S.att1_h) {
-      const SplitDst c_out{S.att1_h, nullptr, A, KIND_BF16};
+      const SplitDst c_out{S.att1_h, nullptr, A, KIND_BF16, S.att1_b8};
       CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", nullptr, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &fsplit, &c_out));
     } else {
       CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", S.att1, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &fsplit));
@@ -474,7 +482,11 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   AddAttnArgs a{};
   a.row_src = reuse ? S.row_src : nullptr;
   a.att1 = S.att1; a.att2 = S.hproj;
-  if (S.att1_h) { a.att1 = reinterpret_cast<const float*>(S.att1_h); a.tile_bf16 = 1; } a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
+  if (S.att1_h) {
+    a.att1 = reinterpret_cast<const float*>(S.att1_h); a.tile_bf16 = S.att1_b8 ? 2 : 1;
+    a.att1_b8 = S.att1_b8; a.feats_b8 = S.feats_b8;
+  }
+  a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
   a.temperature = 1.f; a.mask = nullptr; a.feats = S.att1_h ? reinterpret_cast<const float*>(S.feats_h) : feats;
   a.gate = S.hproj + A; a.ld_gate = A + D;
   a.ctx = S.X[0] + E; a.ld_ctx = S.ldX[0]; a.alpha = alpha; a.ld_alpha = ld_alpha;

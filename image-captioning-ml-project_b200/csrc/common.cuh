@@ -125,7 +125,26 @@ struct SplitDst {
   void* hi; void* lo;      // lo == nullptr: single-term mode; hi == nullptr: no split copy wanted
   int64_t ld;              // row stride in ELEMENTS of the operand type
   int kind;
+  uint8_t* b8;             // KIND_BF16 only, optional: the "p24" byte plane (below), same row stride
 };
+// ---- p24: planar 24-bit storage of an fp32 tile that is streamed every step (attention region tiles, bf16x3 mode) ----
+// plane 1 = the top 16 bits of each fp32 (a truncated bf16: it doubles as the "hi" GEMM operand), plane 2 = one byte
+// q = round(low16 / 257).  Decoding replicates the byte, (hi16 << 16) | (q << 8) | q = hi16:q*257, so it is a single
+// byte-permute per element, needs no carry into the upper plane when encoding, and is within 128.5 fp32 ulps (2^-16
+// relative) of the original -- the same 16 significant bits the 3-term bf16 GEMMs of that mode keep of every operand.
+__device__ __forceinline__ uint32_t p24_q_(uint32_t bits) { return (((bits & 0xffffu) + 128u) * 65281u) >> 24; }   // == (low16 + 128) / 257
+__device__ __forceinline__ float4 p24_decode4_(uint2 hi, uint32_t q) {
+  return make_float4(__uint_as_float(__byte_perm(hi.x, q, 0x1044)), __uint_as_float(__byte_perm(hi.x, q, 0x3255)),
+                     __uint_as_float(__byte_perm(hi.y, q, 0x1066)), __uint_as_float(__byte_perm(hi.y, q, 0x3277)));
+}
+// encode 4 values: returns the 4 hi16 words, the 4 bytes, and the remainders v - hi (for the GEMM's lo operand)
+__device__ __forceinline__ void p24_encode4_(float4 v, uint2* hi, uint32_t* q, float4* rem) {
+  const uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y), b2 = __float_as_uint(v.z), b3 = __float_as_uint(v.w);
+  hi->x = __byte_perm(b0, b1, 0x7632); hi->y = __byte_perm(b2, b3, 0x7632);
+  *q = p24_q_(b0) | (p24_q_(b1) << 8) | (p24_q_(b2) << 16) | (p24_q_(b3) << 24);
+  *rem = make_float4(v.x - __uint_as_float(b0 & 0xffff0000u), v.y - __uint_as_float(b1 & 0xffff0000u),
+                     v.z - __uint_as_float(b2 & 0xffff0000u), v.w - __uint_as_float(b3 & 0xffff0000u));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2_(float a, float b, float* ra, float* rb) {
   const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
   *ra = a - __bfloat162float(ha); *rb = b - __bfloat162float(hb);
@@ -143,6 +162,16 @@ __device__ __forceinline__ void split_store4(const SplitDst& d, int64_t row, int
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.hi) + row * d.ld + col) = h;
     if (d.lo) *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.lo) + row * d.ld + col) = l;
+  } else if (d.b8) {
+    uint2 hp, lp; uint32_t q; float4 r; float dummy0, dummy1;
+    p24_encode4_(v, &hp, &q, &r);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.hi) + row * d.ld + col) = hp;
+    *reinterpret_cast<uint32_t*>(d.b8 + row * d.ld + col) = q;
+    if (d.lo) {
+      lp.x = pack_bf16x2_(r.x, r.y, &dummy0, &dummy1);
+      lp.y = pack_bf16x2_(r.z, r.w, &dummy0, &dummy1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.lo) + row * d.ld + col) = lp;
+    }
   } else {
     float r0, r1, r2, r3, dummy0, dummy1;
     uint2 hp, lp;
@@ -162,6 +191,18 @@ __device__ __forceinline__ void split_store8(const SplitDst& d, int64_t row, int
   if (d.kind == KIND_TF32) {
     split_store4(d, row, col, make_float4(v[0], v[1], v[2], v[3]));
     split_store4(d, row, col + 4, make_float4(v[4], v[5], v[6], v[7]));
+  } else if (d.b8) {
+    uint2 h0, h1, q; float4 r0, r1; float dm0, dm1;
+    p24_encode4_(make_float4(v[0], v[1], v[2], v[3]), &h0, &q.x, &r0);
+    p24_encode4_(make_float4(v[4], v[5], v[6], v[7]), &h1, &q.y, &r1);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.hi) + row * d.ld + col) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint2*>(d.b8 + row * d.ld + col) = q;
+    if (d.lo) {
+      uint4 lp;
+      lp.x = pack_bf16x2_(r0.x, r0.y, &dm0, &dm1); lp.y = pack_bf16x2_(r0.z, r0.w, &dm0, &dm1);
+      lp.z = pack_bf16x2_(r1.x, r1.y, &dm0, &dm1); lp.w = pack_bf16x2_(r1.z, r1.w, &dm0, &dm1);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.lo) + row * d.ld + col) = lp;
+    }
   } else {
     float r[8], dm0, dm1;
     uint4 hp, lp;
@@ -183,6 +224,11 @@ __device__ __forceinline__ void split_store1(const SplitDst& d, int64_t row, int
     const float h = __uint_as_float(t);
     reinterpret_cast<float*>(d.hi)[row * d.ld + col] = h;
     if (d.lo) reinterpret_cast<float*>(d.lo)[row * d.ld + col] = v - h;
+  } else if (d.b8) {
+    const uint32_t b = __float_as_uint(v);
+    reinterpret_cast<uint16_t*>(d.hi)[row * d.ld + col] = (uint16_t)(b >> 16);
+    d.b8[row * d.ld + col] = (uint8_t)p24_q_(b);
+    if (d.lo) reinterpret_cast<__nv_bfloat16*>(d.lo)[row * d.ld + col] = __float2bfloat16_rn(v - __uint_as_float(b & 0xffff0000u));
   } else {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     reinterpret_cast<__nv_bfloat16*>(d.hi)[row * d.ld + col] = h;
