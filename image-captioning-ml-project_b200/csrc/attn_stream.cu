@@ -36,7 +36,7 @@ struct StreamLayout {
   uint32_t stageA, stageF;             // bytes per stage
   uint32_t b8A, b8F;                   // p24 tiles: offset of the byte plane inside a stage
   uint32_t off_ringA, off_ringF, off_att2, off_w, off_e, off_red, off_bar, total;
-  int Lp, G;                           // padded L; context row groups (threads split rows when D/4 <= 128)
+  int Lp, G, gshift;                   // padded L; context row groups (threads split rows when D/4 <= 128), log2(G)
   int stA;                             // att1 ring stages
 };
 
@@ -366,17 +366,12 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   } else {
     // ================================ context warps ================================
     const int t = threadIdx.x - 64 - kScoreThreads;   // 0..255
-    const int Dw = D4 < kCtxThreads ? D4 : kCtxThreads;   // float4 columns covered per pass
-    const int g = t / Dw, c0 = t - g * Dw;
-    const bool active = g < y.G;
-    // per-thread constants of the row loop: byte offsets of this thread's columns inside a tile row (columns past D/4 are
-    // clamped: they compute a duplicate that is never stored), row strides
-    uint32_t offH[NC], offB[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      const int col = min(c0 + j * kCtxThreads, D4 - 1);
-      offH[j] = (uint32_t)col * (BF ? 8u : 16u); offB[j] = (uint32_t)col * 4u;
-    }
+    // NC == 1: thread = (row group g, float4 column c0), G row groups share a chunk's rows.  NC == 2 (D/4 > 256): every
+    // thread owns the two ADJACENT float4 columns 2t, 2t+1 (one 16/32-byte shared-memory load per plane and row), G == 1.
+    const int Dw = D4 < kCtxThreads ? D4 : kCtxThreads;
+    const int g = NC == 2 ? 0 : t / Dw, c0 = NC == 2 ? 2 * t : t - g * Dw;
+    const bool active = NC == 2 ? c0 < D4 : g < y.G;
+    const uint32_t offH = (uint32_t)c0 * (BF ? 8u : 16u), offB = (uint32_t)c0 * 4u;   // byte offsets inside a tile row
     const uint32_t rowH = (uint32_t)D * (uint32_t)ES;
     const uint32_t stepH = (uint32_t)y.G * rowH, stepB = (uint32_t)y.G * (uint32_t)D, stepE = (uint32_t)y.G * KBP;
     uint32_t itF = 0;
@@ -400,16 +395,31 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
         if (active) {
           // rows g, g + G, ... of the chunk, two per iteration (the loads of both rows are in flight before the first
           // FMA needs them); all addresses advance by per-thread constants
-          const uint8_t* ph = tile + (size_t)g * rowH;
-          const uint8_t* pb = tile + y.b8F + (size_t)g * D;
+          const uint8_t* ph = tile + (size_t)g * rowH + offH;
+          const uint8_t* pb = tile + y.b8F + (size_t)g * D + offB;
           const float* ep = e + (size_t)(c * y.rowsF + g) * KBP;
-          int n = (rows - g + y.G - 1) / y.G;
+          int n = (rows - g + y.G - 1) >> y.gshift;   // rows of this chunk that belong to row group g (G is a power of two)
           auto load = [&](float4 (&x)[NC], const uint8_t* h, const uint8_t* q8) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) {
-              if (BF == 2) x[j] = p24_decode4_(*reinterpret_cast<const uint2*>(h + offH[j]), *reinterpret_cast<const uint32_t*>(q8 + offB[j]));
-              else if (BF == 1) x[j] = tile_ld4<1>(h + offH[j], 0);
-              else x[j] = *reinterpret_cast<const float4*>(h + offH[j]);
+            if (NC == 2) {
+              if (BF == 2) {
+                const uint4 hv = *reinterpret_cast<const uint4*>(h);
+                const uint2 qv = *reinterpret_cast<const uint2*>(q8);
+                x[0] = p24_decode4_(make_uint2(hv.x, hv.y), qv.x);
+                x[NC - 1] = p24_decode4_(make_uint2(hv.z, hv.w), qv.y);
+              } else if (BF == 1) {
+                const uint4 hv = *reinterpret_cast<const uint4*>(h);
+                x[0] = make_float4(__uint_as_float(hv.x << 16), __uint_as_float(hv.x & 0xffff0000u),
+                                   __uint_as_float(hv.y << 16), __uint_as_float(hv.y & 0xffff0000u));
+                x[NC - 1] = make_float4(__uint_as_float(hv.z << 16), __uint_as_float(hv.z & 0xffff0000u),
+                                        __uint_as_float(hv.w << 16), __uint_as_float(hv.w & 0xffff0000u));
+              } else {
+                x[0] = reinterpret_cast<const float4*>(h)[0];
+                x[NC - 1] = reinterpret_cast<const float4*>(h)[1];
+              }
+            } else {
+              if (BF == 2) x[0] = p24_decode4_(*reinterpret_cast<const uint2*>(h), *reinterpret_cast<const uint32_t*>(q8));
+              else if (BF == 1) x[0] = tile_ld4<1>(h, 0);
+              else x[0] = *reinterpret_cast<const float4*>(h);
             }
           };
           auto fma_row = [&](const float4 (&x)[NC], const float* al) {
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       if (active && g == 0) {
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-          const int col = c0 + j * kCtxThreads;
+          const int col = c0 + j;
           if (col >= D4) continue;
 #pragma unroll
           for (int b = 0; b < KB; ++b) {
@@ -541,7 +551,8 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   y->off_ringA = take((size_t)kStagesA * y->stageA);
   y->off_ringF = take((size_t)kStagesF * y->stageF);
   y->total = (uint32_t)fixed;
-  y->Lp = Lp; y->G = G;
+  y->Lp = Lp; y->G = G; y->gshift = 0;
+  while ((1 << y->gshift) < G) ++y->gshift;
   (void)A4;
   return fixed <= 227 * 1024;
 }
