@@ -351,12 +351,17 @@ def main():
         att_ms, att_n = stage["attention"]
         per_launch_ms = att_ms / max(att_n, 1)
         # the bf16 mode streams bf16 tiles (half the algorithmic bytes); every other mode streams the fp32 tiles
-        attn_bytes = ATTN_BYTES_PER_IMAGE_STEP // 2 if args.precision == "bf16" else ATTN_BYTES_PER_IMAGE_STEP
+        # tile format the attention kernel streams: bf16 mode -> bf16 tiles (2 B/element), bf16x3 mode -> p24 planes
+        # (3 B/element, csrc/common.cuh), every other mode -> the fp32 tiles
+        tile_fmt = "bf16" if args.precision == "bf16" else \
+            "p24" if args.precision == "bf16x3" and not os.environ.get("CAPDEC_NO_P24_TILES") else "f32"
+        attn_bytes = ATTN_BYTES_PER_IMAGE_STEP * {"bf16": 2, "p24": 3, "f32": 4}[tile_fmt] // 4
         achieved = attn_bytes * B / (per_launch_ms * 1e-3) / 1e9 if att_n else None
         traffic = None
         tf = os.path.join(ROOT, "profiles", "attention_traffic.json")
         if os.path.isfile(tf):
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            tj = json.load(open(tf))
+            traffic = tj.get(tile_fmt, {}).get("dram_bytes_per_launch") if isinstance(tj.get(tile_fmt), dict) else None
         total_stage_ms = sum(v[0] for v in stage.values()) or 1.0
         rec = {
             "metric": "captioned images/sec (beam=5, max_len=20)", "value": value, "unit": "images/s",
@@ -369,9 +374,9 @@ def main():
                        "l2_policy": "inputs (6.6 GB/GPU) larger than L2, no flush"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"kernel": "additive_attention_stream_kernel<5,relu,2,%s>" % ("bf16" if args.precision == "bf16" else "f32"), "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "additive_attention_stream_kernel<5,relu,2,%s>" % tile_fmt, "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic if args.precision != "bf16" else None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "tile_bytes_per_element": {"bf16": 2, "p24": 3, "f32": 4}[tile_fmt],
                          "algorithmic_bytes_per_launch": attn_bytes * B,
                          "avg_launch_ms": per_launch_ms, "launches": att_n},
             "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},

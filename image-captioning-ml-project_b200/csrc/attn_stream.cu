@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   } else if (warp == 1) {
     // ================================ att1 producer ================================
     if (lane == 0) {
-      uint32_t itA = 0;
+      int sA = 0; uint32_t phA = 0;   // ring stage and its phase bit, kept as counters (the stage count is a run-time value)
       const size_t rowA = (size_t)A * ES;
       for (int i = 0; i < n_img; ++i) {
         const int img = blockIdx.x + i * gridDim.x;
-        for (int c = 0; c < y.nA; ++c, ++itA) {
-          const int s = itA % kStagesA;
-          mbar_wait(&emptyA[s], ((itA / kStagesA) & 1) ^ 1);
+        for (int c = 0; c < y.nA; ++c, phA ^= (++sA == kStagesA), sA = sA == kStagesA ? 0 : sA) {
+          const int s = sA;
+          mbar_wait(&emptyA[s], phA ^ 1);
           const int rows = min(y.rowsA, L - c * y.rowsA);
           const uint32_t bytes = (uint32_t)(rows * rowA);
           mbar_expect_tx(&fullA[s], BF == 2 ? bytes + bytes / 2 : bytes);
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       ws = warp_sum(ws);
       if (lane == 0) *s_wsum = ws;
     }
-    uint32_t itA = 0;
+    int sA = 0; uint32_t phA = 0;
     for (int i = 0; i < n_img; ++i) {
       const int img = blockIdx.x + i * gridDim.x;
       const int64_t row0 = (int64_t)img * k;
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       if (ACT == ACT_TANH_FAST && t == 0) s_flag[(i + 1) & 1] = 0;   // its last readers (image i-1) are behind this barrier
       mbar_wait(&e_empty[buf], (((uint32_t)i / kEBuf) & 1) ^ 1);   // the context warps are done with this alpha buffer
       float* e = s_e + (size_t)buf * KBP * Lp;
-      for (int c = 0; c < y.nA; ++c, ++itA) {
-        const int s = itA % kStagesA;
-        mbar_wait(&fullA[s], (itA / kStagesA) & 1);
+      for (int c = 0; c < y.nA; ++c, phA ^= (++sA == kStagesA), sA = sA == kStagesA ? 0 : sA) {
+        const int s = sA;
+        mbar_wait(&fullA[s], phA);
         const int rows = min(y.rowsA, L - c * y.rowsA);
         const uint8_t* tile = ringA + (size_t)s * y.stageA;
         for (int r = sw * 2; r < rows; r += kScoreWarps * 2) {
