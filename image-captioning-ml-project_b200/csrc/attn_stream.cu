@@ -27,7 +27,7 @@ namespace {
 constexpr int kScoreWarps = 8, kCtxWarps = 8;
 constexpr int kScoreThreads = 32 * kScoreWarps, kCtxThreads = 32 * kCtxWarps;
 constexpr int kThreads = 64 + kScoreThreads + kCtxThreads;   // 576
-constexpr int kMaxStagesA = 4, kStagesF = 4;                 // att1 ring: StreamLayout::stA stages (2; CAPDEC_ATTN_STAGES_A overrides: 3 and 4 measured slower, they shrink the feats ring)
+constexpr int kMaxStagesA = 4, kMaxStagesF = 8;                // att1 ring: StreamLayout::stA stages (2; CAPDEC_ATTN_STAGES_A overrides: 3 and 4 measured slower, they shrink the feats ring)
 constexpr int kEBuf = 3;                                     // alpha buffers: scores of image i+1 while context reads image i
 constexpr uint32_t kSpinLimit = 1u << 24;
 
@@ -37,7 +37,7 @@ struct StreamLayout {
   uint32_t b8A, b8F;                   // p24 tiles: offset of the byte plane inside a stage
   uint32_t off_ringA, off_ringF, off_att2, off_w, off_e, off_red, off_bar, total;
   int Lp, G, gshift;                   // padded L; context row groups (threads split rows when D/4 <= 128), log2(G)
-  int stA;                             // att1 ring stages
+  int stA, stF;                        // ring stages
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   uint64_t* emptyA = fullA + kMaxStagesA;
   uint64_t* fullF = emptyA + kMaxStagesA;
   const int kStagesA = y.stA;
-  uint64_t* emptyF = fullF + kStagesF;
-  uint64_t* e_full = emptyF + kStagesF;
+  uint64_t* emptyF = fullF + kMaxStagesF;
+  uint64_t* e_full = emptyF + kMaxStagesF;
+  const int kStagesF = y.stF;
   uint64_t* e_empty = e_full + kEBuf;
   int* s_flag = reinterpret_cast<int*>(e_empty + kEBuf);         // [2] "an att2 value of this image is out of range"
   float* s_wsum = reinterpret_cast<float*>(s_flag + 2);          // sum_a w[a]                (both ACT_TANH_FAST only)
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStagesA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], kScoreWarps); }
-    for (int s = 0; s < kStagesF; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], kCtxWarps); }
+    for (int s = 0; s < kMaxStagesF; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], kCtxWarps); }
     for (int s = 0; s < kEBuf; ++s) { mbar_init(&e_full[s], kScoreWarps); mbar_init(&e_empty[s], kCtxWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_flag[0] = s_flag[1] = 0;
@@ -130,13 +131,13 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   if (warp == 0) {
     // ================================ feats producer ================================
     if (lane == 0) {
-      uint32_t itF = 0;
+      int sF = 0; uint32_t phF = 0;
       const size_t rowF = (size_t)D * ES;
       for (int i = 0; i < n_img; ++i) {
         const int img = blockIdx.x + i * gridDim.x;
-        for (int c = 0; c < y.nF; ++c, ++itF) {
-          const int s = itF % kStagesF;
-          mbar_wait(&emptyF[s], ((itF / kStagesF) & 1) ^ 1);
+        for (int c = 0; c < y.nF; ++c, phF ^= (++sF == kStagesF), sF = sF == kStagesF ? 0 : sF) {
+          const int s = sF;
+          mbar_wait(&emptyF[s], phF ^ 1);
           const int rows = min(y.rowsF, L - c * y.rowsF);
           const uint32_t bytes = (uint32_t)(rows * rowF);
           mbar_expect_tx(&fullF[s], BF == 2 ? bytes + bytes / 2 : bytes);
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
     const uint32_t offH = (uint32_t)c0 * (BF ? 8u : 16u), offB = (uint32_t)c0 * 4u;   // byte offsets inside a tile row
     const uint32_t rowH = (uint32_t)D * (uint32_t)ES;
     const uint32_t stepH = (uint32_t)y.G * rowH, stepB = (uint32_t)y.G * (uint32_t)D, stepE = (uint32_t)y.G * KBP;
-    uint32_t itF = 0;
+    int sF = 0; uint32_t phF = 0;
     for (int i = 0; i < n_img; ++i) {
       const int img = blockIdx.x + i * gridDim.x;
       const int64_t row0 = (int64_t)img * k;
@@ -387,9 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
       for (int j = 0; j < NC; ++j)
 #pragma unroll
         for (int b = 0; b < KB; ++b) acc[j][b][0] = acc[j][b][1] = make_float2(0.f, 0.f);
-      for (int c = 0; c < y.nF; ++c, ++itF) {
-        const int s = itF % kStagesF;
-        mbar_wait(&fullF[s], (itF / kStagesF) & 1);
+      for (int c = 0; c < y.nF; ++c, phF ^= (++sF == kStagesF), sF = sF == kStagesF ? 0 : sF) {
+        const int s = sF;
+        mbar_wait(&fullF[s], phF);
         const int rows = min(y.rowsF, L - c * y.rowsF);
         const uint8_t* tile = ringF + (size_t)s * y.stageF;
         if (active) {
@@ -524,15 +525,19 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   y->off_w = take((size_t)a.A * 4);
   y->off_e = take((size_t)kEBuf * (KB <= 4 ? 4 : 8) * Lp * 4);
   y->off_red = take(G > 1 ? (size_t)(G - 1) * KB * a.D * 4 : 16);
-  y->off_bar = take((size_t)(2 * kMaxStagesA + 2 * kStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
+  y->off_bar = take((size_t)(2 * kMaxStagesA + 2 * kMaxStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
   const size_t budget = 220 * 1024;
   static const int stA_env = getenv("CAPDEC_ATTN_STAGES_A") ? atoi(getenv("CAPDEC_ATTN_STAGES_A")) : 0;
   const int kStagesA = stA_env >= 2 && stA_env <= kMaxStagesA ? stA_env : 2;
   y->stA = kStagesA;
+  static const int stF_env = getenv("CAPDEC_ATTN_STAGES_F") ? atoi(getenv("CAPDEC_ATTN_STAGES_F")) : 0;
+  const int kStagesF = stF_env >= 2 && stF_env <= kMaxStagesF ? stF_env : 3;   // measured at C2: 3 stages of 7 rows beat 4 x 5, 5 x 4, 6 x 3, 8 x 2 (21.5 / 21.9 / 22.4 / 23.6 / 25.2 ms)
+  y->stF = kStagesF;
+  static const int rowsA_env = getenv("CAPDEC_ATTN_ROWS_A") ? atoi(getenv("CAPDEC_ATTN_ROWS_A")) : 0;
   if (fixed + kStagesA * rowA + kStagesF * rowF > budget) return false;
   // att1 ring: one full pass of the score warps (2 rows each) per stage when it fits; the feats ring gets the rest
   const size_t left = budget - fixed;
-  int rowsA = 2 * kScoreWarps, rowsF = 0;
+  int rowsA = rowsA_env > 0 ? rowsA_env : 2 * kScoreWarps, rowsF = 0;
   if (rowsA > a.L) rowsA = a.L;
   for (; rowsA >= 1; rowsA = rowsA > 1 ? rowsA / 2 : 0) {
     const size_t needA = (size_t)kStagesA * (((size_t)rowsA * rowA + 127) & ~(size_t)127);
