@@ -286,6 +286,37 @@ def test_legacy_c2_identical_beams_on_256_images(cuda, precision):
                   min_identical=0.99 if precision == "fp32" else 0.98)
 
 
+def test_legacy_p24_tiles_vs_fp32_tiles(cuda):
+    """bf16x3 mode streams the region tiles as p24 planes (16 significant bits, csrc/common.cuh).  Same model, same
+    1024 images, with the planes and with the fp32 tiles (CAPDEC_NO_P24_TILES): the tile format alone must stay far
+    inside the mode's tolerance -- per-step candidate log-probs within 2e-4 where both runs follow the same
+    hypotheses, identical best beams on >= 99 % of the images, best scores within 2e-4."""
+    B, k, T = 1024, 5, 20
+    m, _ = legacy_weights(10000, 0)
+    m.precision = "bf16x3"
+    m = m.to(cuda)
+    enc = torch.randn(B, 196, 2048, generator=torch.Generator(device=cuda).manual_seed(77), device=cuda).relu_()
+    a = m.beam_search(enc, beam_size=k, max_length=T, trace=True)
+    os.environ["CAPDEC_NO_P24_TILES"] = "1"
+    try:
+        b = m.beam_search(enc, beam_size=k, max_length=T, trace=True)
+    finally:
+        del os.environ["CAPDEC_NO_P24_TILES"]
+    same = (a["tokens"] == b["tokens"]).all(dim=1)
+    assert same.float().mean().item() >= 0.99, same.float().mean().item()
+    assert (a["scores"][same] - b["scores"][same]).abs().max().item() < 2e-4
+    # step 0 has no history, so every image's candidates are comparable there; later steps where the trees still agree
+    # traces are [steps, B, 2k]: compare the candidate log-probs for as long as both runs explore the same hypotheses
+    agree = ((a["top_token"] == b["top_token"]) & (a["top_beam"] == b["top_beam"])).all(dim=-1)
+    alive = agree.long().cumprod(dim=0).bool()
+    d = (a["top_logprob"] - b["top_logprob"]).abs()[alive]
+    d = d[torch.isfinite(d)]
+    assert alive[0].all() or alive[0].float().mean().item() > 0.99
+    assert d.numel() > B * 2 * k and d.max().item() < 2e-4, d.max().item()
+    print(f"[p24 vs fp32 tiles] identical beams {same.float().mean().item():.4f}, max |dlogp| {d.max().item():.2e} "
+          f"over {d.numel()} candidates")
+
+
 def test_legacy_c2_bf16_mode(cuda):
     """The north star's bf16 mode (single-pass kind::f16 MMAs on bf16-rounded operands, fp32 accumulate; attention,
     softmax and the LSTM cell stay fp32): per-step beam log-probs within 2e-2 of the fp32 oracle.  With random-init
