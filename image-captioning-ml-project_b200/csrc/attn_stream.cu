@@ -5,18 +5,23 @@
 //   ctx[b,:] = sum_l alpha[b,l] * feats[img,l,:]   (* gate[row_b,:])
 //   legacy models/decoder.py:152-161 (relu, gate) / src/models/attention.py:76-111 (tanh)
 //
-// Per image-step the kernel must read att1 [L,A] and feats [L,D] exactly once (2.0 MB fp32 for 196 x (512+2048));
+// Per image-step the kernel must read att1 [L,A] and feats [L,D] exactly once (2.0 MB as fp32 tiles for 196 x (512+2048);
+// 1.5 MB as p24 planes in the bf16x3 mode, 1.0 MB as bf16 tiles in the bf16 mode -- template parameter BF = 0 / 2 / 1);
 // everything else is noise.  One CTA per SM walks images blockIdx.x, blockIdx.x + gridDim.x, ...:
 //   warps 0, 1    producers: one thread each streams feats / att1 through its own shared-memory ring with 1-D TMA bulk
-//                 copies (cp.async.bulk, mbarrier complete_tx).  The rows of an image are contiguous in HBM, so a ring
-//                 stage is simply a run of whole rows.  The two streams are independent: the att1 producer runs up to
-//                 two images ahead, so HBM requests never pause at an image boundary.
+//                 copies (cp.async.bulk, mbarrier complete_tx).  The rows of an image are contiguous in HBM (per plane), so
+//                 a ring stage is simply a run of whole rows (p24: the 16-bit rows, then the byte rows).  The two streams
+//                 are independent: the att1 producer runs up to two images ahead, so HBM requests never pause at an
+//                 image boundary.
 //   warps 2-9     score warps: att1 chunks -> scores (lanes split the attention dim, the k beams of the image reuse every
-//                 loaded element, warp-shuffle reduction) -> softmax -> alpha in a triple-buffered shared array.
-//   warps 10-17   context warps: feats chunks x alpha -> k context rows in registers -> gate multiply -> written
-//                 straight into the LSTM operand.
+//                 decoded element; a transposing butterfly reduces the 2k partial sums of a row pair) -> softmax (bias,
+//                 temperature and mask are applied here) -> alpha in a triple-buffered shared array laid out [l][beam].
+//   warps 10-17   context warps: feats chunks x alpha -> k context rows in registers (packed FFMA2, two rows per
+//                 iteration, adjacent columns per thread, constant strides) -> gate multiply -> written straight into
+//                 the LSTM operand.
 // The ALU-heavy score work of image i+1 therefore overlaps the load-heavy context work of image i inside one CTA, and
-// up to ~170 KB of loads are in flight per SM without costing registers.
+// up to ~170 KB of loads are in flight per SM without costing registers.  No loop contains a run-time division or
+// modulo (ring positions are counters, the row-group count is a power of two).
 #include <stdlib.h>
 
 #include "attention.cuh"

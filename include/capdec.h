@@ -55,7 +55,10 @@ typedef enum {
   CAPDEC_ATT_AOA = 3
 } capdec_attention;
 
-/* arithmetic of the dense contractions.  Attention / softmax / cell math is always fp32. */
+/* arithmetic of the dense contractions.  Attention / softmax / cell math is always fp32; what changes with the mode
+   is the storage the legacy attention kernel streams its region tiles from: fp32 (FP32, TF32X3, TF32), bf16 (BF16), or
+   24-bit planes with 16 significant bits (BF16X3), and the soft-attention tanh (exact tanhf in FP32, an exp / reciprocal
+   form accurate to ~1e-6 in the tensor-core modes). */
 typedef enum {
   CAPDEC_PREC_FP32 = 0,    /* CUDA-core FFMA, IEEE fp32 accumulate: the exact mode            */
   CAPDEC_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulate */
