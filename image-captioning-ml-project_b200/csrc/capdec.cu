@@ -1144,7 +1144,6 @@ int capdec_decode_greedy(capdec_handle* h, const float* feats, const float* pool
   carve(h, ar, S, B, L, 1, T, MODE_GREEDY);
   CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
   if (B == 0) return CAPDEC_OK;
-  const capdec_config& c = h->cfg;
   CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
   CAPDEC_RETURN_IF(fill_i32(S.next_tok, S.R, start_token_id, s));
   CAPDEC_RETURN_IF(commit(h, S, nullptr, out_tok, T, 0, false, s));  // out[:,0] = start (decoders.py:271)
