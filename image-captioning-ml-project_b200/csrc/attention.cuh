@@ -25,7 +25,7 @@ struct AddAttnArgs {
   float w_bias, temperature;
   const uint8_t* mask;                  // [B,L] 1 = padding, or nullptr
   const float* feats;                   // [B,L,D]
-  int tile_bf16;                        // tile format (streaming kernel only).  0: fp32.  1: att1 and feats point at bf16 tiles of
+  int tile_fmt;                        // tile format (streaming kernel only).  0: fp32.  1: att1 and feats point at bf16 tiles of
                                         // the same shapes (bf16 mode: half the bytes).  2: "p24" planes (common.cuh; bf16x3 mode:
                                         // three quarters of the bytes): att1 / feats point at the 16-bit planes,
   const uint8_t* att1_b8;               //    att1_b8 / feats_b8 at the byte planes

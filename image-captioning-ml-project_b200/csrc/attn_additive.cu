@@ -215,7 +215,7 @@ int additive_attention(const AddAttnArgs& a, int act, cudaStream_t s) {
   if (a.B == 0) return CAPDEC_OK;
   const int took = additive_attention_stream(a, act, s);   // persistent TMA-streamed kernel for the shapes it covers
   if (took != 0) return took > 0 ? CAPDEC_OK : took;
-  CAPDEC_REQUIRE(!a.tile_bf16, CAPDEC_ERR_UNSUPPORTED, "additive_attention: bf16 tiles need the streaming kernel (A=%d D=%d L=%d k=%d)",
+  CAPDEC_REQUIRE(!a.tile_fmt, CAPDEC_ERR_UNSUPPORTED, "additive_attention: bf16 / p24 tiles need the streaming kernel (A=%d D=%d L=%d k=%d)",
                  a.A, a.D, a.L, a.k);
   switch (a.k) {
     case 1: return launch_kb<1>(a, act, s);

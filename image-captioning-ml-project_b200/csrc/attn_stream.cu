@@ -516,8 +516,8 @@ int sm_count() {
 // Shared-memory plan; returns false when the shape does not fit this kernel (the caller uses the generic kernel).
 bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   const int A4 = a.A / 4, D4 = a.D / 4;
-  const size_t es = a.tile_bf16 == 2 ? 3 : a.tile_bf16 ? 2 : 4;   // bytes per tile element over all planes
-  if (a.tile_bf16 == 2 && (a.A % 16 || a.D % 16)) return false;   // byte-plane rows must stay 16-byte multiples
+  const size_t es = a.tile_fmt == 2 ? 3 : a.tile_fmt ? 2 : 4;   // bytes per tile element over all planes
+  if (a.tile_fmt == 2 && (a.A % 16 || a.D % 16)) return false;   // byte-plane rows must stay 16-byte multiples
   if (a.A % 8 || a.D % 8 || D4 > 2 * kCtxThreads || a.L < 1) return false;   // rows are multiples of 16 bytes in either tile type
   if ((((uintptr_t)a.att1 | (uintptr_t)a.feats | (uintptr_t)a.att2 | (uintptr_t)a.w) & 15) != 0) return false;
   int G = 1;
@@ -579,10 +579,10 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));             \
     CAPDEC_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kThreads), y.total, s, true, a, y));                                                                           \
   }
-  if (a.tile_bf16 == 2) {
+  if (a.tile_fmt == 2) {
     CAPDEC_REQUIRE(act == ACT_RELU && a.att1_b8 && a.feats_b8, CAPDEC_ERR_UNSUPPORTED, "p24 tiles: relu attention with both byte planes only");
     if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 2) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 2)
-  } else if (a.tile_bf16) {
+  } else if (a.tile_fmt) {
     if (act == ACT_RELU)           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_RELU, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_RELU, 2, 1) }
     else if (act == ACT_TANH_FAST) { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH_FAST, 2, 1) }
     else                           { if (nc == 1) CAPDEC_STREAM_LAUNCH(ACT_TANH, 1, 1) else CAPDEC_STREAM_LAUNCH(ACT_TANH, 2, 1) }
@@ -601,7 +601,7 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
 bool additive_attention_stream_supports(int A, int D, int L, int k, int tile_fmt) {
   if (getenv("CAPDEC_ATTN_GENERIC") != nullptr || k < 1 || k > kMaxRowsPerImage) return false;
   AddAttnArgs a{};
-  a.A = A; a.D = D; a.L = L; a.k = k; a.tile_bf16 = tile_fmt;
+  a.A = A; a.D = D; a.L = L; a.k = k; a.tile_fmt = tile_fmt;
   StreamLayout y{};
   return plan(a, k <= 6 ? k : 8, &y);
 }

@@ -483,7 +483,7 @@ int step_legacy(const capdec_handle* h, Session& S, const float* feats, int imag
   a.row_src = reuse ? S.row_src : nullptr;
   a.att1 = S.att1; a.att2 = S.hproj;
   if (S.att1_h) {
-    a.att1 = reinterpret_cast<const float*>(S.att1_h); a.tile_bf16 = S.att1_b8 ? 2 : 1;
+    a.att1 = reinterpret_cast<const float*>(S.att1_h); a.tile_fmt = S.att1_b8 ? 2 : 1;
     a.att1_b8 = S.att1_b8; a.feats_b8 = S.feats_b8;
   }
   a.ld_att2 = A + D; a.w = h->W("att.weight"); a.w_bias = h->energy_bias;
