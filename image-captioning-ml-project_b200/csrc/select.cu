@@ -113,8 +113,9 @@ struct MergeArgs {
   int n_tiles, quota, block_rows;   // the producing GEMM's schedule: tiles per row block, tiles per CTA-group run, rows per block
 };
 // one warp: merge the records of `row`; writes K sorted (log-prob, index) pairs through out_lp / out_idx (any address space)
+constexpr int kMergeStageFloats = 256;   // per-warp staging area: rows with few records (4 x 24 floats at C2) are merged from shared memory
 __device__ __forceinline__ void merge_row(const MergeArgs& a, int row, int lane, uint8_t* pos, float* out_lp, int32_t* out_idx,
-                                          float* out_lse) {
+                                          float* out_lse, float* stage = nullptr) {
   const int PS = a.PS, TKB = a.TKB;
   const float* pr = a.part + (int64_t)row * a.n_rec * PS;
   // slots this row's block actually wrote: one per CTA-group run that intersects its n tiles (x 2 column halves)
@@ -131,6 +132,11 @@ __device__ __forceinline__ void merge_row(const MergeArgs& a, int row, int lane,
     if (t * 128 < a.vocab) { const float2 v = lp2[t]; S += v.y * expf(v.x - M); }
   S = warp_sum(S);
   for (int t = lane; t < n_rec; t += 32) pos[t] = 0;
+  if (stage && n_rec * PS <= kMergeStageFloats) {
+    // one coalesced read of the row's records instead of two dependent L2 reads per merge round
+    for (int i = lane; i < n_rec * PS; i += 32) stage[i] = pr[i];
+    pr = stage;
+  }
   __syncwarp();
   const float logS = logf(S);
   if (lane == 0 && out_lse) *out_lse = M + logS;
@@ -169,10 +175,12 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a, floa
   pdl_trigger();
   pdl_wait();
   __shared__ uint8_t s_pos[4][kMergeMaxRecords];
+  __shared__ float s_stage[4][kMergeStageFloats];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 4 + warp;
   if (row >= a.rows) return;
-  merge_row(a, row, lane, s_pos[warp], out_lp + (int64_t)row * a.K, out_idx + (int64_t)row * a.K, out_lse ? out_lse + row : nullptr);
+  merge_row(a, row, lane, s_pos[warp], out_lp + (int64_t)row * a.K, out_idx + (int64_t)row * a.K, out_lse ? out_lse + row : nullptr,
+            s_stage[warp]);
 }
 
 // One CTA per row: inverse-CDF draw in vocabulary index order (double prefix sums), or argmax for the greedy slot.
@@ -396,11 +404,21 @@ __global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int c
                                  int32_t* dbg_tok, int32_t* dbg_beam) {
   pdl_trigger();
   pdl_wait();
+  // the image's k sorted candidate lists (k * 2k <= 128 entries) are read once, lane-parallel, into shared memory; the
+  // sequential k-way merge then runs on shared-memory latency instead of ten rounds of dependent L2 reads
+  __shared__ float s_lp[4][kMaxRowsPerImage * kMaxTopK];
+  __shared__ int32_t s_idx[4][kMaxRowsPerImage * kMaxTopK];
   const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (img >= B) return;
-  beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, cand_lp + (int64_t)img * k * 2 * k,
-                  cand_idx + (int64_t)img * k * 2 * k, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+  const int n = k * 2 * k;
+  for (int i = lane; i < n; i += 32) {
+    s_lp[w][i] = cand_lp[(int64_t)img * n + i];
+    s_idx[w][i] = cand_idx[(int64_t)img * n + i];
+  }
+  __syncwarp();
+  beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, s_lp[w], s_idx[w], next_tok, src_row, dbg_lp,
+                  dbg_tok, dbg_beam);
 }
 
 __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
