@@ -49,7 +49,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.nv, self.h, self.stop = index, [], None, None, None, threading.Event()
-        self.sm, self.mx, self.reasons = [], None, set()
+        self.sm, self.mx, self.reasons, self.power, self.power_limit = [], None, set(), [], None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -61,6 +61,10 @@ class ClockSampler:
                 phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                self.power_limit = None
             self.nv = pynvml
         except Exception:
             self.nv = None
@@ -79,9 +83,10 @@ class ClockSampler:
                 for n, bit in names:
                     if mask & bit:
                         self.reasons.add(n)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            if self.stop.wait(0.02):
+            if self.stop.wait(0.01):
                 break
 
     def __enter__(self):
@@ -113,8 +118,10 @@ class ClockSampler:
     def summary(self):
         if self.nv is not None:
             sm = sorted(self.sm)
+            pw = sorted(self.power)
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                    "samples": len(sm), "source": "nvml"}
+                    "samples": len(sm), "source": "nvml", "power_w": pw[len(pw) // 2] if pw else None,
+                    "power_limit_w": self.power_limit}
         sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()

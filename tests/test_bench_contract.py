@@ -33,3 +33,37 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_nonzero_rank_is_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert out.strip() == ""
+
+
+def test_clock_sampler_nvml_path_with_a_stub(monkeypatch):
+    """The in-process NVML sampler (no GPU here): a stub pynvml drives the same code path and the summary carries the
+    keys the bench line reports."""
+    import importlib
+    import time
+    import types
+    stub = types.ModuleType("pynvml")
+    stub.NVML_CLOCK_SM = 1
+    stub.nvmlClocksThrottleReasonHwSlowdown = 0x8
+    stub.nvmlClocksThrottleReasonHwThermalSlowdown = 0x40
+    stub.nvmlClocksThrottleReasonSwThermalSlowdown = 0x20
+    stub.nvmlClocksThrottleReasonSwPowerCap = 0x4
+    stub.nvmlClocksThrottleReasonHwPowerBrakeSlowdown = 0x80
+    stub.nvmlInit = lambda: None
+    stub.nvmlDeviceGetHandleByUUID = lambda u: (_ for _ in ()).throw(RuntimeError("no uuid"))
+    stub.nvmlDeviceGetHandleByIndex = lambda i: ("dev", i)
+    stub.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    stub.nvmlDeviceGetEnforcedPowerLimit = lambda h: 1000000
+    stub.nvmlDeviceGetClockInfo = lambda h, c: 1700
+    stub.nvmlDeviceGetCurrentClocksThrottleReasons = lambda h: 0x4
+    stub.nvmlDeviceGetPowerUsage = lambda h: 990000
+    monkeypatch.setitem(sys.modules, "pynvml", stub)
+    sys.path.insert(0, ROOT)
+    try:
+        bench = importlib.import_module("bench")
+        with bench.ClockSampler(0) as c:
+            time.sleep(0.08)
+        out = c.summary()
+    finally:
+        sys.path.remove(ROOT)
+    assert out["source"] == "nvml" and out["samples"] >= 2 and out["sm_mhz"] == 1700.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["power_w"] == 990.0 and out["power_limit_w"] == 1000.0
