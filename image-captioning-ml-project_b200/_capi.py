@@ -16,6 +16,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "capdec.h")
 ARCH_LEGACY_SAT, ARCH_LSTM, ARCH_TRANSFORMER, ARCH_GPT2 = 0, 1, 2, 3
 ATT = {"soft": 0, "multi_head": 1, "adaptive": 2, "aoa": 3}
 PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "tf32": 3, "bf16x3": 4}
+LAYOUT = {"bld": 0, "bdl": 1, "nchw": 1, "cls_bld": 2}          # capdec_layout
+DTYPE = {"f32": 0, "bf16": 1, "f16": 2, "p24": 3}               # capdec_dtype
 
 
 class CapdecError(RuntimeError):
@@ -67,6 +69,16 @@ def _load() -> C.CDLL:
     lib.capdec_forward_teacher.argtypes = [p, p, i32, i32, p, i32, C.POINTER(i32), p, p, p, sz, p]
     lib.capdec_attention_forward.argtypes = [p, p, p, p, p, p, i32, i32, i32, p, p, p, sz, p]
     lib.capdec_decode_beam_host.argtypes = [p, p, p, i32, i32, i32, i32, f32, i32, p, p, p]
+    lib.capdec_forward_tokens.argtypes = [p, p, p, p, i32, i32, i32, p, i32, i32, p, p, p, i32, p, sz, p]
+    lib.capdec_trim_at_eos.argtypes = [p, i64, i32, i32, i32, i32, i32, p, i64, p, p]
+    lib.capdec_source_bytes.argtypes = [i32, i32, i32, i32, i32]
+    lib.capdec_source_bytes.restype = sz
+    lib.capdec_tiles_bytes.argtypes = [p, i32, i32]
+    lib.capdec_tiles_bytes.restype = sz
+    lib.capdec_ingest_features.argtypes = [p, p, i32, i32, i32, i32, p, sz, p]
+    lib.capdec_decode_beam_tiles.argtypes = [p, p, p, p, i32, i32, i32, i32, f32, p, p, p, p, p, p, p, sz, p]
+    lib.capdec_pack_p24_host.argtypes = [p, i64, i64, p]
+    lib.capdec_decode_beam_host_ex.argtypes = [p, p, i32, i32, p, p, i32, i32, i32, i32, f32, i32, p, p, p]
     lib.capdec_stage_timing.argtypes = [p, i32]
     lib.capdec_stage_times.argtypes = [p, C.POINTER(f32), C.POINTER(i32)]
     lib.capdec_linear.argtypes = [i32, p, i64, p, i64, p, p, i64, i32, i32, i32, p]

@@ -17,10 +17,10 @@ import torch.nn as nn
 
 from . import _capi
 from .config import AttentionConfig, AttentionType, attention_kind
-from .engine import Engine
+from .engine import Engine, EngineOwner
 
 
-class AttentionMechanism(nn.Module):
+class AttentionMechanism(EngineOwner, nn.Module):
     """Base class (attention.py:9-35)."""
 
     _kind = None

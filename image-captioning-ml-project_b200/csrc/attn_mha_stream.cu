@@ -295,16 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) mha_attention_stream_kernel(const
   }
 }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return num_sms(); }
 
 bool plan(const MhaArgs& a, int KB, MhaLayout* y) {
   const int H4 = a.H / 4;

@@ -502,16 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) additive_attention_stream_kernel(
   }
 }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return num_sms(); }
 
 // Shared-memory plan; returns false when the shape does not fit this kernel (the caller uses the generic kernel).
 bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {

@@ -11,12 +11,25 @@
 #include <string.h>
 
 #include "handle.cuh"
+#include "ingest.cuh"
 #include "transformer.cuh"
 
 namespace capdec {
 
 static thread_local char g_err[1024] = "";
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
+
+int num_sms() {
+  static std::atomic<int> cache[kMaxDevices];
+  const int d = current_device();
+  int n = cache[d].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    if (n <= 0) n = 148;
+    cache[d].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -93,6 +106,14 @@ std::string base_prefix(const capdec_handle* h) {
   return (a == CAPDEC_ATT_AOA || a == CAPDEC_ATT_ADAPTIVE) ? "attention.base_attention." : "attention.";
 }
 
+// tile set produced by capdec_ingest_features: what the decode streams instead of the caller's fp32 [B,L,D] features
+struct TileSet {
+  bool valid = false, p24 = false;
+  float* f32 = nullptr;                                  // generic: dense fp32 [B,L,D]
+  void* hi = nullptr; void* lo = nullptr; uint8_t* b8 = nullptr; float* mean = nullptr;   // p24: planes + GEMM lo operand + region mean
+  size_t bytes = 0;
+};
+
 // ---- per-call workspace layout --------------------------------------------------------------------------
 struct Session {
   int B = 0, L = 0, k = 1, R = 0, T = 0;
@@ -134,9 +155,41 @@ struct Session {
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
+  int64_t logits_ld = 0;                // row stride of S.logits (0 = vocab_size); capdec_forward_tokens writes [R, t, V] blocks
+  // teacher-forced pass (capdec_forward_tokens), transformer family: key positions whose forced token is pad are masked
+  const int32_t* key_tok = nullptr; int64_t ld_key_tok = 0; int key_pad = -1;
+  // encoder hand-off (capdec_ingest_features): the p24 planes / lo operand / region mean already exist in a caller-owned
+  // tile set, so the prologue neither allocates nor recomputes them
+  TileSet ext{};
 };
 
 enum Mode { MODE_BEAM, MODE_GREEDY, MODE_SAMPLE, MODE_TEACHER, MODE_ATTENTION };
+
+// does this handle keep its region tiles as p24 planes (legacy decoder, BF16X3 mode)?  k-independent part of the test
+bool tiles_p24(const capdec_handle* h) {
+  const capdec_config& c = h->cfg;
+  const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
+  return is_legacy(h) && c.precision == CAPDEC_PREC_BF16X3 && (E + D + H) % 8 == 0 && H % 8 == 0 && E % 4 == 0 && A % 16 == 0 &&
+         D % 16 == 0 && !getenv("CAPDEC_NO_PRESPLIT") && !getenv("CAPDEC_NO_MEAN_SPLIT") && !getenv("CAPDEC_NO_P24_TILES");
+}
+// carve-up of a tile set for B images (base == nullptr: sizes only)
+TileSet tiles_layout(const capdec_handle* h, void* base, int B, int L) {
+  const size_t n = (size_t)B * L * h->cfg.feature_dim;
+  Arena ar(base, (size_t)-1);
+  TileSet t{};
+  t.valid = true;
+  if (tiles_p24(h)) {
+    t.p24 = true;
+    t.hi = ar.take<char>(n * 2);
+    t.b8 = ar.take<uint8_t>(n);
+    t.lo = ar.take<char>(n * 2);
+    t.mean = ar.take<float>((size_t)B * h->cfg.feature_dim);
+  } else {
+    t.f32 = ar.take<float>(n);
+  }
+  t.bytes = align_up(ar.off, 256);
+  return t;
+}
 
 int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, int T, Mode mode) {
   const capdec_config& c = h->cfg;
@@ -248,17 +301,24 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
         S.att1_h = ar.take<char>((size_t)B * L * A * 2);
       } else if (D % 8 == 0 && !getenv("CAPDEC_NO_MEAN_SPLIT")) {
         // operand copies of the features for the hoisted enc_att GEMM, written by the same pass that takes the region mean
-        S.feats_h = ar.take<char>((size_t)B * L * D * es);
-        S.feats_l = lo ? ar.take<char>((size_t)B * L * D * es) : nullptr;
-        if (c.precision == CAPDEC_PREC_BF16X3 && !getenv("CAPDEC_NO_P24_TILES") && additive_attention_stream_supports(A, D, L, k, 2)) {
-          S.feats_b8 = ar.take<uint8_t>((size_t)B * L * D);
+        const bool p24 = c.precision == CAPDEC_PREC_BF16X3 && !getenv("CAPDEC_NO_P24_TILES") && additive_attention_stream_supports(A, D, L, k, 2);
+        if (S.ext.valid && S.ext.p24) {
+          if (!p24) return CAPDEC_ERR_UNSUPPORTED;   // the planes are all there is: no fp32 features to fall back to
+          S.feats_h = S.ext.hi; S.feats_l = S.ext.lo; S.feats_b8 = S.ext.b8;
+        } else {
+          S.feats_h = ar.take<char>((size_t)B * L * D * es);
+          S.feats_l = lo ? ar.take<char>((size_t)B * L * D * es) : nullptr;
+          if (p24) S.feats_b8 = ar.take<uint8_t>((size_t)B * L * D);
+        }
+        if (p24) {
           S.att1_h = ar.take<char>((size_t)B * L * A * 2);
           S.att1_b8 = ar.take<uint8_t>((size_t)B * L * A);
         }
       }
     }
+    if (S.ext.valid && S.ext.p24 && !S.feats_b8) return CAPDEC_ERR_UNSUPPORTED;
     if (!S.att1_h) S.att1 = ar.take<float>((size_t)B * L * A);
-    S.meanb = ar.take<float>((size_t)B * D);
+    S.meanb = (S.ext.valid && S.ext.p24) ? S.ext.mean : ar.take<float>((size_t)B * D);
     S.init = ar.take<float>((size_t)B * 2 * H);
     S.hproj = ar.take<float>(R * (A + D));
   } else {
@@ -340,7 +400,7 @@ int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool
     // one pass over the features: region mean (for h0 / c0, :137-139) + the hi/lo operand copies.  In the bf16 mode the
     // hi copy is also what the attention kernel streams every step and the GEMM's epilogue emits att1 directly as bf16.
     const SplitDst fsplit{S.feats_h, S.feats_l, D, kind, S.feats_b8};
-    CAPDEC_RETURN_IF(mean_regions_split(feats, S.B, S.L, D, S.meanb, fsplit, s));
+    if (!(S.ext.valid && S.ext.p24)) CAPDEC_RETURN_IF(mean_regions_split(feats, S.B, S.L, D, S.meanb, fsplit, s));
     if (S.att1_h) {
       const SplitDst c_out{S.att1_h, nullptr, A, KIND_BF16, S.att1_b8};
       CAPDEC_RETURN_IF(linear(h, feats, D, "enc_att", nullptr, A, S.B * S.L, EPI_STORE, s, nullptr, 0, &fsplit, &c_out));
@@ -557,7 +617,7 @@ int step_lstm(const capdec_handle* h, Session& S, const float* feats, const uint
   // logits = output_layer(context)  (decoders.py:303)
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   CAPDEC_RETURN_IF(vocab_project(h, S, S.ctx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits,
-                                 c.vocab_size, s));
+                                 S.logits_ld ? S.logits_ld : c.vocab_size, s));
   return CAPDEC_OK;
 }
 
@@ -591,7 +651,7 @@ int prologue_transformer(const capdec_handle* h, Session& S, const float* feats,
 }
 
 // one KV-cached decode step at position t: tokens S.next_tok -> S.logits
-int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
+int step_transformer(const capdec_handle* h, Session& S, const uint8_t* mask, int t, cudaStream_t s) {
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, rows = S.R, heads = c.num_heads;
   const DevTensor* pos = h->find("position_encoding.weight");
@@ -611,6 +671,7 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
       a.anc = S.anc_cur >= 0 ? S.anc[S.anc_cur] : nullptr; a.n_prefix = 0; a.rows_per_image = S.k;
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
+      a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -620,7 +681,8 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
                               S.tqc, H, rows, H, H, EPI_STORE, s, &S.mx)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       MhaArgs m{};
-      m.q = S.tqc; m.ld_q = H; m.kproj = S.tck[l]; m.vproj = S.tcv[l]; m.ld_kv = H; m.mask = nullptr;
+      // memory_key_padding_mask: masked region keys get -1e9 (decoders.py:393-398; attention.py:97-100,183-186 semantics)
+      m.q = S.tqc; m.ld_q = H; m.kproj = S.tck[l]; m.vproj = S.tcv[l]; m.ld_kv = H; m.mask = mask;
       m.denom = (float)sqrt((double)(H / heads)); m.out = S.tca; m.ld_out = H; m.alpha = nullptr; m.ld_alpha = 0;
       m.B = S.B; m.L = S.L; m.H = H; m.heads = heads; m.k = S.k;
       CAPDEC_RETURN_IF(mha_attention(m, s)); }
@@ -634,7 +696,8 @@ int step_transformer(const capdec_handle* h, Session& S, int t, cudaStream_t s) 
       CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(tl(l, "norm3.weight")), h->W(tl(l, "norm3.bias")), nullptr, S.tx, rows, H, eps, s, &S.mx)); }
   }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
-  return vocab_project(h, S, S.tx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits, c.vocab_size, s);
+  return vocab_project(h, S, S.tx, H, h->W("output_layer.weight"), h->W("output_layer.bias"), rows, S.logits,
+                       S.logits_ld ? S.logits_ld : c.vocab_size, s);
 }
 
 // after position t_done: record tokens, and (beam) re-point every row's earlier cache positions at its parent's
@@ -693,6 +756,7 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
       a.prefix_k = S.gprefix; a.prefix_v = S.gprefix; a.n_prefix = P; a.rows_per_image = S.k;
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
+      a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -706,14 +770,14 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
     CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s, &S.mx)); }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   // lm_head is tied to wte and has no bias
-  return vocab_project(h, S, S.txn, H, h->W("model.lm_head.weight"), nullptr, rows, S.logits, c.vocab_size, s);
+  return vocab_project(h, S, S.txn, H, h->W("model.lm_head.weight"), nullptr, rows, S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, s);
 }
 
 int step_any(const capdec_handle* h, Session& S, const float* feats, const uint8_t* mask, float* alpha,
              int64_t ld_alpha, int t, cudaStream_t s) {
-  if (is_transformer(h)) return step_transformer(h, S, t, s);
+  if (is_transformer(h)) return step_transformer(h, S, mask, t, s);
   if (is_gpt2(h)) return step_gpt2(h, S, t, s);
-  if (is_legacy(h)) return step_legacy(h, S, feats, S.B, S.logits, h->cfg.vocab_size, alpha, ld_alpha, s);
+  if (is_legacy(h)) return step_legacy(h, S, feats, S.B, S.logits, S.logits_ld ? S.logits_ld : h->cfg.vocab_size, alpha, ld_alpha, s);
   return step_lstm(h, S, feats, mask, alpha, ld_alpha, s);
 }
 
@@ -765,7 +829,7 @@ int prologue_any(const capdec_handle* h, Session& S, const float* feats, const f
   return prologue_lstm(h, S, feats, pooled, s);
 }
 
-int check_common(const capdec_handle* h, const float* feats, const float* pooled, int B, int L, int k, int T) {
+int check_common(const capdec_handle* h, const void* feats, const float* pooled, int B, int L, int k, int T) {
   CAPDEC_REQUIRE(h != nullptr, CAPDEC_ERR_INVALID, "null handle");
   CAPDEC_REQUIRE(h->finalized, CAPDEC_ERR_STATE, "capdec_finalize has not been called");
   CAPDEC_REQUIRE(B == 0 || is_gpt2(h) || feats != nullptr, CAPDEC_ERR_INVALID, "features pointer is null");
@@ -827,7 +891,7 @@ extern "C" {
 
 const char* capdec_last_error(void) { return g_err; }
 int capdec_version(void) { return CAPDEC_VERSION; }
-int64_t capdec_launch_count(void) { return g_launch_count; }
+int64_t capdec_launch_count(void) { return g_launch_count.load(); }
 
 int capdec_create(const capdec_config* cfg, capdec_handle** out) {
   CAPDEC_REQUIRE(cfg && out, CAPDEC_ERR_INVALID, "capdec_create: null argument");
@@ -1080,17 +1144,21 @@ size_t capdec_workspace_bytes(const capdec_handle* h, int32_t B, int32_t L, int3
   return align_up(need + 4096, 4096);
 }
 
-int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
-                       int32_t L, int32_t k, int32_t T, float length_penalty, int32_t* out_tok, int32_t* out_len,
-                       float* out_score, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes,
-                       void* stream) {
-  CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, k, T));
+static int decode_beam_impl(capdec_handle* h, const float* feats, const TileSet* ext, const float* pooled, const uint8_t* mask,
+                            int32_t B, int32_t L, int32_t k, int32_t T, float length_penalty, int32_t* out_tok, int32_t* out_len,
+                            float* out_score, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes,
+                            void* stream) {
+  CAPDEC_RETURN_IF(check_common(h, ext ? (const void*)ext : (const void*)feats, pooled, B, L, k, T));
   CAPDEC_REQUIRE(B == 0 || (out_tok && out_len && out_score), CAPDEC_ERR_INVALID, "output pointers must not be null");
   CAPDEC_REQUIRE(is_legacy(h) ? mask == nullptr : true, CAPDEC_ERR_UNSUPPORTED, "legacy decoder takes no padding mask");
+  CAPDEC_REQUIRE(is_gpt2(h) ? mask == nullptr : true, CAPDEC_ERR_UNSUPPORTED,
+                 "GPT-2 decoder reads only pooled_features (decoders.py:629-637): a region padding mask has nothing to mask");
   cudaStream_t s = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
   Session S;
-  carve(h, ar, S, B, L, k, T, MODE_BEAM);
+  if (ext) S.ext = *ext;
+  CAPDEC_REQUIRE(carve(h, ar, S, B, L, k, T, MODE_BEAM) == CAPDEC_OK, CAPDEC_ERR_UNSUPPORTED,
+                 "p24 tile set cannot be decoded with %d rows per image (no streaming-attention plan); decode the fp32 features instead", k);
   CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
@@ -1130,6 +1198,115 @@ int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled
     if (more) CAPDEC_RETURN_IF(commit(h, S, S.src_row, nullptr, 0, -1, true, s, cur_len - 1));
   }
   CAPDEC_RETURN_IF(beam_finalize(S.beam, (T - 1) & 1, B, k, T, out_tok, out_len, out_score, s));
+  return CAPDEC_OK;
+}
+
+int capdec_decode_beam(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B,
+                       int32_t L, int32_t k, int32_t T, float length_penalty, int32_t* out_tok, int32_t* out_len,
+                       float* out_score, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes,
+                       void* stream) {
+  return decode_beam_impl(h, feats, nullptr, pooled, mask, B, L, k, T, length_penalty, out_tok, out_len, out_score, dbg_lp,
+                          dbg_tok, dbg_beam, ws, ws_bytes, stream);
+}
+
+// ---- encoder -> decoder feature hand-off -------------------------------------------------------------------
+size_t capdec_source_bytes(int32_t layout, int32_t dtype, int32_t B, int32_t L, int32_t D) {
+  if (B < 0 || L < 1 || D < 1) return 0;
+  return (size_t)B * ingest_source_image_bytes(layout, dtype, L, D);
+}
+
+size_t capdec_tiles_bytes(const capdec_handle* h, int32_t B, int32_t L) {
+  if (!h || B < 0 || L < 1) return 0;
+  return tiles_layout(h, nullptr, B, L).bytes;
+}
+
+int capdec_ingest_features(capdec_handle* h, const void* src, int32_t layout, int32_t dtype, int32_t B, int32_t L,
+                           void* tiles, size_t tiles_bytes, void* stream) {
+  CAPDEC_REQUIRE(h != nullptr && h->finalized, CAPDEC_ERR_STATE, "capdec_ingest_features: handle not finalized");
+  CAPDEC_REQUIRE(!is_gpt2(h), CAPDEC_ERR_UNSUPPORTED, "GPT-2 decoder consumes pooled_features only (decoders.py:629-637)");
+  CAPDEC_REQUIRE(B >= 0 && L >= 1, CAPDEC_ERR_INVALID, "bad sizes B=%d L=%d", B, L);
+  const TileSet t = tiles_layout(h, tiles, B, L);
+  CAPDEC_REQUIRE(B == 0 || (tiles != nullptr && tiles_bytes >= t.bytes && (((uintptr_t)tiles) & 255) == 0), CAPDEC_ERR_WORKSPACE,
+                 "tile buffer too small or not 256-byte aligned: need %zu bytes, got %zu", t.bytes, tiles_bytes);
+  IngestArgs a{};
+  a.src = src; a.layout = layout; a.dtype = dtype; a.B = B; a.L = L; a.D = h->cfg.feature_dim;
+  if (t.p24) { a.split = SplitDst{t.hi, t.lo, h->cfg.feature_dim, KIND_BF16, t.b8}; a.mean = t.mean; }
+  else a.out_f32 = t.f32;
+  StageScope sc(h, STAGE_PROLOGUE, (cudaStream_t)stream);
+  return ingest_features(a, (cudaStream_t)stream);
+}
+
+int capdec_decode_beam_tiles(capdec_handle* h, const void* tiles, const float* pooled, const uint8_t* mask, int32_t B, int32_t L,
+                             int32_t k, int32_t T, float length_penalty, int32_t* out_tok, int32_t* out_len, float* out_score,
+                             float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, void* ws, size_t ws_bytes, void* stream) {
+  CAPDEC_REQUIRE(h != nullptr && h->finalized, CAPDEC_ERR_STATE, "capdec_decode_beam_tiles: handle not finalized");
+  CAPDEC_REQUIRE(B == 0 || tiles != nullptr, CAPDEC_ERR_INVALID, "tiles pointer is null");
+  const TileSet t = tiles_layout(h, const_cast<void*>(tiles), B, L);
+  if (!t.p24)
+    return decode_beam_impl(h, t.f32, nullptr, pooled, mask, B, L, k, T, length_penalty, out_tok, out_len, out_score, dbg_lp,
+                            dbg_tok, dbg_beam, ws, ws_bytes, stream);
+  return decode_beam_impl(h, nullptr, &t, pooled, mask, B, L, k, T, length_penalty, out_tok, out_len, out_score, dbg_lp, dbg_tok,
+                          dbg_beam, ws, ws_bytes, stream);
+}
+
+int capdec_pack_p24_host(const float* src, int64_t num_images, int64_t elems, void* dst) {
+  CAPDEC_REQUIRE(src && dst && num_images >= 0 && elems >= 0, CAPDEC_ERR_INVALID, "capdec_pack_p24_host: bad argument");
+  for (int64_t b = 0; b < num_images; ++b) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(src) + b * elems;
+    uint16_t* hi = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(dst) + b * elems * 3);
+    uint8_t* q = reinterpret_cast<uint8_t*>(hi + elems);
+    for (int64_t i = 0; i < elems; ++i) {
+      const uint32_t bits = in[i];
+      hi[i] = (uint16_t)(bits >> 16);
+      q[i] = (uint8_t)((((bits & 0xffffu) + 128u) * 65281u) >> 24);   // == p24_q_ in common.cuh
+    }
+  }
+  return CAPDEC_OK;
+}
+
+int capdec_trim_at_eos(const int32_t* tok, int64_t ld, int32_t rows, int32_t T, int32_t eos, int32_t pad, int32_t keep_eos,
+                       int32_t* out, int64_t ld_out, int32_t* out_len, void* stream) {
+  CAPDEC_REQUIRE(tok && rows >= 0 && T >= 1 && (out || out_len), CAPDEC_ERR_INVALID, "capdec_trim_at_eos: bad argument");
+  return trim_at_eos(tok, ld, rows, T, eos, pad, keep_eos, out, ld_out, out_len, (cudaStream_t)stream);
+}
+
+int capdec_forward_tokens(capdec_handle* h, const float* feats, const float* pooled, const uint8_t* mask, int32_t B, int32_t L,
+                          int32_t k, const int32_t* tokens, int32_t tok_stride, int32_t n_tok, float* logits_out,
+                          float* logprob_out, float* alpha_out, int32_t mask_pad_keys, void* ws, size_t ws_bytes, void* stream) {
+  const int T = n_tok + 1;   // cache / workspace sized like a decode of n_tok generated positions
+  CAPDEC_RETURN_IF(check_common(h, feats, pooled, B, L, k, T));
+  CAPDEC_REQUIRE(tokens && n_tok >= 1 && tok_stride >= n_tok, CAPDEC_ERR_INVALID, "capdec_forward_tokens: bad token block");
+  CAPDEC_REQUIRE(is_legacy(h) || is_gpt2(h) ? mask == nullptr : true, CAPDEC_ERR_UNSUPPORTED, "this decoder takes no region padding mask");
+  CAPDEC_REQUIRE(!alpha_out || !is_tf_family(h), CAPDEC_ERR_UNSUPPORTED,
+                 "attention weights are not exposed by the transformer decoders (decoders.py:435)");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Session S;
+  carve(h, ar, S, B, L, k, T, MODE_SAMPLE);
+  CAPDEC_REQUIRE(ws != nullptr && ar.ok(), CAPDEC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ar.off, ws_bytes);
+  if (B == 0) return CAPDEC_OK;
+  const capdec_config& c = h->cfg;
+  const int V = c.vocab_size;
+  if (mask_pad_keys && is_tf_family(h)) { S.key_tok = tokens; S.ld_key_tok = tok_stride; S.key_pad = c.pad_token_id; }
+  CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
+  float* const logits_buf = S.logits;
+  const bool direct = logits_out != nullptr && V % 4 == 0;   // step t's GEMM writes straight into logits_out[:, t, :]
+  for (int t = 0; t < n_tok; ++t) {
+    CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(S.next_tok, sizeof(int32_t), tokens + t, (size_t)tok_stride * sizeof(int32_t),
+                                        sizeof(int32_t), S.R, cudaMemcpyDeviceToDevice, s));
+    CAPDEC_RETURN_IF(commit(h, S, nullptr, nullptr, 0, -1, t > 0, s));
+    if (direct) { S.logits = logits_out + (size_t)t * V; S.logits_ld = (int64_t)n_tok * V; }
+    else        { S.logits = logits_buf; S.logits_ld = 0; }
+    CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha_out ? alpha_out + (size_t)t * L : nullptr, (int64_t)n_tok * L, t, s));
+    const int64_t ld = S.logits_ld ? S.logits_ld : V;
+    if (logits_out && !direct)
+      CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(logits_out + (size_t)t * V, (size_t)n_tok * V * sizeof(float), logits_buf,
+                                          (size_t)V * sizeof(float), (size_t)V * sizeof(float), S.R, cudaMemcpyDeviceToDevice, s));
+    if (logprob_out && t + 1 < n_tok) {
+      StageScope sc(h, STAGE_SELECT, s);
+      CAPDEC_RETURN_IF(token_logprob(S.logits, ld, S.R, V, tokens + t + 1, tok_stride, logprob_out + t, n_tok - 1, s));
+    }
+  }
   return CAPDEC_OK;
 }
 
@@ -1252,53 +1429,33 @@ int capdec_attention_forward(capdec_handle* h, const float* query, const float* 
   return run_attention(h, S, feats, mask, query, H, memory, H, cell, H, B, context, weights, L, s);
 }
 
-int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const float* pooled_host, int32_t B, int32_t L,
-                            int32_t k, int32_t T, float length_penalty, int32_t chunk, int32_t* out_tok_host,
-                            int32_t* out_len_host, float* out_score_host) {
+static int decode_beam_host_impl(capdec_handle* h, const void* feats_host, int layout, int dtype, const float* pooled_host,
+                                 const uint8_t* mask_host, int32_t B, int32_t L, int32_t k, int32_t T, float length_penalty,
+                                 int32_t chunk, int32_t* out_tok_host, int32_t* out_len_host, float* out_score_host) {
   CAPDEC_RETURN_IF(check_common(h, feats_host, pooled_host, B, L, k, T));
   CAPDEC_REQUIRE(out_tok_host && out_len_host && out_score_host, CAPDEC_ERR_INVALID, "output pointers must not be null");
+  CAPDEC_REQUIRE(layout >= CAPDEC_LAYOUT_BLD && layout <= CAPDEC_LAYOUT_CLS_BLD && dtype >= CAPDEC_DT_F32 && dtype <= CAPDEC_DT_P24,
+                 CAPDEC_ERR_INVALID, "unknown feature layout %d / dtype %d", layout, dtype);
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
   if (chunk <= 0) {
     // default: two images per SM -- whole rounds of the persistent attention kernel and about one wave of gate-GEMM tiles
     // per step, which measured best on B200 (126 ms vs 129 ms at 512 for 4096 images; the copy alone is 118.5 ms)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    chunk = 2 * (sms > 0 ? sms : 148);
+    chunk = 2 * num_sms();
   }
   if (chunk > B) chunk = B;
-  const size_t feat_chunk = align_up((size_t)chunk * L * c.feature_dim * sizeof(float), 256);
-  const size_t pool_chunk = align_up((size_t)chunk * c.hidden_dim * sizeof(float), 256);
-  const size_t ws_bytes = capdec_workspace_bytes(h, chunk, L, k, T);
-  const size_t out_bytes = align_up((size_t)B * T * 4, 256) + 2 * align_up((size_t)B * 4, 256);
-  const size_t total = kHostBufs * (feat_chunk + pool_chunk) + ws_bytes + out_bytes;
-  if (h->stage_bytes < total) {
-    if (h->stage_dev) CAPDEC_CHECK_CUDA(cudaFree(h->stage_dev));
-    h->stage_dev = nullptr; h->stage_bytes = 0;
-    CAPDEC_CHECK_CUDA(cudaMalloc(&h->stage_dev, total));
-    h->stage_bytes = total;
-  }
-  if (!h->stream_compute) {
-    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_compute, cudaStreamNonBlocking));
-    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
-    for (int i = 0; i < kHostBufs; ++i) {
-      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
-      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
-  }
-  char* base = (char*)h->stage_dev;
-  float* d_feat[kHostBufs];
-  float* d_pool[kHostBufs];
-  for (int i = 0; i < kHostBufs; ++i) {
-    d_feat[i] = (float*)(base + (size_t)i * feat_chunk);
-    d_pool[i] = (float*)(base + (size_t)kHostBufs * feat_chunk + (size_t)i * pool_chunk);
-  }
-  void* d_ws = base + (size_t)kHostBufs * (feat_chunk + pool_chunk);
-  int32_t* d_tok = (int32_t*)((char*)d_ws + ws_bytes);
-  int32_t* d_len = (int32_t*)((char*)d_tok + align_up((size_t)B * T * 4, 256));
-  float* d_score = (float*)((char*)d_len + align_up((size_t)B * 4, 256));
-  const size_t img_floats = (size_t)L * c.feature_dim;
+  // One in-flight call per handle: the GEMM activation scratch and the lazily split weights are handle state, and this
+  // call runs on private streams that have no ordering with the caller's.  Draining the device first makes a preceding
+  // asynchronous decode on the caller's stream safe (the call is synchronous by contract anyway).
+  CAPDEC_CHECK_CUDA(cudaDeviceSynchronize());
+  const bool have_feats = feats_host != nullptr;
+  const bool direct = layout == CAPDEC_LAYOUT_BLD && dtype == CAPDEC_DT_F32 && !tiles_p24(h);   // decode straight from the staged chunk
+  const size_t img_src = have_feats ? ingest_source_image_bytes(layout, dtype, L, c.feature_dim) : 0;
+  const int pooled_w = is_gpt2(h) ? c.feature_dim : c.hidden_dim;
+  const size_t feat_chunk = align_up((size_t)chunk * img_src + 16, 256);
+  const size_t pool_chunk = align_up((size_t)chunk * pooled_w * sizeof(float), 256);
+  const size_t mask_chunk = mask_host ? align_up((size_t)chunk * L, 256) : 0;
+  const size_t tiles_bytes = (have_feats && !direct) ? tiles_layout(h, nullptr, chunk, L).bytes : 0;
   // Chunk schedule: the copy engine runs back to back from t = 0, so the call ends one chunk-decode after the last
   // byte lands (and starts decoding one chunk-copy after the first).  Ramp the chunk size up from chunk/8 at the start
   // and down to chunk/8 at the end so both exposed pieces are small; full-size chunks in between keep the GEMMs efficient.
@@ -1316,28 +1473,106 @@ int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const flo
     while (left > 0) { const int n = left < chunk ? left : chunk; sizes.push_back(n); left -= n; }
     for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
   }
-  int idx = 0, b0 = 0;
-  for (size_t ci = 0; ci < sizes.size(); b0 += sizes[ci], ++ci, ++idx) {
-    const int nb = sizes[ci];
-    const int buf = idx % kHostBufs;   // three staging buffers: the copy engine never waits on the decode of the previous chunk
-    if (idx >= kHostBufs) CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_done[buf], 0));
-    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_feat[buf], feats_host + (size_t)b0 * img_floats, (size_t)nb * img_floats * sizeof(float),
-                                      cudaMemcpyHostToDevice, h->stream_copy));
-    if (pooled_host)
-      CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_pool[buf], pooled_host + (size_t)b0 * c.hidden_dim,
-                                        (size_t)nb * c.hidden_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream_copy));
-    CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_copied[buf], h->stream_copy));
-    CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_compute, h->ev_copied[buf], 0));
-    CAPDEC_RETURN_IF(capdec_decode_beam(h, d_feat[buf], pooled_host ? d_pool[buf] : nullptr, nullptr, nb, L, k, T,
-                                        length_penalty, d_tok + (size_t)b0 * T, d_len + b0, d_score + b0, nullptr,
-                                        nullptr, nullptr, d_ws, ws_bytes, h->stream_compute));
-    CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_done[buf], h->stream_compute));
+  // the fused top-k record count is not monotone in the row count, so size the shared workspace for every chunk size used
+  size_t ws_bytes = 0;
+  {
+    std::vector<int> seen;
+    for (int n : sizes) {
+      bool dup = false;
+      for (int m : seen) dup = dup || m == n;
+      if (dup) continue;
+      seen.push_back(n);
+      const size_t w = capdec_workspace_bytes(h, n, L, k, T);
+      ws_bytes = w > ws_bytes ? w : ws_bytes;
+    }
   }
-  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_tok_host, d_tok, (size_t)B * T * 4, cudaMemcpyDeviceToHost, h->stream_compute));
-  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
-  CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_score_host, d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
-  CAPDEC_CHECK_CUDA(cudaStreamSynchronize(h->stream_compute));
+  const size_t out_bytes = align_up((size_t)B * T * 4, 256) + 2 * align_up((size_t)B * 4, 256);
+  const size_t total = kHostBufs * (feat_chunk + pool_chunk + mask_chunk) + tiles_bytes + ws_bytes + out_bytes;
+  if (h->stage_bytes < total) {
+    if (h->stage_dev) CAPDEC_CHECK_CUDA(cudaFree(h->stage_dev));
+    h->stage_dev = nullptr; h->stage_bytes = 0;
+    CAPDEC_CHECK_CUDA(cudaMalloc(&h->stage_dev, total));
+    h->stage_bytes = total;
+  }
+  if (!h->stream_compute) {
+    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_compute, cudaStreamNonBlocking));
+    CAPDEC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostBufs; ++i) {
+      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CAPDEC_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  char* base = (char*)h->stage_dev;
+  char* d_feat[kHostBufs];
+  float* d_pool[kHostBufs];
+  uint8_t* d_mask[kHostBufs];
+  for (int i = 0; i < kHostBufs; ++i) {
+    d_feat[i] = base + (size_t)i * feat_chunk;
+    d_pool[i] = (float*)(base + (size_t)kHostBufs * feat_chunk + (size_t)i * pool_chunk);
+    d_mask[i] = (uint8_t*)(base + (size_t)kHostBufs * (feat_chunk + pool_chunk) + (size_t)i * mask_chunk);
+  }
+  char* d_tiles = base + (size_t)kHostBufs * (feat_chunk + pool_chunk + mask_chunk);
+  void* d_ws = d_tiles + tiles_bytes;
+  int32_t* d_tok = (int32_t*)((char*)d_ws + ws_bytes);
+  int32_t* d_len = (int32_t*)((char*)d_tok + align_up((size_t)B * T * 4, 256));
+  float* d_score = (float*)((char*)d_len + align_up((size_t)B * 4, 256));
+  auto run = [&]() -> int {
+    int idx = 0, b0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); b0 += sizes[ci], ++ci, ++idx) {
+      const int nb = sizes[ci];
+      const int buf = idx % kHostBufs;   // three staging buffers: the copy engine never waits on the decode of the previous chunk
+      if (idx >= kHostBufs) CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_done[buf], 0));
+      if (have_feats)
+        CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_feat[buf], (const char*)feats_host + (size_t)b0 * img_src, (size_t)nb * img_src,
+                                          cudaMemcpyHostToDevice, h->stream_copy));
+      if (pooled_host)
+        CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_pool[buf], pooled_host + (size_t)b0 * pooled_w, (size_t)nb * pooled_w * sizeof(float),
+                                          cudaMemcpyHostToDevice, h->stream_copy));
+      if (mask_host)
+        CAPDEC_CHECK_CUDA(cudaMemcpyAsync(d_mask[buf], mask_host + (size_t)b0 * L, (size_t)nb * L, cudaMemcpyHostToDevice, h->stream_copy));
+      CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_copied[buf], h->stream_copy));
+      CAPDEC_CHECK_CUDA(cudaStreamWaitEvent(h->stream_compute, h->ev_copied[buf], 0));
+      const float* pool = pooled_host ? d_pool[buf] : nullptr;
+      const uint8_t* msk = mask_host ? d_mask[buf] : nullptr;
+      if (have_feats && !direct) {
+        // hand-off pass on the device: the chunk arrives in the encoder's format and leaves as the tiles the decode streams
+        CAPDEC_RETURN_IF(capdec_ingest_features(h, d_feat[buf], layout, dtype, nb, L, d_tiles, tiles_bytes, h->stream_compute));
+        CAPDEC_RETURN_IF(capdec_decode_beam_tiles(h, d_tiles, pool, msk, nb, L, k, T, length_penalty, d_tok + (size_t)b0 * T,
+                                                  d_len + b0, d_score + b0, nullptr, nullptr, nullptr, d_ws, ws_bytes, h->stream_compute));
+      } else {
+        CAPDEC_RETURN_IF(capdec_decode_beam(h, have_feats ? (const float*)d_feat[buf] : (const float*)d_feat[0], pool, msk, nb, L, k, T,
+                                            length_penalty, d_tok + (size_t)b0 * T, d_len + b0, d_score + b0, nullptr, nullptr,
+                                            nullptr, d_ws, ws_bytes, h->stream_compute));
+      }
+      CAPDEC_CHECK_CUDA(cudaEventRecord(h->ev_done[buf], h->stream_compute));
+    }
+    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_tok_host, d_tok, (size_t)B * T * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_len_host, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+    CAPDEC_CHECK_CUDA(cudaMemcpyAsync(out_score_host, d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream_compute));
+    return CAPDEC_OK;
+  };
+  const int st = run();
+  // success or failure, nothing of this call is left in flight: copies from caller memory included
+  const cudaError_t e1 = cudaStreamSynchronize(h->stream_copy);
+  const cudaError_t e2 = cudaStreamSynchronize(h->stream_compute);
+  CAPDEC_RETURN_IF(st);
+  CAPDEC_CHECK_CUDA(e1);
+  CAPDEC_CHECK_CUDA(e2);
   return CAPDEC_OK;
+}
+
+int capdec_decode_beam_host(capdec_handle* h, const float* feats_host, const float* pooled_host, int32_t B, int32_t L,
+                            int32_t k, int32_t T, float length_penalty, int32_t chunk, int32_t* out_tok_host,
+                            int32_t* out_len_host, float* out_score_host) {
+  return decode_beam_host_impl(h, feats_host, CAPDEC_LAYOUT_BLD, CAPDEC_DT_F32, pooled_host, nullptr, B, L, k, T, length_penalty,
+                               chunk, out_tok_host, out_len_host, out_score_host);
+}
+
+int capdec_decode_beam_host_ex(capdec_handle* h, const void* feats_host, int32_t layout, int32_t dtype, const float* pooled_host,
+                               const uint8_t* mask_host, int32_t B, int32_t L, int32_t k, int32_t T, float length_penalty,
+                               int32_t chunk, int32_t* out_tok_host, int32_t* out_len_host, float* out_score_host) {
+  return decode_beam_host_impl(h, feats_host, layout, dtype, pooled_host, mask_host, B, L, k, T, length_penalty, chunk,
+                               out_tok_host, out_len_host, out_score_host);
 }
 
 int capdec_stage_timing(capdec_handle* h, int32_t enable) {

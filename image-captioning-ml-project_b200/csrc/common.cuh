@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/capdec.h"
@@ -14,7 +15,7 @@ namespace capdec {
 
 // ---- error plumbing ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;   // atomic: handles on different host threads launch concurrently
 
 #define CAPDEC_CHECK_CUDA(expr)                                                          \
   do {                                                                                   \
@@ -51,6 +52,16 @@ extern int64_t g_launch_count;
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Per-device caches: one process may drive several GPUs (Engine(device=...)), and SM counts, occupancy answers and
+// cudaFuncSetAttribute state belong to a device, not to the process.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+int num_sms();   // SM count of the current device (capdec.cu)
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- programmatic dependent launch ------------------------------------------------------------------------

@@ -634,24 +634,14 @@ int make_map(CUtensorMap* m, int kind, const void* base, int64_t rows, int64_t c
   return CAPDEC_OK;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 // CTA groups one launch may keep resident: every SM for single CTAs; for pairs, what the occupancy calculator grants
 // clusters of 2 (both SMs of a TPC).  All instantiations of a mode share thread count and shared-memory size, so one
 // representative kernel answers for all of them.  tk_records() (the EPI_TOPK record layout) depends on this number.
 int tc_max_groups(int cg) {
-  static int cache[3] = {0, 0, 0};
-  if (cache[cg]) return cache[cg];
-  if (cg == 1) return cache[1] = num_sms();
+  static std::atomic<int> cache_dev[kMaxDevices][3];
+  std::atomic<int>* cache = cache_dev[current_device()];
+  if (cache[cg].load()) return cache[cg].load();
+  if (cg == 1) { cache[1].store(num_sms()); return num_sms(); }
   auto kern = gemm_tcgen05_kernel<256, EPI_STORE, 3, 0, 2, KIND_TF32>;
   constexpr int smem = SmemLayout<256, 2>::kTotal;
   int n = 0;
@@ -667,7 +657,8 @@ int tc_max_groups(int cg) {
   cudaGetLastError();
   if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
   if (const char* e = getenv("CAPDEC_GEMM_MAX_GROUPS")) { const int c = atoi(e); if (c > 0 && c < n) n = c; }   // experiments: SM partitioning
-  return cache[2] = n;
+  cache[2].store(n);
+  return n;
 }
 int tc_cta_group(int M) {
   static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
@@ -682,10 +673,11 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   {                                                                                                               \
     auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                 \
     constexpr int smem = E == EPI_TOPK ? SmemLayout<BN, CG>::kTotalTopk : SmemLayout<BN, CG>::kTotal;             \
-    static bool configured = false;                                                                               \
-    if (!configured) {                                                                                            \
+    static std::atomic<bool> configured[kMaxDevices];   /* function attributes are per device */                 \
+    const int dev_ = current_device();                                                                            \
+    if (!configured[dev_].load()) {                                                                               \
       CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
-      configured = true;                                                                                          \
+      configured[dev_].store(true);                                                                               \
     }                                                                                                             \
     const int max_groups = tc_max_groups(CG);                                                                     \
     const int groups = num_tiles < max_groups ? num_tiles : max_groups;                                           \
@@ -795,9 +787,17 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
   if (h) {
     auto it = h->tc_weights.find(a.W);
     if (it == h->tc_weights.end()) {
+      // first use of this weight: split it once and keep the copies.  The split is COMPLETE before this call returns
+      // (stream sync), so a later call on another stream can never read half-written copies; inside a stream capture
+      // neither the allocation nor the sync is legal, so a captured loop must have been run once eagerly before.
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      CAPDEC_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
+      CAPDEC_REQUIRE(cap == cudaStreamCaptureStatusNone, CAPDEC_ERR_STATE,
+                     "gemm: weight operand copies are built on first use; run the call once outside stream capture first");
       float* buf = nullptr;
       CAPDEC_CHECK_CUDA(cudaMalloc((void**)&buf, 2 * w_bytes));
       CAPDEC_RETURN_IF(split_operand(kind, a.W, a.ldw, a.N, K, Kp, buf, terms == 3 ? (char*)buf + w_bytes : nullptr, s));
+      CAPDEC_CHECK_CUDA(cudaStreamSynchronize(s));
       h->tc_weights[a.W] = buf;
       it = h->tc_weights.find(a.W);
     }

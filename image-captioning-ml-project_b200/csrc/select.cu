@@ -2,6 +2,7 @@
 // bookkeeping, and the in-place index gathers that reorder decoder state by back-pointer.
 #include "select.cuh"
 #include "attention.cuh"
+#include "ingest.cuh"
 #include <limits.h>
 
 namespace capdec {
@@ -256,6 +257,39 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
   }
 }
 
+// lp[r] = logits[r, tok[r]] - logsumexp(logits[r, :])   (log-prob of a GIVEN token: re-scoring of sampled captions,
+// src/train/trainer.py:423-428 without the draw).  One CTA per row, two passes over the row (it sits in L2).
+__global__ void __launch_bounds__(kThreads) token_logprob_kernel(const float* __restrict__ logits, int64_t ld, int V,
+                                                                 const int32_t* __restrict__ tok, int64_t ld_tok,
+                                                                 float* __restrict__ out_lp, int64_t ld_out) {
+  __shared__ float s_tmp[kThreads / 32];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (int64_t)r * ld;
+  float bv = -INFINITY;
+  for (int i = tid; i < V; i += kThreads) bv = fmaxf(bv, x[i]);
+  const float M = block_max(bv, s_tmp);
+  float sum = 0.f;
+  for (int i = tid; i < V; i += kThreads) sum += expf(x[i] - M);
+  const float S = block_sum(sum, s_tmp);
+  if (tid == 0) {
+    const int t = tok[(int64_t)r * ld_tok];
+    out_lp[(int64_t)r * ld_out] = (t >= 0 && t < V) ? (x[t] - M) - logf(S) : -INFINITY;
+  }
+}
+
+// everything after a row's first EOS becomes pad; length = tokens kept.  One thread per row (T is 20-50).
+__global__ void trim_at_eos_kernel(const int32_t* __restrict__ tok, int64_t ld, int rows, int T, int eos, int pad, int keep_eos,
+                                   int32_t* __restrict__ out, int64_t ld_out, int32_t* __restrict__ out_len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int len = T;
+  for (int t = 0; t < T; ++t)
+    if (tok[(int64_t)r * ld + t] == eos) { len = min(T, t + (keep_eos ? 1 : 0)); break; }
+  if (out)
+    for (int t = 0; t < T; ++t) out[(int64_t)r * ld_out + t] = t < len ? tok[(int64_t)r * ld + t] : pad;
+  if (out_len) out_len[r] = len;
+}
+
 // ---- beam bookkeeping: one thread per image -------------------------------------------------------
 __global__ void beam_init_kernel(BeamState st, int B, int k, int T, int bos, int fill) {
   const int img = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,32 +539,6 @@ __global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restri
   reinterpret_cast<float4*>(out + (int64_t)b * D)[c] = make_float4(acc.x / fl, acc.y / fl, acc.z / fl, acc.w / fl);
 }
 
-// mean over regions fused with the operand split of the same tile: one pass over feats [B,L,D] produces the region mean
-// (h0 / c0 input, models/decoder.py:137) AND the hi/lo copies the hoisted enc_att GEMM (and, in the bf16 mode, the
-// attention kernel) read, instead of one pass for the mean and another for the split
-__global__ void __launch_bounds__(256) mean_split_kernel(const float* __restrict__ feats, int L, int D,
-                                                         float* __restrict__ out, const SplitDst split) {
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
-  if (c >= D / 4) return;
-  const float4* p = reinterpret_cast<const float4*>(feats + (int64_t)b * L * D) + c;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int l0 = 0; l0 < L; l0 += 4) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ldg_stream(p + (int64_t)min(l0 + u, L - 1) * (D / 4));
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (l0 + u < L) {
-        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-        split_store4(split, (int64_t)b * L + l0 + u, c * 4, v[u]);
-      }
-    }
-  }
-  const float fl = (float)L;
-  reinterpret_cast<float4*>(out + (int64_t)b * D)[c] = make_float4(acc.x / fl, acc.y / fl, acc.z / fl, acc.w / fl);
-}
-
 __global__ void __launch_bounds__(128) expand_rows_kernel(const float* __restrict__ src, int64_t ld_src,
                                                           float* __restrict__ dst, int64_t ld_dst, int k, int width) {
   const int r = blockIdx.x;
@@ -587,6 +595,22 @@ int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const floa
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sample_kernel<<<rows, kThreads, smem, s>>>(logits, ld, vocab, uniforms, ld_u, step, rows_per_image, greedy_slot,
                                              out_tok, out_lp);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int token_logprob(const float* logits, int64_t ld, int rows, int vocab, const int32_t* tok, int64_t ld_tok, float* out_lp,
+                  int64_t ld_out, cudaStream_t s) {
+  if (rows == 0) return CAPDEC_OK;
+  token_logprob_kernel<<<rows, kThreads, 0, s>>>(logits, ld, vocab, tok, ld_tok, out_lp, ld_out);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int trim_at_eos(const int32_t* tok, int64_t ld, int rows, int T, int eos, int pad, int keep_eos, int32_t* out, int64_t ld_out,
+                int32_t* out_len, cudaStream_t s) {
+  if (rows == 0) return CAPDEC_OK;
+  trim_at_eos_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(tok, ld, rows, T, eos, pad, keep_eos, out, ld_out, out_len);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -653,12 +677,11 @@ int mean_regions(const float* feats, int B, int L, int D, float* out, cudaStream
 }
 
 int mean_regions_split(const float* feats, int B, int L, int D, float* out, const SplitDst& split, cudaStream_t s) {
+  // the row-major fp32 case of the encoder hand-off pass (ingest.cu): region mean + operand copies in one read of feats
   CAPDEC_REQUIRE(D % 8 == 0 && split.ld % 8 == 0, CAPDEC_ERR_UNSUPPORTED, "mean_regions_split: D must be a multiple of 8");
-  if (B == 0) return CAPDEC_OK;
-  dim3 grid(ceil_div(D / 4, 256), B);
-  mean_split_kernel<<<grid, 256, 0, s>>>(feats, L, D, out, split);
-  CAPDEC_LAUNCH_CHECK();
-  return CAPDEC_OK;
+  IngestArgs a{};
+  a.src = feats; a.layout = CAPDEC_LAYOUT_BLD; a.dtype = CAPDEC_DT_F32; a.B = B; a.L = L; a.D = D; a.split = split; a.mean = out;
+  return ingest_features(a, s);
 }
 
 int expand_rows(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int k, int width, cudaStream_t s) {

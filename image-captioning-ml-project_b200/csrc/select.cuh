@@ -21,6 +21,13 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
 int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const float* uniforms, int64_t ld_u, int step,
                 int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s);
 
+// out_lp[r*ld_out] = log_softmax(logits[r,:])[tok[r*ld_tok]]
+int token_logprob(const float* logits, int64_t ld, int rows, int vocab, const int32_t* tok, int64_t ld_tok, float* out_lp,
+                  int64_t ld_out, cudaStream_t s);
+// pad everything after the first EOS of each row; out_len = tokens kept (out / out_len may be nullptr)
+int trim_at_eos(const int32_t* tok, int64_t ld, int rows, int T, int eos, int pad, int keep_eos, int32_t* out, int64_t ld_out,
+                int32_t* out_len, cudaStream_t s);
+
 struct BeamState {          // all device pointers; [B,k,...] row-major
   int32_t* run_seq[2];      // [B,k,T] ping-pong
   int32_t* fin_seq[2];      // [B,k,T] ping-pong

@@ -122,6 +122,7 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
       if (e < d) dot = fmaf(q[j], kp[hd * d + e], dot);
     }
     dot = warp_sum(dot) * a.scale;
+    if (a.key_tok && p >= a.n_prefix && a.key_tok[(int64_t)r * a.ld_key_tok + (p - a.n_prefix)] == a.key_pad) continue;   // masked key
     const float m_new = fmaxf(m, dot);
     const float corr = expf(m - m_new);       // exp(-inf) = 0 on the first key
     const float w = expf(dot - m_new);
@@ -228,6 +229,8 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   for (int i = 0; i < NK; ++i) {
     const int p = lane + 32 * i;
     sc[i] = p < n_keys ? my_sc[p] : -INFINITY;
+    if (a.key_tok && p < n_keys && p >= a.n_prefix && a.key_tok[(int64_t)r * a.ld_key_tok + (p - a.n_prefix)] == a.key_pad)
+      sc[i] = -INFINITY;   // masked key: weight exactly 0, as the reference's -inf additive mask
   }
   // ---- softmax across the lanes
   float m = sc[0];

@@ -14,6 +14,9 @@ struct SelfAttnArgs {
   float* out; int64_t ld_out;           // [R, H]
   SplitDst out_split;                   // optional: out also as the split operand of the projection GEMM that follows
   int rows, H, heads, T, t;
+  // optional (teacher-forced pass): cache position p of row r is masked as a KEY when key_tok[r*ld_key_tok + p] == key_pad
+  // (nn.TransformerDecoder tgt_key_padding_mask, decoders.py:405; HF attention_mask, decoders.py:581)
+  const int32_t* key_tok; int64_t ld_key_tok; int key_pad;
 };
 
 int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s,

@@ -10,7 +10,11 @@ select the decode entry points the north star adds on the same step kernels:
     do_sample=True         ancestral sampling rollout (trainer.py:383-438): num_samples rows per image
                            (+ with_greedy=True for the SCST baseline row), uniforms=... to fix the draws
 
-The teacher-forced `forward(captions=...)` is the training path (out of scope per SURVEY.md section 8) and raises.
+`forward(encoder_features, captions=ids)` is the teacher-forced pass as ONE batched call of the step kernels with
+forced tokens; it returns {"logits": [B,t,V], ...} like the reference, so CaptioningTrainer._sample_captions
+(src/train/trainer.py:413-420) runs unmodified on these classes.  It is inference-only: no autograd graph is built and
+dropout is the identity (the REINFORCE gradient stays with the PyTorch module); `score_tokens`
+returns the per-token log-probs of given captions in the same single pass (trainer.py:366-378's sample_logprobs).
 """
 from __future__ import annotations
 
@@ -23,10 +27,10 @@ import torch.nn as nn
 from . import _capi
 from .attention import build_attention
 from .config import AttentionConfig, DecoderConfig, DecoderType, attention_kind, decoder_kind
-from .engine import Engine
+from .engine import Engine, EngineOwner, Tiles
 
 
-class CaptionDecoder(nn.Module, ABC):
+class CaptionDecoder(EngineOwner, nn.Module, ABC):
     """Base class for all caption decoders (decoders.py:20-69)."""
 
     @abstractmethod
@@ -36,6 +40,14 @@ class CaptionDecoder(nn.Module, ABC):
     @abstractmethod
     def generate(self, encoder_features, max_length: int, **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
         ...
+
+
+def _reject_unknown(kwargs, where):
+    """The reference forwards **kwargs to the generation backend (decoders.py:640-650).  Anything this path does not
+    implement must fail loudly instead of silently decoding with defaults."""
+    if kwargs:
+        raise TypeError(f"{where}: unsupported generation argument(s) {sorted(kwargs)}; supported: num_beams, "
+                        "length_penalty, do_sample, num_samples, with_greedy, uniforms, trace, return_scores")
 
 
 def _padding_mask(encoder_features):
@@ -92,21 +104,37 @@ class LSTMDecoder(CaptionDecoder):
         return self._eng
 
     def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
-        """decoders.py:137-234.  Only the inference branch (captions is None) is on the decode path."""
+        """decoders.py:137-234: teacher forcing, step t consumes captions[:, t] and the previous context; logits[:, t] =
+        output_layer(context_t).  `caption_lengths` is ignored: the reference sorts captions and features by it but
+        takes h0 / c0 from the unsorted pooled features (:157-171), pairing rows with another image's initial state;
+        its only caller on this path, _sample_captions, passes None."""
         if captions is None:
             return self.generate(encoder_features, self.max_length)   # reference hits a NameError here (:148)
-        raise NotImplementedError(
-            "teacher-forced training forward is outside the accelerated decode path (SURVEY.md section 8: the trainer is "
-            "out of scope); train with the reference module and load its state_dict here for decoding. "
-            "For the SCST rollout (trainer.py:383-438) call generate(..., do_sample=True).")
+        feats = encoder_features["features"]
+        eng = self._engine(feats.device)
+        logits, _, alpha = eng.forward_tokens(feats, encoder_features["pooled_features"], _padding_mask(encoder_features),
+                                              captions, want_alpha=True)
+        return {"logits": logits, "attention_weights": alpha}
+
+    def score_tokens(self, encoder_features, tokens, rows_per_image: int = 1) -> torch.Tensor:
+        """log p(tokens[:, t+1] | tokens[:, :t+1], image) for every t, one pass; tokens [B*rows_per_image, T]."""
+        feats = encoder_features["features"]
+        _, lp, _ = self._engine(feats.device).forward_tokens(feats, encoder_features["pooled_features"],
+                                                             _padding_mask(encoder_features), tokens, rows_per_image,
+                                                             want_logits=False, want_logprob=True)
+        return lp
 
     def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, start_token_id: int = 1,
                  num_beams: int = 1, do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
                  uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
-                 **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+                 return_scores: bool = True, **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        _reject_unknown(kwargs, "LSTMDecoder.generate")
         feats = encoder_features["features"]
         pooled = encoder_features["pooled_features"]
         mask = _padding_mask(encoder_features)
+        if (do_sample or num_beams > 1) and int(start_token_id) != int(self.bos_token_id):
+            raise ValueError(f"beam search / sampling start from bos_token_id={self.bos_token_id}; "
+                             f"start_token_id={start_token_id} is honoured by the greedy path only (decoders.py:240)")
         eng = self._engine(feats.device)
         if do_sample:
             B = feats.shape[0]
@@ -166,17 +194,34 @@ class TransformerDecoder(CaptionDecoder):
         return self._eng
 
     def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
+        """decoders.py:377-438: full-prefix teacher forcing under the causal mask == the KV-cached step applied to the
+        forced tokens position by position.  Pad tokens inside `captions` are masked as keys (tgt_key_padding_mask, :405);
+        an `attention_mask` (True = valid region) masks region keys with -1e9 as the reference intends (:393-398; as shipped
+        its [B,T,L] mask only has a valid shape for T == 1)."""
         if captions is None:
             return self.generate(encoder_features, 50)      # decoders.py:385-387
-        raise NotImplementedError(
-            "teacher-forced training forward is outside the accelerated decode path; for the SCST rollout "
-            "(trainer.py:383-438) call generate(..., do_sample=True)")
+        feats = encoder_features["features"]
+        if captions.shape[1] > self.position_encoding.num_embeddings:
+            raise IndexError("caption length exceeds the position_encoding table (index out of range in self)")
+        logits, _, _ = self._engine(feats.device).forward_tokens(feats, None, _padding_mask(encoder_features), captions)
+        return {"logits": logits}          # ("hidden_states" of the reference are internal to the fused step)
+
+    def score_tokens(self, encoder_features, tokens, rows_per_image: int = 1) -> torch.Tensor:
+        feats = encoder_features["features"]
+        _, lp, _ = self._engine(feats.device).forward_tokens(feats, None, _padding_mask(encoder_features), tokens,
+                                                             rows_per_image, want_logits=False, want_logprob=True)
+        return lp
 
     def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, num_beams: int = 1,
                  do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
                  uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
+                 return_scores: bool = True, memory_key_padding_mask: Optional[torch.Tensor] = None,
                  **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        """decoders.py:439-493.  The reference's generate never looks at encoder_features["attention_mask"]; padded
+        region sets (Q-Former / object-region encoders) pass `memory_key_padding_mask` [B,L] (True = padding) explicitly."""
+        _reject_unknown(kwargs, "TransformerDecoder.generate")
         feats = encoder_features["features"]
+        mkpm = memory_key_padding_mask
         if max_length > self.position_encoding.num_embeddings:
             raise IndexError("max_length exceeds the position_encoding table (index out of range in self)")
         eng = self._engine(feats.device)
@@ -185,18 +230,18 @@ class TransformerDecoder(CaptionDecoder):
             k = num_samples + (1 if with_greedy else 0)
             if uniforms is None:
                 uniforms = torch.rand(B * k, max_length - 1, device=feats.device)
-            tok, lp = eng.decode_sample(feats, None, None, num_samples, with_greedy, max_length, uniforms)
+            tok, lp = eng.decode_sample(feats, None, mkpm, num_samples, with_greedy, max_length, uniforms)
             tok = tok.long()
             n = _all_eos_cut(tok, self.eos_token_id)          # trainer.py:435 batch-wide break
             return tok[:, :n], {"log_probs": lp[:, : n - 1]}
         if num_beams > 1:
-            out = eng.decode_beam(feats, None, None, num_beams, max_length, length_penalty, trace=trace)
+            out = eng.decode_beam(feats, None, mkpm, num_beams, max_length, length_penalty, trace=trace)
             seq = out["tokens"].long()[:, : int(out["lengths"].max().item())]
             info = {"scores": out["scores"], "lengths": out["lengths"].long()}
             if trace:
                 info.update({k: out[k] for k in ("top_logprob", "top_token", "top_beam")})
             return seq, info
-        tok, _ = eng.decode_greedy(feats, None, None, max_length, self.bos_token_id, want_alpha=False)
+        tok, _ = eng.decode_greedy(feats, None, mkpm, max_length, self.bos_token_id, want_alpha=False)
         tok = tok.long()
         return tok[:, : _all_eos_cut(tok, self.eos_token_id)], {}
 
@@ -256,16 +301,43 @@ class GPT2Decoder(CaptionDecoder):
         return self._eng
 
     def forward(self, encoder_features, captions=None, caption_lengths=None, **kwargs):
+        """decoders.py:563-596 with the prefix bound as SURVEY section 8(c) pins it: logits of GPT2LMHeadModel over
+        `captions` behind the 10-token image prefix (past K == V of every layer), pad tokens masked as keys
+        (attention_mask = captions != pad, :581), and HF's shifted cross-entropy against labels = captions (:578,:589)."""
         if captions is None:
             return self.generate(encoder_features, 50)      # decoders.py:572-574
-        raise NotImplementedError(
-            "teacher-forced training forward is outside the accelerated decode path; for the SCST rollout "
-            "(trainer.py:383-438) call generate(..., do_sample=True)")
+        pooled = encoder_features["pooled_features"]
+        if self.prefix_length + captions.shape[1] > self.model.config.n_positions:
+            raise IndexError("prefix + caption length exceeds GPT-2 n_positions (index out of range in self)")
+        logits, lp, _ = self._engine(pooled.device).forward_tokens(None, pooled, None, captions, want_logprob=True)
+        out = {"logits": logits}
+        if lp.numel():
+            out["loss"] = -lp.mean()
+        return out
+
+    def score_tokens(self, encoder_features, tokens, rows_per_image: int = 1) -> torch.Tensor:
+        pooled = encoder_features["pooled_features"]
+        _, lp, _ = self._engine(pooled.device).forward_tokens(None, pooled, None, tokens, rows_per_image,
+                                                              want_logits=False, want_logprob=True)
+        return lp
+
+    # HF generate() arguments whose DEFAULT value is what this path implements; any other value, or any other argument,
+    # raises (the reference forwards **kwargs to transformers' generate, decoders.py:640-650)
+    _HF_DEFAULTS = {"early_stopping": False, "repetition_penalty": 1.0, "no_repeat_ngram_size": 0,
+                    "num_return_sequences": 1, "min_length": 0, "temperature": 1.0, "top_k": 50, "top_p": 1.0,
+                    "num_beam_groups": 1, "diversity_penalty": 0.0, "use_cache": True}
 
     def generate(self, encoder_features: Dict[str, torch.Tensor], max_length: int, num_beams: int = 4,
                  do_sample: bool = False, num_samples: int = 1, with_greedy: bool = False,
                  uniforms: Optional[torch.Tensor] = None, length_penalty: float = 1.0, trace: bool = False,
-                 **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+                 return_scores: bool = False, **kwargs) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        for key in list(kwargs):
+            if key in self._HF_DEFAULTS and kwargs[key] == self._HF_DEFAULTS[key]:
+                kwargs.pop(key)
+            elif key in self._HF_DEFAULTS:
+                raise NotImplementedError(f"GPT2Decoder.generate: {key}={kwargs[key]!r} is not implemented by the CUDA beam "
+                                          f"search (only the HF default {self._HF_DEFAULTS[key]!r})")
+        _reject_unknown(kwargs, "GPT2Decoder.generate")
         pooled = encoder_features["pooled_features"]
         B = pooled.shape[0]
         if self.prefix_length + max_length > self.model.config.n_positions:
@@ -283,7 +355,7 @@ class GPT2Decoder(CaptionDecoder):
         if num_beams > 1:
             out = eng.decode_beam(dummy, pooled, None, num_beams, max_length, length_penalty, trace=trace)
             seq = out["tokens"].long()[:, : int(out["lengths"].max().item())]
-            info = {"scores": out["scores"], "lengths": out["lengths"].long()} if trace or kwargs.get("return_scores") else {}
+            info = {"scores": out["scores"], "lengths": out["lengths"].long()} if trace or return_scores else {}
             if trace:
                 info.update({k: out[k] for k in ("top_logprob", "top_token", "top_beam")})
             return seq, info

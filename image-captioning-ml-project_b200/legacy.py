@@ -14,12 +14,13 @@ import torch
 from torch import nn
 
 from . import _capi
-from .engine import Engine
+from .engine import Engine, EngineOwner, Tiles
 
 PAD, START, END, UNK = 0, 1, 2, 3   # models/constants.py
 
 
-class Decoder(nn.Module):
+
+class Decoder(EngineOwner, nn.Module):
     def __init__(self, vocab_size, use_bert=False, device="cuda", precision: str = "fp32"):
         super().__init__()
         if use_bert:
@@ -60,7 +61,18 @@ class Decoder(nn.Module):
 
     @staticmethod
     def _regions(encoder_out):
+        if isinstance(encoder_out, Tiles):
+            return encoder_out
         return encoder_out.reshape(encoder_out.size(0), -1, encoder_out.size(-1))   # models/decoder.py:127
+
+    @torch.no_grad()
+    def ingest(self, trunk_out: torch.Tensor, layout: str = "nchw") -> Tiles:
+        """Encoder hand-off: the resnet trunk's [B,2048,14,14] output (models/encoder.py:13, BEFORE its permute; fp32 or the
+        bf16/fp16 of an autocast encoder) -> the tile set `beam_search` streams.  One device pass does the permute, the
+        region mean and the operand packing the decode prologue would otherwise redo from fp32 [B,14,14,2048]."""
+        if layout == "bld" and trunk_out.dim() == 4:
+            trunk_out = trunk_out.reshape(trunk_out.size(0), -1, trunk_out.size(-1))
+        return self._engine(trunk_out.device).ingest_features(trunk_out, layout)
 
     def forward(self, encoder_out, encoded_captions, caption_lengths):
         """models/decoder.py:120-176 (eval semantics: dropout is the identity)."""
@@ -71,11 +83,25 @@ class Decoder(nn.Module):
 
     @torch.no_grad()
     def beam_search(self, encoder_out, beam_size: int = 5, max_length: int = 20, length_penalty: float = 1.0,
-                    trace: bool = False):
+                    trace: bool = False, crop: bool = True):
+        """-> {"tokens" int32 [B,T], "lengths" int32 [B], "scores" float [B]} on the device (asynchronous), plus
+        "sequences" = the int64 [B, longest] HF-style view when `crop` (cropping needs max(lengths) on the host, i.e.
+        one synchronisation; batch pipelines pass crop=False and trim with `lengths`).  `encoder_out` is the encoder's
+        [B,14,14,2048] output or a tile set from `ingest`."""
         enc = self._regions(encoder_out)
         out = self._engine(enc.device).decode_beam(enc, None, None, beam_size, max_length, length_penalty, trace=trace)
-        out["sequences"] = out["tokens"].long()[:, : int(out["lengths"].max().item())]
+        if crop:
+            out["sequences"] = out["tokens"].long()[:, : int(out["lengths"].max().item())]
         return out
+
+    @torch.no_grad()
+    def score_tokens(self, encoder_out, tokens, rows_per_image: int = 1) -> torch.Tensor:
+        """log p(tokens[:, t+1] | tokens[:, :t+1], image), one teacher-forced pass (the SCST re-scoring of sampled
+        captions, src/train/trainer.py:366-378, on the legacy step models/decoder.py:148-173)."""
+        enc = self._regions(encoder_out)
+        _, lp, _ = self._engine(enc.device).forward_tokens(enc, None, None, tokens, rows_per_image, want_logits=False,
+                                                           want_logprob=True)
+        return lp
 
     @torch.no_grad()
     def greedy(self, encoder_out, max_length: int = 20, start_token_id: int = START):

@@ -12,7 +12,9 @@ to the host once per batch:
   decode_captions  `tokenizer.batch_decode` when the tokenizer has it, else the reference's per-caption `decode`
   coco_results / write_results_json   the reference's results format
 
-Host-side plumbing only: nothing here touches the CUDA library.
+Tokens that live on a CUDA device are trimmed by libcapdec's `capdec_trim_at_eos` kernel (one launch, no
+synchronisation); the torch formulation below it serves host tensors only.  Beam-search output needs no trimming at
+all: `capdec_decode_beam` already returns `lengths` and fills everything behind the EOS (pass `lengths=` through).
 """
 import json
 from typing import Iterable, List, Optional, Sequence, Tuple
@@ -30,6 +32,10 @@ def trim_at_eos(tokens: torch.Tensor, eos_token_id: int, pad_token_id: int = 0,
     tokenizer to hide them; trimming first makes the text independent of what follows the EOS.)"""
     if tokens.dim() != 2:
         raise ValueError(f"tokens must be [B,T], got {tuple(tokens.shape)}")
+    if tokens.is_cuda:
+        from .engine import trim_at_eos_device
+        out, lengths = trim_at_eos_device(tokens.to(torch.int32), eos_token_id, pad_token_id, keep_eos)
+        return out.to(tokens.dtype), lengths.to(torch.int64)
     B, T = tokens.shape
     is_eos = tokens == eos_token_id
     pos = torch.arange(T, device=tokens.device).expand(B, T)
@@ -54,13 +60,13 @@ def to_token_lists(tokens: torch.Tensor, lengths: Optional[torch.Tensor] = None,
 
 
 def decode_captions(tokens: torch.Tensor, tokenizer, eos_token_id: Optional[int] = None, pad_token_id: int = 0,
-                    skip_special_tokens: bool = True) -> List[str]:
+                    skip_special_tokens: bool = True, lengths: Optional[torch.Tensor] = None) -> List[str]:
     """The reference's `[tokenizer.decode(c, skip_special_tokens=True) for c in captions]` for a [B,T] block:
-    trimmed at EOS on the device, copied once, decoded with `batch_decode` when available."""
+    trimmed at EOS on the device, copied once, decoded with `batch_decode` when available.  `lengths` (beam search
+    returns them) skips the trimming pass."""
     if eos_token_id is None:
         eos_token_id = getattr(tokenizer, "eos_token_id", None)
-    lengths = None
-    if eos_token_id is not None:
+    if lengths is None and eos_token_id is not None:
         tokens, lengths = trim_at_eos(tokens, int(eos_token_id), pad_token_id)
     rows = to_token_lists(tokens, lengths)
     if hasattr(tokenizer, "batch_decode"):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CAPDEC_VERSION 100
+#define CAPDEC_VERSION 200
 
 typedef enum {
   CAPDEC_OK = 0,
@@ -161,6 +161,64 @@ int capdec_attention_forward(capdec_handle* h, const float* query_dev, const flo
                              int32_t rows_per_image, float* context_dev, float* weights_dev,
                              void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- teacher-forced pass over given tokens (SCST boundary) ------------------------------------------
+ * One batched pass of the decode step with FORCED tokens: position t consumes tokens[:, t] and produces the
+ * distribution of position t+1.  This is what the reference's `decoder(encoder_features, captions=ids)["logits"]`
+ * returns (src/models/decoders.py:137-234 LSTM, :377-438 transformer, :563-596 GPT-2) and what
+ * CaptioningTrainer._sample_captions calls once per generated token (src/train/trainer.py:413-420); with
+ * logprob_dev it is the single-pass re-scoring of sampled captions for the REINFORCE term (trainer.py:366-378).
+ * Inference only (no autograd graph).
+ *   tokens_dev int32 [R, tok_stride] with R = num_images * rows_per_image (rows of an image adjacent, sharing its tiles);
+ *   logits_dev float [R, num_tokens, V] or NULL;  logprob_dev float [R, num_tokens-1] or NULL:
+ *   logprob[r,t] = log_softmax(logits[r,t,:])[tokens[r,t+1]];  alpha_dev float [R, num_tokens, L] or NULL (LSTM / legacy);
+ *   mask_pad_keys != 0 (transformer / GPT-2): positions whose token == pad_token_id are masked as attention KEYS, the
+ *   reference's tgt_key_padding_mask (decoders.py:405) / attention_mask (decoders.py:581). */
+int capdec_forward_tokens(capdec_handle* h, const float* features_dev, const float* pooled_dev,
+                          const uint8_t* key_padding_mask_dev, int32_t num_images, int32_t num_regions,
+                          int32_t rows_per_image, const int32_t* tokens_dev, int32_t tok_stride, int32_t num_tokens,
+                          float* logits_dev, float* logprob_dev, float* alpha_dev, int32_t mask_pad_keys,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- token -> text boundary (src/train/trainer.py:546-547, src/evaluate/metrics.py:322-323) -----------
+ * Per row: everything after the first EOS becomes pad_token_id, out_lengths = tokens kept (the EOS included when
+ * keep_eos).  In place allowed (out_tokens_dev == tokens_dev).  Replaces the per-caption Python loop's implicit trimming. */
+int capdec_trim_at_eos(const int32_t* tokens_dev, int64_t ld, int32_t rows, int32_t max_length, int32_t eos_token_id,
+                       int32_t pad_token_id, int32_t keep_eos, int32_t* out_tokens_dev, int64_t ld_out,
+                       int32_t* out_lengths_dev, void* stream);
+
+/* ---- encoder -> decoder feature hand-off -----------------------------------------------------------------
+ * What the encoders emit (models/encoder.py:12-16 before its permute; src/models/encoders.py:118-137, :209-230 before
+ * the CLS drop) goes in ONE pass into the layout the decode kernels stream ("tiles"): the layout change
+ * (permute(0,2,3,1) / [:,1:,:]), the widening from bf16/fp16, the region mean (models/decoder.py:137) and -- legacy
+ * decoder in BF16X3 mode -- the p24 planes + the hoisted enc_att GEMM's lo operand are produced together, so the
+ * decode prologue no longer re-reads and re-packs fp32 features. */
+typedef enum {
+  CAPDEC_LAYOUT_BLD = 0,      /* [B, L, D] row-major (what the decoders take) */
+  CAPDEC_LAYOUT_BDL = 1,      /* [B, D, L]: NCHW feature map [B, D, h, w] with L = h*w (ResNet trunk output) */
+  CAPDEC_LAYOUT_CLS_BLD = 2   /* [B, 1+L, D]: ViT / CLIP last_hidden_state, token 0 (CLS) dropped */
+} capdec_layout;
+typedef enum {
+  CAPDEC_DT_F32 = 0,
+  CAPDEC_DT_BF16 = 1,
+  CAPDEC_DT_F16 = 2,
+  CAPDEC_DT_P24 = 3           /* BLD only: per image a uint16 [L,D] plane (top 16 bits of the fp32) followed by a uint8 [L,D]
+                                 plane (round(low16 / 257)): 3 bytes per element, 16 significant bits (csrc/common.cuh) */
+} capdec_dtype;
+size_t capdec_source_bytes(int32_t layout, int32_t dtype, int32_t num_images, int32_t num_regions, int32_t feature_dim);
+size_t capdec_tiles_bytes(const capdec_handle* h, int32_t num_images, int32_t num_regions);
+int capdec_ingest_features(capdec_handle* h, const void* src_dev, int32_t layout, int32_t dtype, int32_t num_images,
+                           int32_t num_regions, void* tiles_dev, size_t tiles_bytes, void* stream);
+/* capdec_decode_beam on a tile set written by capdec_ingest_features (same outputs, same results as decoding the
+ * fp32 [B,L,D] features the tiles were made from) */
+int capdec_decode_beam_tiles(capdec_handle* h, const void* tiles_dev, const float* pooled_dev,
+                             const uint8_t* key_padding_mask_dev, int32_t num_images, int32_t num_regions,
+                             int32_t num_beams, int32_t max_length, float length_penalty,
+                             int32_t* out_tokens_dev, int32_t* out_lengths_dev, float* out_scores_dev,
+                             float* dbg_top_logprob_dev, int32_t* dbg_top_token_dev, int32_t* dbg_top_beam_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+/* fp32 [L,D] features -> the CAPDEC_DT_P24 source format, on the HOST (for feature caches kept in host memory / on disk) */
+int capdec_pack_p24_host(const float* src, int64_t num_images, int64_t elems_per_image, void* dst);
+
 /* ---- host-buffer entry point (end-to-end path) ----------------------------------------------
  * Same as capdec_decode_beam but every buffer is HOST memory (pinned recommended): the call
  * allocates device staging on first use, streams the features host->device in image chunks
@@ -171,6 +229,15 @@ int capdec_decode_beam_host(capdec_handle* h, const float* features_host, const 
                             int32_t num_images, int32_t num_regions, int32_t num_beams,
                             int32_t max_length, float length_penalty, int32_t chunk_images,
                             int32_t* out_tokens_host, int32_t* out_lengths_host, float* out_scores_host);
+
+/* The same with the encoder hand-off formats above and an optional padding mask: features_host holds
+ * capdec_source_bytes(layout, dtype, B, L, D) bytes; every chunk is copied in its source format (2-3 bytes per
+ * element for bf16 / fp16 / p24 instead of 4) and ingested on the device.  key_padding_mask_host uint8 [B,L] or NULL. */
+int capdec_decode_beam_host_ex(capdec_handle* h, const void* features_host, int32_t layout, int32_t dtype,
+                               const float* pooled_host, const uint8_t* key_padding_mask_host,
+                               int32_t num_images, int32_t num_regions, int32_t num_beams,
+                               int32_t max_length, float length_penalty, int32_t chunk_images,
+                               int32_t* out_tokens_host, int32_t* out_lengths_host, float* out_scores_host);
 
 /* ---- per-stage device timing ---------------------------------------------------------------------
  * When enabled, every stage launch of subsequent decode calls is bracketed by a cudaEvent pair on the

@@ -95,6 +95,21 @@ def _make_config_module() -> types.ModuleType:
         bos_token_id: int = 1
         eos_token_id: int = 2
 
+    @dataclass
+    class TrainingConfig:          # src/config.py:61-90 (only constructed, never read by the hot path)
+        batch_size: int = 64
+        num_epochs: int = 30
+        learning_rate: float = 5e-5
+        use_rl: bool = False
+        rl_start_epoch: int = 20
+
+    @dataclass
+    class Config:                  # src/config.py:127-152
+        model: ModelConfig = field(default_factory=ModelConfig)
+        training: TrainingConfig = field(default_factory=TrainingConfig)
+        inference: InferenceConfig = field(default_factory=InferenceConfig)
+        device: str = "cpu"
+
     for k, v in dict(locals()).items():
         if k != "m":
             setattr(m, k, v)
@@ -143,3 +158,31 @@ def load_reference():
     ns = types.SimpleNamespace(config=config, attention=attention, decoders=decoders, legacy=legacy)
     _cached = ns
     return ns
+
+
+_cached_trainer = None
+
+
+def load_reference_trainer():
+    """The reference's trainer / facade modules, imported unmodified: CaptioningTrainer (src/train/trainer.py, for its
+    `_sample_captions` :383-438), QFormer (src/models/captioning_model.py:153-245) and ObjectRegionEncoder
+    (src/models/encoders.py:233-296)."""
+    global _cached_trainer
+    if _cached_trainer is not None:
+        return _cached_trainer
+    load_reference()
+    for name in ("train", "evaluate", "data"):
+        key = "src." + name
+        if key not in sys.modules:
+            pkg = types.ModuleType(key)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, "src", name)]
+            sys.modules[key] = pkg
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):      # metrics.py prints a warning when pycocoevalcap is absent
+        trainer = importlib.import_module("src.train.trainer")
+    cm = importlib.import_module("src.models.captioning_model")
+    enc = importlib.import_module("src.models.encoders")
+    _cached_trainer = types.SimpleNamespace(trainer=trainer, CaptioningTrainer=trainer.CaptioningTrainer, QFormer=cm.QFormer,
+                                            ObjectRegionEncoder=enc.ObjectRegionEncoder, captioning_model=cm, encoders=enc)
+    return _cached_trainer

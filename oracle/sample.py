@@ -12,6 +12,10 @@ to the nearest CDF edge so tests can excuse boundary cases explicitly.
 greedy_rollout is the legacy path's free-running argmax decode with LSTMDecoder.generate's
 conventions (src/models/decoders.py:269-306): position 0 = start token, exactly max_length steps
 evaluated, last argmax discarded, no EOS stop.
+
+sample_captions_loop is the SAME loop driven through a `decoder_forward(captions) -> {"logits": [R,t,V]}` callable,
+i.e. literally the call structure of trainer.py:413-436 (full teacher-forced forward on the growing prefix, last
+position's logits); it is what runs against the drop-in modules' `forward(captions=...)`.
 """
 from __future__ import annotations
 
@@ -67,3 +71,22 @@ def sample_rollout(stepper, num_rows, max_length, uniforms, bos_token_id=1, eos_
         if bool((tok == eos_token_id).all()):
             break
     return ids, torch.stack(lps, dim=1), torch.stack(edges, dim=1)
+
+
+@torch.no_grad()
+def sample_captions_loop(decoder_forward, num_rows, max_length, uniforms, bos_token_id=1, eos_token_id=2, device="cpu"):
+    """trainer.py:383-438 with the Categorical draw replaced by the inverse-CDF draw on shared uniforms.
+    decoder_forward(input_ids int64 [R,t]) must return {"logits": [R,t,V]}.  -> (input_ids [R,<=T], log_probs [R,steps])"""
+    input_ids = torch.full((num_rows, 1), bos_token_id, dtype=torch.long, device=device)          # :402-407
+    log_probs = []
+    for t in range(max_length - 1):                                                             # :413
+        logits = decoder_forward(input_ids)["logits"][:, -1, :].float()                         # :415-420
+        probs = torch.softmax(logits, dim=-1)                                                   # :423
+        cdf = probs.double().cumsum(dim=-1)
+        u = uniforms[:, t].to(device).double().unsqueeze(1)
+        next_token = (cdf <= u).sum(dim=1).clamp(max=logits.size(1) - 1)                        # :424-425 (draw)
+        log_probs.append(torch.log(probs.gather(1, next_token[:, None]).squeeze(1)))            # :428 Categorical.log_prob
+        input_ids = torch.cat([input_ids, next_token.unsqueeze(1)], dim=1)                      # :432
+        if bool((next_token == eos_token_id).all()):                                            # :435
+            break
+    return input_ids, torch.stack(log_probs, dim=1)

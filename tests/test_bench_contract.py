@@ -28,6 +28,33 @@ def test_reference_arm_prints_one_json_line():
     assert rec["cpu_baseline"]["value"] == rec["value"]
     assert rec["e2e"] == {"value": rec["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[1]" in rec["config"]["workload"] and "model" not in rec["config"]
+    assert rec["scaling"] == "strong" and rec["config"]["total_images"] == 4096
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """the reference arm is the CPU oracle only: importing it must not pull in capdec_b200 / libcapdec.so"""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; "
+            "runpy.run_path('bench.py', run_name='__main__'); "
+            "bad = [m for m in sys.modules if 'capdec' in m]; assert not bad, bad; "
+            "assert 'libcapdec' not in open('/proc/self/maps').read()")
+    env = dict(os.environ, CAPDEC_BENCH_CPU_IMAGES="4")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_global_features_are_shard_consistent():
+    """any rank can generate exactly its shard of the global synthetic batch (strong scaling: 4096 images in total)"""
+    import importlib
+    import torch
+    sys.path.insert(0, ROOT)
+    try:
+        bench = importlib.import_module("bench")
+        full = bench.global_features(0, 600)
+        assert torch.equal(bench.global_features(100, 300), full[100:300])
+        assert torch.equal(bench.global_features(512, 600), full[512:600])
+        assert full.shape == (600, 14, 14, 2048) and float(full.min()) == 0.0
+    finally:
+        sys.path.remove(ROOT)
 
 
 def test_reference_arm_nonzero_rank_is_silent():

@@ -14,11 +14,12 @@ from capdec_b200 import _capi
 def test_library_is_in_tree_and_exports_header():
     assert os.path.isfile(_capi.LIB_PATH) and "image-captioning-ml-project_b200/csrc" in _capi.LIB_PATH
     syms = _capi.declared_symbols()
-    assert len(syms) >= 15 and "capdec_decode_beam" in syms and "capdec_decode_beam_host" in syms
+    assert len(syms) >= 28 and {"capdec_decode_beam", "capdec_decode_beam_host", "capdec_decode_beam_host_ex", "capdec_forward_tokens",
+                                 "capdec_ingest_features", "capdec_decode_beam_tiles", "capdec_trim_at_eos"} <= set(syms)
     out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(syms) <= exported, set(syms) - exported
-    assert _capi.lib.capdec_version() == 100
+    assert _capi.lib.capdec_version() == 200
 
 
 def test_library_contains_sm100a_code():

@@ -261,29 +261,44 @@ def test_legacy_beam_c1_vs_oracle(cuda, precision):
 
 
 _C2_CACHE = {}
+C2_IMAGES = int(os.environ.get("CAPDEC_TEST_C2_IMAGES", 1024))
+
+
+def _c2_reference(sd, enc, k, T):
+    """CPU oracle on the C2-shaped sample, decoded once per session (about 40-50 s for 1024 images) and shared by every
+    precision mode; decoded in slices so the step recording stays small."""
+    key = (enc.shape[0], k, T)
+    if key not in _C2_CACHE:
+        parts = [obeam.beam_search(olegacy.LegacyStepper(sd, enc[i:i + 256], k), min(256, enc.shape[0] - i), k, T, record_steps=True)
+                 for i in range(0, enc.shape[0], 256)]
+        ref = {n: torch.cat([p[n] for p in parts], dim=0) for n in ("sequences", "scores", "lengths")}
+        for n in ("top_lp", "top_tok", "top_beam"):
+            ref[n] = torch.cat([torch.stack([s_[n] for s_ in p["steps"]]) for p in parts], dim=1)     # [steps, B, 2k]
+        _C2_CACHE[key] = ref
+    return _C2_CACHE[key]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
-def test_legacy_c2_identical_beams_on_256_images(cuda, precision):
-    """BASELINE config 2 shape (beam 5, max_len 20, vocab 10k) on 256 images against the CPU oracle: the north
-    star's '>= 99% identical beams, per-step log-probs within 1e-3' bar, for the exact fp32 mode and the
-    tcgen05 3xTF32 mode the benchmark runs in."""
-    B, k, T = 256, 5, 20
+def test_legacy_c2_identical_beams_on_1024_images(cuda, precision):
+    """BASELINE config 2 shape (beam 5, max_len 20, vocab 10k) on 1024 images against the CPU oracle: the north
+    star's bar -- identical beams on >= 99 % of the images, per-step beam log-probs within 1e-3 -- for the exact fp32
+    mode AND both tensor-core split modes (bf16x3 is the mode bench.py's headline runs in).  1024 images resolve 99 %
+    from 98.4 % (10 vs 16 differing images); every differing beam must additionally be a near-tie for the oracle
+    itself (its oracle score within 2e-3 of the oracle's best)."""
+    B, k, T = C2_IMAGES, 5, 20
     m, sd = legacy_weights(10000, 0)
     m.precision = precision
     enc = legacy_features(B, seed=4242)
-    if "ref" not in _C2_CACHE:
-        _C2_CACHE["ref"] = obeam.beam_search(olegacy.LegacyStepper(sd, enc, k), B, k, T, record_steps=True)
-    ref = _C2_CACHE["ref"]
+    ref = _c2_reference(sd, enc, k, T)
     out = m.to(cuda).beam_search(enc.to(cuda), beam_size=k, max_length=T, trace=True)
 
     def rescore(seq, lengths):
-        return osample.rescore(olegacy.LegacyStepper(sd, enc, 1), seq, lengths)
-    # exact mode: the north star's >= 99%.  3xTF32 mode: the tensor core's round-toward-zero accumulation leaves
-    # ~1e-4 log-prob noise, so one or two more near-tied images may flip on this 256-image sample (every flip
-    # is verified to be a near-tie by the oracle rescoring inside _compare_beam).
-    _compare_beam(out, ref, B, k, f"legacy C2x256 {precision}", rescore=rescore,
-                  min_identical=0.99 if precision == "fp32" else 0.98)
+        bad = torch.nonzero((seq != ref["sequences"]).any(dim=1)).flatten()        # re-score only the differing images
+        sc = ref["scores"].clone()
+        if bad.numel():
+            sc[bad] = osample.rescore(olegacy.LegacyStepper(sd, enc[bad], 1), seq[bad], lengths[bad])
+        return sc
+    _compare_beam(out, ref, B, k, f"legacy C2x{B} {precision}", rescore=rescore, min_identical=0.99)
 
 
 def test_legacy_p24_tiles_vs_fp32_tiles(cuda):
@@ -326,13 +341,12 @@ def test_legacy_c2_bf16_mode(cuda):
     m, sd = legacy_weights(10000, 0)
     m.precision = "bf16"
     enc = legacy_features(B, seed=4242)
-    if "ref" not in _C2_CACHE:
-        _C2_CACHE["ref"] = obeam.beam_search(olegacy.LegacyStepper(sd, enc, k), B, k, T, record_steps=True)
+    ref = _c2_reference(sd, enc, k, T)
     out = m.to(cuda).beam_search(enc.to(cuda), beam_size=k, max_length=T, trace=True)
 
     def rescore(seq, lengths):
         return osample.rescore(olegacy.LegacyStepper(sd, enc, 1), seq, lengths)
-    _compare_beam(out, _C2_CACHE["ref"], B, k, "legacy C2x256 bf16", rescore=rescore, min_identical=0.0, logp_tol=2e-2,
+    _compare_beam(out, ref, B, k, "legacy C2x256 bf16", rescore=rescore, min_identical=0.0, logp_tol=2e-2,
                   tie_tol=2e-2)
 
 
@@ -369,7 +383,7 @@ def test_legacy_beam_edge_shapes(cuda, precision, B, k, T, V):
     enc = legacy_features(B, seed=17)
     ref = obeam.beam_search(olegacy.LegacyStepper(sd, enc, k), B, k, T, record_steps=True)
     out = m.to(cuda).beam_search(enc.to(cuda), beam_size=k, max_length=T, trace=True)
-    _compare_beam(out, ref, B, k, f"legacy edge B={B} k={k} T={T} V={V} {precision}", min_identical=0.97)
+    _compare_beam(out, ref, B, k, f"legacy edge B={B} k={k} T={T} V={V} {precision}", min_identical=0.99)
     assert torch.equal(out["lengths"].cpu().long(), ref["lengths"]) or precision != "fp32"
 
 
@@ -403,7 +417,8 @@ def _assert_tokens_match(tok, ref_tok, margins, what, precision="fp32"):
     assert unexcused == 0
 
 
-def _check_sampling(stepper, tok, lp, u, B, k, T, greedy_slot, ref_greedy=None):
+def _check_sampling(stepper, tok, lp, u, B, k, T, greedy_slot, ref_greedy=None, logp_tol=LOGP_TOL, edge_tol=1e-5,
+                    margin=MARGIN_EXCUSE["fp32"]):
     """Replay the CUDA tokens through the oracle stepper: per-step log-probs must agree (1e-3), and each
     sampled token must be the oracle's inverse-CDF draw unless u sits within 1e-5 of a CDF edge."""
     R = B * k
@@ -412,16 +427,16 @@ def _check_sampling(stepper, tok, lp, u, B, k, T, greedy_slot, ref_greedy=None):
     for t in range(T - 1):
         logits = stepper(tok[:, t])
         logp = torch.log_softmax(logits.float(), -1)
-        assert torch.allclose(lp[:, t], logp.gather(1, tok[:, t + 1:t + 2]).squeeze(1), atol=LOGP_TOL)
+        assert torch.allclose(lp[:, t], logp.gather(1, tok[:, t + 1:t + 2]).squeeze(1), atol=logp_tol)
         cdf = torch.softmax(logits.double(), -1).cumsum(-1)
         draw = (cdf <= u[:, t:t + 1].double()).sum(1).clamp(max=logits.shape[1] - 1)
         edge = (cdf - u[:, t:t + 1].double()).abs().min(1).values
         for r in range(R):
             if r % k == greedy_slot:
                 top2 = logits[r].topk(2).values
-                assert tok[r, t + 1] == logits[r].argmax() or (top2[0] - top2[1]) / logits[r].std() < MARGIN_EXCUSE["fp32"]
+                assert tok[r, t + 1] == logits[r].argmax() or (top2[0] - top2[1]) / logits[r].std() < margin
             elif tok[r, t + 1] != draw[r]:
-                assert edge[r] < 1e-5, (r, t, float(edge[r]))
+                assert edge[r] < edge_tol, (r, t, float(edge[r]))
                 mismatched += 1
     print(f"[sampling] edge-excused draws: {mismatched}/{R * (T - 1)}")
 
@@ -469,7 +484,7 @@ def test_lstm_beam_vs_oracle(cuda, kind, heads, layers, precision):
     def rescore(seq, lengths):
         st1 = olstm.LSTMStepper(sd, feats, pooled, kind, layers, heads, 1, None if mask is None else ~mask)
         return osample.rescore(st1, seq, lengths)
-    _compare_beam(out, ref, B, k, f"lstm beam {kind} {precision}", rescore=rescore, min_identical=0.0)
+    _compare_beam(out, ref, B, k, f"lstm beam {kind} {precision}", rescore=rescore, min_identical=0.99)
 
 
 def test_lstm_sample_rollout_vs_oracle(cuda):
@@ -515,7 +530,7 @@ def test_transformer_all_eos_break_and_beam_and_sample(cuda):
 
     def rescore(s_, lengths):
         return osample.rescore(otr.TransformerStepper(sd, feats, layers, heads, 1), s_, lengths)
-    _compare_beam(out, ref, B, k, "transformer beam", rescore=rescore, min_identical=0.0)
+    _compare_beam(out, ref, B, k, "transformer beam", rescore=rescore, min_identical=0.99)
     # SCST rollout: 2 samples + greedy row, uniforms shared with the oracle replay
     u = torch.rand(B * 3, T - 1, generator=torch.Generator().manual_seed(6))
     tok, sinfo = m.generate(ef, T, do_sample=True, num_samples=2, with_greedy=True, uniforms=u.to(cuda))
@@ -554,7 +569,7 @@ def test_gpt2_beam_and_sample_vs_hf(cuda, precision):
 
     def rescore(s_, lengths):
         return osample.rescore(ogpt.HFStepper(hf, sd, pooled, 1), s_, lengths)
-    _compare_beam(out, ref, B, k, f"gpt2 beam {precision}", rescore=rescore, min_identical=0.0)
+    _compare_beam(out, ref, B, k, f"gpt2 beam {precision}", rescore=rescore, min_identical=0.99)
     seq2, info2 = mg.generate({"pooled_features": pooled.to(cuda)}, T)
     assert info2 == {} and torch.equal(seq2, seq)
     if precision == "fp32":
@@ -570,7 +585,7 @@ def test_gpt2_beam_and_sample_vs_hf(cuda, precision):
 def test_gpt2_124m_config4_vs_hf(cuda, precision):
     """BASELINE config 4 shape: GPT-2 124M (12 layers, 12 heads, 768, vocab 50257), beam 5, max_len 20, random init;
     config 4 names bf16, so the bf16 mode is held to the north star's 2e-2 log-prob tolerance."""
-    B, T, k = 4, 20, 5
+    B, T, k = 16, 20, 5
     m, sd = gpt2_decoder(H=768, layers=12, heads=12, V=50257, max_length=64)
     m.precision = precision
     import copy
@@ -585,8 +600,49 @@ def test_gpt2_124m_config4_vs_hf(cuda, precision):
     def rescore(s_, lengths):
         return osample.rescore(ogpt.HFStepper(hf, sd, pooled, 1), s_, lengths)
     tol = 2e-2 if precision == "bf16" else LOGP_TOL
-    _compare_beam(out, ref, B, k, f"gpt2-124M beam5 {precision}", rescore=rescore, min_identical=0.0, logp_tol=tol,
-                  tie_tol=2e-2 if precision == "bf16" else 2e-3)
+    # fp32-class modes: the north star's >= 99 % (here: at most one of the 16 images, and it must be an oracle near-tie);
+    # the bf16 mode is held to its own bar (per-step log-probs within 2e-2), differing beams must be 2e-2 near-ties
+    _compare_beam(out, ref, B, k, f"gpt2-124M beam5 {precision}", rescore=rescore, min_identical=0.0 if precision == "bf16" else 0.99,
+                  logp_tol=tol, tie_tol=2e-2 if precision == "bf16" else 2e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_transformer_config3_shape_beam_vs_oracle(cuda, precision):
+    """BASELINE config 3 shape: 6-layer post-LN transformer decoder, H=768, 8 heads (head_dim 96), 196 x 768 ViT-B/16
+    region features, vocab 10k, beam 3, max_len 20, KV-cached on the GPU vs the oracle's un-cached full-prefix recompute
+    (decoders.py:463-483), 8 images."""
+    H, layers, heads, V, L, B, T, k = 768, 6, 8, 10000, 196, 8, 20, 3
+    m, sd = transformer_decoder(H=H, layers=layers, heads=heads, V=V, max_length=50, seed=7)
+    m.precision = precision
+    feats, _, _ = lstm_inputs(B, L, H, seed=71)
+    ref = obeam.beam_search(otr.TransformerStepper(sd, feats, layers, heads, k), B, k, T, record_steps=True)
+    seq, info = m.to(cuda).generate({"features": feats.to(cuda)}, T, num_beams=k, trace=True)
+    out = {"tokens": torch.nn.functional.pad(seq, (0, T - seq.shape[1]), value=2).int(), "scores": info["scores"],
+           "lengths": info["lengths"], "top_logprob": info["top_logprob"], "top_token": info["top_token"],
+           "top_beam": info["top_beam"]}
+
+    def rescore(s_, lengths):
+        return osample.rescore(otr.TransformerStepper(sd, feats, layers, heads, 1), s_, lengths)
+    _compare_beam(out, ref, B, k, f"transformer C3-shape beam3 {precision}", rescore=rescore, min_identical=0.99)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gpt2_124m_config5_sampling_vs_hf(cuda, precision):
+    """BASELINE config 5 shape: SCST rollout on GPT-2 124M (vocab 50257), 5 multinomial samples + 1 greedy row per image,
+    4 images = 24 rows, max_len 20, uniforms shared with the oracle replay through transformers itself.  The config names
+    bf16: that mode is held to the north star's 2e-2 per-step log-prob bar, fp32 to 1e-3."""
+    B, T, k = 4, 20, 6
+    m, sd = gpt2_decoder(H=768, layers=12, heads=12, V=50257, max_length=64)
+    m.precision = precision
+    import copy
+    hf = copy.deepcopy(m.model)
+    pooled = torch.randn(B, 768, generator=torch.Generator().manual_seed(12))
+    u = torch.rand(B * k, T - 1, generator=torch.Generator().manual_seed(13))
+    tok, info = m.to(cuda).generate({"pooled_features": pooled.to(cuda)}, T, do_sample=True, num_samples=5, with_greedy=True,
+                                    uniforms=u.to(cuda))
+    _check_sampling(ogpt.HFStepper(hf, sd, pooled, k), tok.cpu(), info["log_probs"].cpu()[:, : tok.shape[1] - 1], u, B, k,
+                    tok.shape[1], greedy_slot=5, logp_tol=2e-2 if precision == "bf16" else LOGP_TOL,
+                    edge_tol=2e-3 if precision == "bf16" else 1e-5, margin=0.1 if precision == "bf16" else MARGIN_EXCUSE["fp32"])
 
 
 # ------------------------------------------------------------------------------------------------ properties at size

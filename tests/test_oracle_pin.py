@@ -253,3 +253,155 @@ def test_sample_rollout_inverse_cdf():
     st2 = olstm.LSTMStepper(sd, feats, pooled, "soft", 1, rows_per_image=2)
     ids2, _, _ = osample.sample_rollout(st2, 6, 10, u)
     assert torch.equal(ids, ids2)
+
+
+# ---------------------------------------------------------------- teacher-forced forward + the trainer's sampling loop
+@needs_ref
+@pytest.mark.parametrize("kind,heads,ragged", [("soft", 1, False), ("multi_head", 4, True), ("aoa", 4, False)])
+def test_teacher_lstm_logits_match_reference_forward(kind, heads, ragged):
+    """oracle/teacher.py::lstm_logits == the reference LSTMDecoder.forward(captions=...) (decoders.py:137-234)."""
+    from oracle import teacher as oteach
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(7)
+    H, layers, V, L, B, T = 64, 2, 300, 21, 5, 9
+    ref = ns.decoders.LSTMDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.LSTM, hidden_dim=H, num_layers=layers),
+        C.AttentionConfig(attention_type=C.AttentionType(kind), num_heads=heads, hidden_dim=H),
+        vocab_size=V, pad_token_id=0).eval()
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    feats, pooled, mask = lstm_inputs(B, L, H, seed=3, ragged=ragged)
+    caps = torch.randint(0, V, (B, T), generator=torch.Generator().manual_seed(4))
+    ef = {"features": feats, "pooled_features": pooled}
+    if mask is not None:
+        ef["attention_mask"] = mask
+    out = ref(ef, captions=caps)
+    logits, alphas = oteach.lstm_logits(sd, feats, pooled, kind, layers, heads, caps, None if mask is None else ~mask)
+    assert torch.allclose(out["logits"], logits, atol=1e-5) and torch.allclose(out["attention_weights"], alphas, atol=1e-6)
+    # (with caption_lengths the reference sorts captions / features but takes h0, c0 from the UNSORTED pooled features,
+    #  decoders.py:157-171, so rows get another image's initial state; _sample_captions passes None and the drop-in
+    #  ignores the argument rather than reproduce the mis-pairing)
+
+
+@needs_ref
+def test_teacher_transformer_logits_match_reference_forward():
+    """oracle/teacher.py::transformer_logits == the reference TransformerDecoder.forward(captions=...) (decoders.py:377-438),
+    pad tokens inside the captions included (tgt_key_padding_mask)."""
+    from oracle import teacher as oteach
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(8)
+    H, layers, heads, V, B, T = 64, 2, 4, 120, 4, 8
+    ref = ns.decoders.TransformerDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.TRANSFORMER, hidden_dim=H, num_layers=layers, num_heads=heads,
+                        max_length=50), vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    feats, _, _ = lstm_inputs(B, 19, H, seed=9)
+    caps = torch.randint(1, V, (B, T), generator=torch.Generator().manual_seed(5))
+    caps[:, 0] = 1
+    caps[1, 3] = 0          # a pad token in the middle of a prefix: masked as a key for every later position
+    caps[2, 6:] = 0
+    out = ref({"features": feats}, captions=caps)
+    logits = oteach.transformer_logits(sd, feats, layers, heads, caps, pad_token_id=0)
+    assert torch.allclose(out["logits"], logits, atol=1e-5), (out["logits"] - logits).abs().max()
+    # the KV-cached stepper (what the CUDA path is built like) agrees wherever no pad key is involved
+    st = otr.TransformerStepper(sd, feats, layers, heads, 1)
+    step_logits = torch.stack([st(caps[:, t]) for t in range(T)], dim=1)
+    assert torch.allclose(step_logits[0], logits[0], atol=1e-4) and torch.allclose(step_logits[3], logits[3], atol=1e-4)
+    assert torch.allclose(step_logits[1, :3], logits[1, :3], atol=1e-4)
+    assert not torch.allclose(step_logits[1, 4:], logits[1, 4:], atol=1e-4)      # the pad key does matter
+
+
+@needs_ref
+def test_sample_loop_restatement_matches_reference_trainer():
+    """oracle/sample.py::sample_captions_loop (and the step-wise sample_rollout) == the UNMODIFIED
+    CaptioningTrainer._sample_captions (trainer.py:383-438) when torch.distributions.Categorical is patched to draw by
+    inverse CDF from the same uniforms."""
+    import types
+    rt = refshim.load_reference_trainer()
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(9)
+    H, layers, heads, V, B, T = 64, 2, 4, 90, 6, 9
+    dec = ns.decoders.TransformerDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.TRANSFORMER, hidden_dim=H, num_layers=layers, num_heads=heads,
+                        max_length=50), vocab_size=V, pad_token_id=0, bos_token_id=1, eos_token_id=2).eval()
+    sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    feats, _, _ = lstm_inputs(B, 19, H, seed=10)
+    u = torch.rand(B, T - 1, generator=torch.Generator().manual_seed(11))
+
+    class FakeCategorical:                       # consumes column `step` of the shared uniforms, in call order
+        step = 0
+
+        def __init__(self, probs):
+            self.probs = probs
+
+        def sample(self):
+            cdf = self.probs.double().cumsum(-1)
+            tok = (cdf <= u[:, FakeCategorical.step:FakeCategorical.step + 1].double()).sum(1).clamp(max=self.probs.size(1) - 1)
+            FakeCategorical.step += 1
+            return tok
+
+        def log_prob(self, tok):
+            return torch.log(self.probs.gather(1, tok[:, None]).squeeze(1))
+
+    fake_self = types.SimpleNamespace(
+        config=types.SimpleNamespace(inference=types.SimpleNamespace(max_length=T)),
+        model=types.SimpleNamespace(encoder=lambda images: {"features": feats}, decoder=dec))
+    orig = torch.distributions.Categorical
+    torch.distributions.Categorical = FakeCategorical
+    try:
+        ids_ref, lp_ref = rt.CaptioningTrainer._sample_captions(fake_self, torch.zeros(B, 3, 8, 8))
+    finally:
+        torch.distributions.Categorical = orig
+    ids2, lp2 = osample.sample_captions_loop(lambda ids: dec({"features": feats}, captions=ids), B, T, u)
+    assert torch.equal(ids_ref, ids2) and torch.allclose(lp_ref, lp2, atol=1e-6)
+    # step-wise rollout over the cached stepper: same tokens unless a sampled pad token (id 0) sits in a prefix
+    ids3, lp3, _ = osample.sample_rollout(otr.TransformerStepper(sd, feats, layers, heads, 1), B, T, u)
+    clean = ~(ids_ref[:, 1:-1] == 0).any(dim=1)
+    assert clean.any()
+    assert torch.equal(ids_ref[clean], ids3[clean]) and torch.allclose(lp_ref[clean], lp3[clean], atol=1e-4)
+
+
+@needs_ref
+def test_feature_producers_with_padding_masks_run_through_the_oracle():
+    """the reference's alternative feature producers -- ObjectRegionEncoder (36 x 2048 regions with a
+    padding mask, encoders.py:233-296) and QFormer (32 x 768 queries, captioning_model.py:153-245) -- emit exactly the
+    {features, pooled_features, attention_mask} contract the decode path consumes; the reference LSTMDecoder on their
+    output equals the oracle restatement with key_padding_mask = ~attention_mask."""
+    rt = refshim.load_reference_trainer()
+    ns = refshim.load_reference()
+    C = ns.config
+    torch.manual_seed(12)
+    H, B, L = 64, 4, 36
+    enc = rt.ObjectRegionEncoder(C.EncoderConfig(feature_dim=H, use_object_features=True)).eval()
+    g = torch.Generator().manual_seed(13)
+    region_mask = torch.ones(B, L)
+    for b, n in enumerate((36, 20, 7, 1)):
+        region_mask[b, n:] = 0
+    ef = enc({"region_features": torch.randn(B, L, 2048, generator=g), "region_boxes": torch.rand(B, L, 4, generator=g),
+              "region_mask": region_mask})
+    assert ef["features"].shape == (B, L, H) and ef["pooled_features"].shape == (B, H)
+    dec = ns.decoders.LSTMDecoder(
+        C.DecoderConfig(decoder_type=C.DecoderType.LSTM, hidden_dim=H, num_layers=1),
+        C.AttentionConfig(attention_type=C.AttentionType.MULTI_HEAD, num_heads=4, hidden_dim=H), vocab_size=200,
+        pad_token_id=0).eval()
+    sd = {k: v.detach() for k, v in dec.state_dict().items()}
+    ef_bool = dict(ef, attention_mask=ef["attention_mask"].bool())        # the float mask trips `~` (SURVEY 0.4)
+    ids, info = dec.generate(ef_bool, 8)
+    ids2, al2 = olstm.generate_greedy(sd, ef["features"], ef["pooled_features"], "multi_head", 1, 8, num_heads=4,
+                                      mask=~ef_bool["attention_mask"])
+    assert torch.equal(ids, ids2) and torch.allclose(info["attention_weights"], al2, atol=1e-6)
+    assert float(info["attention_weights"][2, :, 7:].abs().max()) < 1e-12       # padded regions get no weight
+    q = rt.QFormer(query_dim=H, vision_dim=H, num_queries=32, num_layers=1, num_heads=4, dropout=0.0).eval()
+    out = q(ef["features"])
+    assert out["queries"].shape == (B, 32, H)
+
+
+def test_plain_torch_weights_equal_dropin_init():
+    """oracle/weights.py (what bench.py's reference arm uses, so that arm never imports the product) == the seeded init of
+    the drop-in Decoder == the reference Decoder's own init (test_dropin_init_equals_reference_init)."""
+    from oracle.weights import legacy_state_dict
+    a = legacy_state_dict(300, 3)
+    _, b = legacy_weights(300, 3)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
