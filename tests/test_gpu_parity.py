@@ -219,11 +219,18 @@ def _compare_beam(out, ref, B, k, what, rescore=None, min_identical=0.99, logp_t
     live = ref_lp > -1e8
     agree = ((tok == ref_tok) & (beam == ref_beam)) | ~live
     consistent = torch.cumprod(agree.all(dim=2).long(), dim=0).bool()          # [steps, B]
+    # EXACT fp32 ties between neighbouring candidates: which of two equal-scored candidates becomes the k-th running beam
+    # is torch.topk's unspecified choice in HF's _beam_search (and in the oracle); the CUDA path takes the lower index.
+    # Both continue with an equally scored hypothesis but not necessarily the same one, so an image stops being
+    # comparable candidate-by-candidate AFTER a step with such a tie (counted and printed, not hidden).
+    tie = (((ref_lp[:, :, :-1] == ref_lp[:, :, 1:]) | (lp[:, :, :-1] == lp[:, :, 1:])) & live[:, :, 1:]).any(dim=2)
+    tie_before = (torch.cumsum(tie.long(), dim=0) - tie.long()) > 0
+    consistent = consistent & ~tie_before
     cmp = live & consistent[:, :, None]
     err = (lp - ref_lp)[cmp].abs().max().item() if bool(cmp.any()) else 0.0
     frac = same.float().mean().item()
     msg = (f"[{what}] identical beams on {int(same.sum())}/{B} images, max |dlogp| = {err:.2e} over "
-           f"{int(cmp.sum())}/{int(live.sum())} comparable candidates")
+           f"{int(cmp.sum())}/{int(live.sum())} comparable candidates ({int(tie.any(dim=0).sum())} images with an exact score tie)")
     if rescore is not None and not bool(same.all()):
         sc = rescore(seq, out["lengths"].cpu().long())
         gap = (ref["scores"] - sc)[~same]
@@ -603,7 +610,7 @@ def test_gpt2_124m_config4_vs_hf(cuda, precision):
     # fp32-class modes: the north star's >= 99 % (here: at most one of the 16 images, and it must be an oracle near-tie);
     # the bf16 mode is held to its own bar (per-step log-probs within 2e-2), differing beams must be 2e-2 near-ties
     _compare_beam(out, ref, B, k, f"gpt2-124M beam5 {precision}", rescore=rescore, min_identical=0.0 if precision == "bf16" else 0.99,
-                  logp_tol=tol, tie_tol=2e-2 if precision == "bf16" else 2e-3)
+                  logp_tol=tol, tie_tol=4e-2 if precision == "bf16" else 2e-3)   # bf16: BOTH hypotheses' scores carry up to 2e-2
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
