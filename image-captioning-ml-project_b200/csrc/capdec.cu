@@ -672,6 +672,7 @@ int step_transformer(const capdec_handle* h, Session& S, const uint8_t* mask, in
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
+      a.cache_bf16 = c.precision == CAPDEC_PREC_BF16 ? 1 : 0;   // single-pass bf16 mode: K / V cached as bf16 (half the bytes)
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -757,6 +758,7 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
+      a.cache_bf16 = c.precision == CAPDEC_PREC_BF16 ? 1 : 0;   // single-pass bf16 mode: K / V cached as bf16 (half the bytes)
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -1176,19 +1178,6 @@ static int decode_beam_impl(capdec_handle* h, const float* feats, const TileSet*
     const float div_heur = div_fin;
     const size_t o = (size_t)(cur_len - 1) * B * k2;
     const bool more = cur_len + 1 < T;
-    // Opt-in (CAPDEC_FUSED_SELECT=1): measured on B200 at 4096 images the single per-image kernel takes 3.8 ms per decode
-    // against 2.9 ms for the three specialised kernels (its phases serialise inside a CTA), so the default keeps them apart.
-    static const bool fused_select = getenv("CAPDEC_FUSED_SELECT") != nullptr;
-    if (S.fuse_k > 0 && !is_tf_family(h) && fused_select) {
-      // candidate merge + beam bookkeeping + state reorder / embedding gather of an image in one CTA
-      GatherArgs ga{};
-      if (more) build_gather(h, S, S.src_row, nullptr, 0, -1, true, &ga);
-      StageScope sc(h, STAGE_BEAM, s);
-      CAPDEC_RETURN_IF(select_fused(S.tk_part, S.tk_lse, c.vocab_size, S.tk_ntotal, S.fuse_k, S.beam, B, k, T, cur_len,
-                                    c.eos_token_id, div_fin, div_heur, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
-                                    dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, more ? &ga : nullptr, s));
-      continue;
-    }
     { StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(select_topk(h, S, k2, S.cand_lp, S.cand_idx, s)); }
     { StageScope sc(h, STAGE_BEAM, s);

@@ -132,12 +132,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int kind, int m, int n) {
 // each CTA staging its own 128 rows of A and HALF of the W tile (BN/2 rows), which halves the shared-memory bytes per
 // flop -- a single CTA's 3xTF32 main loop needs ~158 B/clk of shared-memory bandwidth (MMA operand reads + TMA fills),
 // more than the SM's 128 B/clk; the pair needs ~106 B/clk.
-template <int BN, int CG>
+template <int BN, int CG, int TERMS>
 struct SmemLayout {
-  static constexpr int kStages = CG == 2 ? 3 : 2;
   static constexpr uint32_t kABytes = BM * kRowBytes;
   static constexpr uint32_t kWBytes = (BN / CG) * kRowBytes;
-  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kWBytes;
+  // a stage holds one K block of A and W, as hi + lo copies in the 3-term modes.  The single-term modes have half the
+  // bytes and a third of the MMA time per K block, so their ring is twice as deep: with 3 stages the loop waits on the
+  // L2 -> shared-memory latency of every block (measured 46 us per GPT-2 projection GEMM against 5-17 us of MMA time)
+  static constexpr uint32_t kStageBytes = TERMS == 3 ? 2 * kABytes + 2 * kWBytes : kABytes + kWBytes;
+  static constexpr uint32_t kOffALo = kABytes;                                   // (3-term only)
+  static constexpr uint32_t kOffWHi = TERMS == 3 ? 2 * kABytes : kABytes;
+  static constexpr uint32_t kOffWLo = kOffWHi + kWBytes;                        // (3-term only)
+  static constexpr int kStages = (CG == 2 ? 3 : 2) * (TERMS == 3 ? 1 : 2);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kStashOffset = kBarOffset + 256;   // EPI_TOPK only: 8 warps x 32 columns x 32 lanes floats
   static constexpr uint32_t kStashBytes = 8 * 32 * 32 * 4;
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const GemmArgs p) {
-  using SL = SmemLayout<BN, CG>;
+  using SL = SmemLayout<BN, CG, TERMS>;
   constexpr int kStages = SL::kStages;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -224,23 +230,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * SL::kStageBytes;
-          constexpr uint32_t kTx = TERMS == 3 ? SL::kStageBytes : SL::kABytes + SL::kWBytes;
+          constexpr uint32_t kTx = SL::kStageBytes;
           if (CG == 2) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * kTx);   // bytes of both CTAs land on the leader's barrier
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
             tma_load_2d_pair(st, &map_a_hi, lbar, kb * BK, a_row);
-            tma_load_2d_pair(st + 2 * SL::kABytes, &map_w_hi, lbar, kb * BK, w_row);
+            tma_load_2d_pair(st + SL::kOffWHi, &map_w_hi, lbar, kb * BK, w_row);
             if (TERMS == 3) {
-              tma_load_2d_pair(st + SL::kABytes, &map_a_lo, lbar, kb * BK, a_row);
-              tma_load_2d_pair(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, lbar, kb * BK, w_row);
+              tma_load_2d_pair(st + SL::kOffALo, &map_a_lo, lbar, kb * BK, a_row);
+              tma_load_2d_pair(st + SL::kOffWLo, &map_w_lo, lbar, kb * BK, w_row);
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[s], kTx);
             tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, a_row);
-            tma_load_2d(st + 2 * SL::kABytes, &map_w_hi, &full_bar[s], kb * BK, w_row);
+            tma_load_2d(st + SL::kOffWHi, &map_w_hi, &full_bar[s], kb * BK, w_row);
             if (TERMS == 3) {
-              tma_load_2d(st + SL::kABytes, &map_a_lo, &full_bar[s], kb * BK, a_row);
-              tma_load_2d(st + 2 * SL::kABytes + SL::kWBytes, &map_w_lo, &full_bar[s], kb * BK, w_row);
+              tma_load_2d(st + SL::kOffALo, &map_a_lo, &full_bar[s], kb * BK, a_row);
+              tma_load_2d(st + SL::kOffWLo, &map_w_lo, &full_bar[s], kb * BK, w_row);
             }
           }
         }
@@ -267,9 +273,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * SL::kStageBytes);
-          const uint32_t a_lo = a_hi + SL::kABytes;
-          const uint32_t w_hi = a_hi + 2 * SL::kABytes;
-          const uint32_t w_lo = w_hi + SL::kWBytes;
+          const uint32_t a_lo = a_hi + SL::kOffALo;
+          const uint32_t w_hi = a_hi + SL::kOffWHi;
+          const uint32_t w_lo = a_hi + SL::kOffWLo;
 #pragma unroll
           for (int k = 0; k < kRowBytes / 32; ++k) {
             const uint32_t koff = k * 32;  // one MMA consumes 32 bytes along K (8 tf32 / 16 bf16) inside the 128-byte swizzle span
@@ -643,7 +649,7 @@ int tc_max_groups(int cg) {
   if (cache[cg].load()) return cache[cg].load();
   if (cg == 1) { cache[1].store(num_sms()); return num_sms(); }
   auto kern = gemm_tcgen05_kernel<256, EPI_STORE, 3, 0, 2, KIND_TF32>;
-  constexpr int smem = SmemLayout<256, 2>::kTotal;
+  constexpr int smem = SmemLayout<256, 2, 3>::kTotal;
   int n = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
@@ -672,7 +678,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
     auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                 \
-    constexpr int smem = E == EPI_TOPK ? SmemLayout<BN, CG>::kTotalTopk : SmemLayout<BN, CG>::kTotal;             \
+    constexpr int smem = E == EPI_TOPK ? SmemLayout<BN, CG, TERMS>::kTotalTopk : SmemLayout<BN, CG, TERMS>::kTotal; \
     static std::atomic<bool> configured[kMaxDevices];   /* function attributes are per device */                 \
     const int dev_ = current_device();                                                                            \
     if (!configured[dev_].load()) {                                                                               \

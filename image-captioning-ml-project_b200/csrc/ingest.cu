@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestArgs a, in
   }
 }
 
-// Channel-major source [B,D,L] (NCHW feature map): a CTA transposes a [32 channels, L] slab through shared memory --
+// Channel-major source [B,D,L] (NCHW feature map): a CTA transposes a [64 channels, L] slab through shared memory --
 // reads run along l (contiguous in the source), writes along d (contiguous in every output).
-constexpr int kTC = 32;   // channels per slab
+constexpr int kTC = 64;   // channels per slab: a region row of the slab is 128 B of hi plane, 64 B of byte plane, 128 B of lo
 template <int DT>
 __global__ void __launch_bounds__(256) ingest_transpose_kernel(const IngestArgs a, int pitch) {
   extern __shared__ float tile[];   // [kTC][pitch], pitch odd
@@ -95,9 +95,34 @@ __global__ void __launch_bounds__(256) ingest_transpose_kernel(const IngestArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t es = DT == CAPDEC_DT_F32 ? 4 : 2;
   const char* img = reinterpret_cast<const char*>(a.src) + (int64_t)b * D * L * es;
-  for (int c = warp; c < kTC; c += 8) {
-    const bool live = d0 + c < D;
-    for (int l = lane; l < L; l += 32) tile[c * pitch + l] = live ? load1<DT>(img, (int64_t)(d0 + c) * L + l) : 0.f;
+  // a warp owns channels warp, warp + 8, ...; it takes them four at a time and issues all 32 loads per lane before the
+  // first shared-memory store, so a warp keeps 4 KB of the source in flight (one 128-byte row at a time made the kernel
+  // latency-bound at 2.3 TB/s)
+  constexpr int CH = 4;
+  for (int c0 = warp; c0 < kTC; c0 += 8 * CH) {
+    for (int l0 = 0; l0 < L; l0 += 256) {
+      float v[CH][8];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int c = c0 + 8 * j;
+        const bool live = c < kTC && d0 + c < D;
+        const int64_t base = (int64_t)(d0 + c) * L;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int l = l0 + lane + 32 * u;
+          v[j][u] = (live && l < L) ? load1<DT>(img, base + l) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int c = c0 + 8 * j;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int l = l0 + lane + 32 * u;
+          if (c < kTC && l < L) tile[c * pitch + l] = v[j][u];
+        }
+      }
+    }
   }
   __syncthreads();
   if (a.mean && threadIdx.x < kTC && d0 + threadIdx.x < D) {
@@ -105,6 +130,7 @@ __global__ void __launch_bounds__(256) ingest_transpose_kernel(const IngestArgs 
     for (int l = 0; l < L; ++l) s += tile[threadIdx.x * pitch + l];   // region order, as the row-major kernel
     a.mean[(int64_t)b * D + d0 + threadIdx.x] = s / (float)L;
   }
+  // 16 threads per region row (4 channels each): a half-warp writes one row's 128 / 64 / 128 contiguous bytes
   for (int i = threadIdx.x; i < L * (kTC / 4); i += 256) {
     const int l = i / (kTC / 4), cg = i - l * (kTC / 4);
     const int d = d0 + cg * 4;

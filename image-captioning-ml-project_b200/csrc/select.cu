@@ -311,38 +311,47 @@ __global__ void beam_init_kernel(BeamState st, int B, int k, int T, int bos, int
 
 // one WARP per image: every lane evaluates the (tiny) selection logic redundantly on the same inputs, the token
 // sequences are copied lane-parallel, lane 0 writes the scalars.  cand_lp / cand_idx: the image's k sorted lists of 2k
-// candidates, cand[(b * 2k) + j] (global or shared memory).
-__device__ __forceinline__ void beam_step_image(const BeamState& st, int img, int lane, int k, int T, int cur_len, int eos,
+// candidates, cand[(b * 2k) + j] (shared memory).  The beam width is a template parameter and every per-image array is
+// indexed by unrolled loop counters only, so the whole merge state lives in registers (the run-time-k form kept 656 bytes
+// of it in local memory).
+template <int K>
+__device__ __forceinline__ void beam_step_image(const BeamState& st, int img, int lane, int T, int cur_len, int eos,
                                                 float div_fin, float div_heur, const float* cand_lp, const int32_t* cand_idx,
                                                 int32_t* next_tok, int32_t* src_row, float* dbg_lp, int32_t* dbg_tok,
                                                 int32_t* dbg_beam) {
-  constexpr int KM = kMaxRowsPerImage, K2 = kMaxTopK;
-  const int k2 = 2 * k;
+  constexpr int k = K, k2 = 2 * K;
   const int par = (cur_len - 1) & 1;  // read buffers [par], write [par ^ 1]
-  const int32_t* run_old = st.run_seq[par] + (int64_t)img * k * T;
-  int32_t* run_new = st.run_seq[par ^ 1] + (int64_t)img * k * T;
-  const int32_t* fin_old = st.fin_seq[par] + (int64_t)img * k * T;
-  int32_t* fin_new = st.fin_seq[par ^ 1] + (int64_t)img * k * T;
+  // (ternaries, not st.run_seq[par]: a run-time index into a by-value kernel parameter forces a local-memory copy of it)
+  const int32_t* run_old = (par ? st.run_seq[1] : st.run_seq[0]) + (int64_t)img * k * T;
+  int32_t* run_new = (par ? st.run_seq[0] : st.run_seq[1]) + (int64_t)img * k * T;
+  const int32_t* fin_old = (par ? st.fin_seq[1] : st.fin_seq[0]) + (int64_t)img * k * T;
+  int32_t* fin_new = (par ? st.fin_seq[0] : st.fin_seq[1]) + (int64_t)img * k * T;
 
   // (c) top-2k continuations over the k*V accumulated log-probs: k-way merge of the per-row sorted lists
-  float score[KM];
-  int ptr[KM];
+  float score[k];
+  int ptr[k];
+#pragma unroll
   for (int b = 0; b < k; ++b) { score[b] = st.run_score[img * k + b]; ptr[b] = 0; }
-  float top_lp[K2];
-  int top_tok[K2], top_beam[K2];
+  float top_lp[k2];
+  int top_tok[k2], top_beam[k2];
+#pragma unroll
   for (int j = 0; j < k2; ++j) {
     float bv = -INFINITY;
     int bb = -1, bt = 0;
+#pragma unroll
     for (int b = 0; b < k; ++b) {
-      if (ptr[b] >= k2) continue;
-      const int o = b * k2 + ptr[b];
-      const int tok = cand_idx[o];
-      if (tok < 0) continue;
-      const float v = cand_lp[o] + score[b];
-      if (bb < 0 || v > bv) { bv = v; bb = b; bt = tok; }  // ties keep the lower flat index (lower beam first)
+      if (ptr[b] < k2) {
+        const int o = b * k2 + ptr[b];
+        const int tok = cand_idx[o];
+        if (tok >= 0) {
+          const float v = cand_lp[o] + score[b];
+          if (bb < 0 || v > bv) { bv = v; bb = b; bt = tok; }  // ties keep the lower flat index (lower beam first)
+        }
+      }
     }
     top_lp[j] = bv; top_tok[j] = bt; top_beam[j] = bb < 0 ? 0 : bb;
-    if (bb >= 0) ptr[bb]++;
+#pragma unroll
+    for (int b = 0; b < k; ++b) ptr[b] += (b == bb) ? 1 : 0;
     if (dbg_lp && lane == 0) {
       const int64_t o = (int64_t)img * k2 + j;
       dbg_lp[o] = bv; dbg_tok[o] = bt; dbg_beam[o] = top_beam[j];
@@ -351,75 +360,89 @@ __device__ __forceinline__ void beam_step_image(const BeamState& st, int img, in
 
   // (d) stopping criteria on the extended sequences: MaxLength | Eos
   const bool at_max = cur_len + 1 >= T;
-  bool hits[K2];
-  float run_lp[K2];
+  unsigned hits = 0u;
+  float run_lp[k2];
+#pragma unroll
   for (int j = 0; j < k2; ++j) {
-    hits[j] = at_max || top_tok[j] == eos;
-    run_lp[j] = top_lp[j] + (hits[j] ? kNeg : 0.f);
+    const bool hit = at_max || top_tok[j] == eos;
+    hits |= (hit ? 1u : 0u) << j;
+    run_lp[j] = top_lp[j] + (hit ? kNeg : 0.f);
   }
 
   // (e) next running beams: top-k of run_lp (stable)
-  bool used[K2];
-  for (int j = 0; j < k2; ++j) used[j] = false;
-  float new_score[KM];
+  unsigned used = 0u;
+  float new_score[k];
+#pragma unroll
   for (int i = 0; i < k; ++i) {
     int bj = -1;
+    float bvv = 0.f;
+    int stok = 0, sbeam = 0;
+#pragma unroll
     for (int j = 0; j < k2; ++j)
-      if (!used[j] && (bj < 0 || run_lp[j] > run_lp[bj])) bj = j;
-    used[bj] = true;
-    new_score[i] = run_lp[bj];
-    const int32_t* srcp = run_old + (int64_t)top_beam[bj] * T;
+      if (!((used >> j) & 1u) && (bj < 0 || run_lp[j] > bvv)) { bj = j; bvv = run_lp[j]; stok = top_tok[j]; sbeam = top_beam[j]; }
+    used |= 1u << bj;
+    new_score[i] = bvv;
+    const int32_t* srcp = run_old + (int64_t)sbeam * T;
     int32_t* dstp = run_new + (int64_t)i * T;
-    for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? top_tok[bj] : srcp[t];
+    for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? stok : srcp[t];
     if (lane == 0) {
-      next_tok[img * k + i] = top_tok[bj];
-      src_row[img * k + i] = img * k + top_beam[bj];
+      next_tok[img * k + i] = stok;
+      src_row[img * k + i] = img * k + sbeam;
     }
   }
 
   // (f) finished beams: merge the k finished with the 2k candidates, keep the best k (stable)
   const bool unsat = st.unsatisfied[img] != 0;
-  float m_sc[KM + K2];
+  float m_sc[k + k2];
+#pragma unroll
   for (int b = 0; b < k; ++b) m_sc[b] = st.fin_score[img * k + b];
+#pragma unroll
   for (int j = 0; j < k2; ++j) {
-    const bool just_fin = hits[j] && j < k;
+    const bool just_fin = ((hits >> j) & 1u) && j < k;
     float v = top_lp[j] / div_fin;
     v += unsat ? 0.f : kNeg;
     v += just_fin ? 0.f : kNeg;
     m_sc[k + j] = v;
   }
-  bool m_used[KM + K2];
-  for (int j = 0; j < k + k2; ++j) m_used[j] = false;
-  float f_sc[KM];
-  int f_len[KM];
-  uint8_t f_flag[KM];
+  unsigned m_used = 0u;
+  float f_sc[k];
+  int f_len[k];
+  unsigned f_flags = 0u;
+#pragma unroll
   for (int i = 0; i < k; ++i) {
     int bj = -1;
+    float bvv = 0.f;
+#pragma unroll
     for (int j = 0; j < k + k2; ++j)
-      if (!m_used[j] && (bj < 0 || m_sc[j] > m_sc[bj])) bj = j;
-    m_used[bj] = true;
-    f_sc[i] = m_sc[bj];
+      if (!((m_used >> j) & 1u) && (bj < 0 || m_sc[j] > bvv)) { bj = j; bvv = m_sc[j]; }
+    m_used |= 1u << bj;
+    f_sc[i] = bvv;
     int32_t* dstp = fin_new + (int64_t)i * T;
     if (bj < k) {
       const int32_t* srcp = fin_old + (int64_t)bj * T;
       for (int t = lane; t < T; t += 32) dstp[t] = srcp[t];
       f_len[i] = st.fin_len[img * k + bj];
-      f_flag[i] = st.fin_flag[img * k + bj];
+      f_flags |= (st.fin_flag[img * k + bj] ? 1u : 0u) << i;
     } else {
-      const int j = bj - k;
-      const int32_t* srcp = run_old + (int64_t)top_beam[j] * T;
-      for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? top_tok[j] : srcp[t];
+      int stok = 0, sbeam = 0;
+      bool fin = false;
+#pragma unroll
+      for (int j = 0; j < k2; ++j)
+        if (j == bj - k) { stok = top_tok[j]; sbeam = top_beam[j]; fin = ((hits >> j) & 1u) && j < k; }
+      const int32_t* srcp = run_old + (int64_t)sbeam * T;
+      for (int t = lane; t < T; t += 32) dstp[t] = t == cur_len ? stok : srcp[t];
       f_len[i] = cur_len + 1;
-      f_flag[i] = (hits[j] && j < k) ? 1 : 0;
+      f_flags |= (fin ? 1u : 0u) << i;
     }
   }
   __syncwarp();   // every lane has read the old per-image state before lane 0 overwrites it
   float fmin = f_sc[0];
+#pragma unroll
   for (int i = 0; i < k; ++i) {
     if (lane == 0) {
       st.fin_score[img * k + i] = f_sc[i];
       st.fin_len[img * k + i] = f_len[i];
-      st.fin_flag[img * k + i] = f_flag[i];
+      st.fin_flag[img * k + i] = (uint8_t)((f_flags >> i) & 1u);
       st.run_score[img * k + i] = new_score[i];
     }
     fmin = fminf(fmin, f_sc[i]);
@@ -428,31 +451,34 @@ __device__ __forceinline__ void beam_step_image(const BeamState& st, int img, in
   // (g) early-stop heuristic (early_stopping=False): can the best running beam still beat the worst finished?
   const float best_possible = new_score[0] / div_heur;
   bool any = false;
-  for (int i = 0; i < k; ++i) any = any || (best_possible > (f_flag[i] ? fmin : kNeg));
+#pragma unroll
+  for (int i = 0; i < k; ++i) any = any || (best_possible > (((f_flags >> i) & 1u) ? fmin : kNeg));
   if (lane == 0) st.unsatisfied[img] = (unsat && any) ? 1 : 0;
 }
 
-__global__ void beam_step_kernel(BeamState st, int B, int k, int T, int V, int cur_len, int eos, float div_fin,
-                                 float div_heur, const float* __restrict__ cand_lp, const int32_t* __restrict__ cand_idx,
-                                 int32_t* __restrict__ next_tok, int32_t* __restrict__ src_row, float* dbg_lp,
-                                 int32_t* dbg_tok, int32_t* dbg_beam) {
+template <int K>
+__global__ void __launch_bounds__(128) beam_step_kernel(BeamState st, int B, int T, int cur_len, int eos, float div_fin,
+                                                        float div_heur, const float* __restrict__ cand_lp,
+                                                        const int32_t* __restrict__ cand_idx, int32_t* __restrict__ next_tok,
+                                                        int32_t* __restrict__ src_row, float* dbg_lp, int32_t* dbg_tok,
+                                                        int32_t* dbg_beam) {
   pdl_trigger();
   pdl_wait();
   // the image's k sorted candidate lists (k * 2k <= 128 entries) are read once, lane-parallel, into shared memory; the
   // sequential k-way merge then runs on shared-memory latency instead of ten rounds of dependent L2 reads
-  __shared__ float s_lp[4][kMaxRowsPerImage * kMaxTopK];
-  __shared__ int32_t s_idx[4][kMaxRowsPerImage * kMaxTopK];
+  __shared__ float s_lp[4][2 * K * K];
+  __shared__ int32_t s_idx[4][2 * K * K];
   const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (img >= B) return;
-  const int n = k * 2 * k;
+  constexpr int n = 2 * K * K;
   for (int i = lane; i < n; i += 32) {
     s_lp[w][i] = cand_lp[(int64_t)img * n + i];
     s_idx[w][i] = cand_idx[(int64_t)img * n + i];
   }
   __syncwarp();
-  beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, s_lp[w], s_idx[w], next_tok, src_row, dbg_lp,
-                  dbg_tok, dbg_beam);
+  beam_step_image<K>(st, img, lane, T, cur_len, eos, div_fin, div_heur, s_lp[w], s_idx[w], next_tok, src_row, dbg_lp, dbg_tok,
+                     dbg_beam);
 }
 
 __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int T, int32_t* out_tok, int32_t* out_len,
@@ -460,7 +486,7 @@ __global__ void beam_finalize_kernel(BeamState st, int parity, int B, int k, int
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int img = i / T, t = i - img * T;
-  out_tok[i] = st.fin_seq[parity][((int64_t)img * k) * T + t];
+  out_tok[i] = (parity ? st.fin_seq[1] : st.fin_seq[0])[((int64_t)img * k) * T + t];
   if (t == 0) {
     out_len[img] = st.fin_len[img * k];
     out_score[img] = st.fin_score[img * k];
@@ -499,29 +525,6 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
   pdl_trigger();
   pdl_wait();
   gather_row(a, blockIdx.x, threadIdx.x, blockDim.x);
-}
-
-// Per-image fusion of the three bookkeeping kernels of a beam step (fused top-k path): the image's k rows are merged
-// from the vocabulary GEMM's records into k sorted candidate lists in shared memory (one warp per row), warp 0 runs
-// the HF beam step on them, then the whole CTA gathers the image's new rows (state reorder by back-pointer + embedding).
-// Beams reorder only inside an image, so no other CTA's results are needed.
-__global__ void __launch_bounds__(128) select_fused_kernel(const MergeArgs ma, const BeamState st, int k, int T, int cur_len,
-                                                           int eos, float div_fin, float div_heur, int32_t* next_tok,
-                                                           int32_t* src_row, float* dbg_lp, int32_t* dbg_tok,
-                                                           int32_t* dbg_beam, const GatherArgs ga, int do_gather) {
-  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
-  __shared__ float s_lp[kMaxRowsPerImage * kMaxTopK];
-  __shared__ int32_t s_idx[kMaxRowsPerImage * kMaxTopK];
-  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k2 = 2 * k;
-  for (int b = warp; b < k; b += 4) merge_row(ma, img * k + b, lane, s_pos[warp], s_lp + b * k2, s_idx + b * k2, nullptr);
-  __syncthreads();
-  if (warp == 0)
-    beam_step_image(st, img, lane, k, T, cur_len, eos, div_fin, div_heur, s_lp, s_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
-  if (!do_gather) return;
-  __threadfence_block();
-  __syncthreads();   // next_tok / src_row of this image's rows are visible to the whole CTA
-  for (int b = 0; b < k; ++b) gather_row(ga, img * k + b, threadIdx.x, blockDim.x);
 }
 
 __global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restrict__ feats, int L, int D,
@@ -627,9 +630,19 @@ int beam_step(const BeamState& st, int B, int k, int T, int V, int cur_len, int 
               int32_t* src_row, float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, cudaStream_t s) {
   CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage, CAPDEC_ERR_UNSUPPORTED, "beam_step: num_beams %d not in [1,%d]", k,
                  kMaxRowsPerImage);
+  (void)V;
   if (B == 0) return CAPDEC_OK;
-  CAPDEC_CHECK_CUDA(launch_k(beam_step_kernel, dim3(ceil_div(B, 4)), dim3(128), 0, s, true, st, B, k, T, V, cur_len, eos,
-                             len_div_finished, len_div_heuristic, cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam));
+#define CAPDEC_BEAM_CASE(KV)                                                                                              \
+  case KV:                                                                                                                \
+    CAPDEC_CHECK_CUDA(launch_k(beam_step_kernel<KV>, dim3(ceil_div(B, 4)), dim3(128), 0, s, true, st, B, T, cur_len, eos,  \
+                               len_div_finished, len_div_heuristic, cand_lp, cand_idx, next_tok, src_row, dbg_lp, dbg_tok, \
+                               dbg_beam));                                                                                \
+    break;
+  switch (k) {
+    CAPDEC_BEAM_CASE(1) CAPDEC_BEAM_CASE(2) CAPDEC_BEAM_CASE(3) CAPDEC_BEAM_CASE(4)
+    CAPDEC_BEAM_CASE(5) CAPDEC_BEAM_CASE(6) CAPDEC_BEAM_CASE(7) CAPDEC_BEAM_CASE(8)
+  }
+#undef CAPDEC_BEAM_CASE
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
@@ -638,23 +651,6 @@ int beam_finalize(const BeamState& st, int parity, int B, int k, int T, int32_t*
                   float* out_score, cudaStream_t s) {
   if (B == 0) return CAPDEC_OK;
   beam_finalize_kernel<<<ceil_div(B * T, 256), 256, 0, s>>>(st, parity, B, k, T, out_tok, out_len, out_score);
-  CAPDEC_LAUNCH_CHECK();
-  return CAPDEC_OK;
-}
-
-int select_fused(const float* part, const float* lse_part, int vocab, int n_total, int part_k, const BeamState& st, int B, int k,
-                 int T, int cur_len, int eos, float div_fin, float div_heur, int32_t* next_tok, int32_t* src_row,
-                 float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, const GatherArgs* ga, cudaStream_t s) {
-  const int rows = B * k, n_rec = tk_records(rows, n_total);
-  CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage && 2 * k <= tk_bucket(part_k) && n_rec <= kMergeMaxRecords, CAPDEC_ERR_INVALID,
-                 "select_fused: num_beams %d / record layout unsupported", k);
-  if (B == 0) return CAPDEC_OK;
-  MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, 2 * k, 0, 0, 0};
-  tk_schedule(rows, n_total, &ma.n_tiles, &ma.quota, &ma.block_rows);
-  GatherArgs g{};
-  if (ga) g = *ga;
-  select_fused_kernel<<<B, 128, 0, s>>>(ma, st, k, T, cur_len, eos, div_fin, div_heur, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam,
-                                        g, ga ? 1 : 0);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }

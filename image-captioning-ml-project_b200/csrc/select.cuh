@@ -59,11 +59,6 @@ struct GatherArgs {
 };
 int gather_rows(const GatherArgs& a, cudaStream_t s);
 
-// fused per-image form of topk_merge + beam_step + gather_rows for the fused top-k path (ga == nullptr: no gather, last step)
-int select_fused(const float* part, const float* lse_part, int vocab, int n_total, int part_k, const BeamState& st, int B, int k,
-                 int T, int cur_len, int eos, float div_fin, float div_heur, int32_t* next_tok, int32_t* src_row,
-                 float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, const GatherArgs* ga, cudaStream_t s);
-
 // mean over regions: out[b,:] = mean_l feats[b,l,:]
 int mean_regions(const float* feats, int B, int L, int D, float* out, cudaStream_t s);
 // the same mean, fused with writing the hi/lo operand copies of feats ([B*L, D], row pitch split.ld) in one pass
