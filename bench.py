@@ -361,6 +361,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         out = one_step()
     barrier()
+    # host-side cost of enqueuing one decode (126 launches + tensor-map encodes) against its device time: when the
+    # enqueue returns well before the GPU finishes, launch overhead is hidden and a CUDA graph has nothing to remove
+    t0 = time.perf_counter()
+    one_step()
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
 
     # ---- timed region: device-resident features, CUDA events on the launching stream
     eng.stage_timing(True)
@@ -424,7 +430,8 @@ def main():
         e2e_ms, host_out = time_e2e(fh)
         local_tok = out["tokens"][lo:hi] if world > 1 else out["tokens"]
         same = bool(torch.equal(host_out["tokens"], local_tok.cpu()))
-        chunk = args.chunk if args.chunk > 0 else 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        chunk = args.chunk if args.chunk > 0 else 2 * sms
         e2e = {"value": N_total / (e2e_ms / 1000.0), "unit": "images/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(fh.numel() * 4) * world, "d2h_bytes_per_step": int(B * MAXLEN * 4 + B * 8) * world,
                "host_feature_format": "fp32 [B,196,2048] (the reference's decoder input)", "chunk_images": chunk,
@@ -434,7 +441,7 @@ def main():
         fh16 = fh.bfloat16().pin_memory()
         ms16, ho16 = time_e2e(fh16)
         e2e_formats["bf16"] = {"value": N_total / (ms16 / 1000.0), "unit": "images/s", "ms_per_step": ms16,
-                               "h2d_bytes_per_step": int(fh16.numel() * 2) * world,
+                               "h2d_bytes_per_step": int(fh16.numel() * 2) * world, "chunk_images": args.chunk if args.chunk > 0 else 4 * sms,
                                "captions_identical_to_fp32_features": float((ho16["tokens"] == host_out["tokens"]).all(dim=1).float().mean())}
         del fh16
         if world == 1:
@@ -517,7 +524,7 @@ def main():
                        "parallelism": f"image-sharded x{world}, all-gather of captions (capdec_b200.sharding.gather_captions)",
                        "api": "capdec_b200.Decoder.beam_search (drop-in for models/decoder.py::Decoder)",
                        "l2_policy": f"inputs ({feats.numel() * 4 / 1e9:.1f} GB/GPU) larger than L2, no flush"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks.summary(),
             "roofline": attention_roofline(stage, B, tile_fmt),
             "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in stage.items()},

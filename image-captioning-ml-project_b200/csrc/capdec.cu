@@ -672,7 +672,6 @@ int step_transformer(const capdec_handle* h, Session& S, const uint8_t* mask, in
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
-      a.cache_bf16 = c.precision == CAPDEC_PREC_BF16 ? 1 : 0;   // single-pass bf16 mode: K / V cached as bf16 (half the bytes)
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, tl(l, "self_attn.out_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -758,7 +757,6 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
       a.scale = (float)(1.0 / sqrt((double)(H / heads))); a.out = S.tsa; a.ld_out = H; a.out_split = S.msa;
       a.rows = rows; a.H = H; a.heads = heads; a.T = S.T; a.t = t;
       a.key_tok = S.key_tok; a.ld_key_tok = S.ld_key_tok; a.key_pad = S.key_pad;
-      a.cache_bf16 = c.precision == CAPDEC_PREC_BF16 ? 1 : 0;   // single-pass bf16 mode: K / V cached as bf16 (half the bytes)
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
@@ -1428,9 +1426,11 @@ static int decode_beam_host_impl(capdec_handle* h, const void* feats_host, int l
   if (B == 0) return CAPDEC_OK;
   const capdec_config& c = h->cfg;
   if (chunk <= 0) {
-    // default: two images per SM -- whole rounds of the persistent attention kernel and about one wave of gate-GEMM tiles
-    // per step, which measured best on B200 (126 ms vs 129 ms at 512 for 4096 images; the copy alone is 118.5 ms)
-    chunk = 2 * num_sms();
+    // default: whole rounds of the persistent attention kernel.  fp32 sources are PCIe-bound (6.6 GB per 4096 images at
+    // ~55 GB/s): two images per SM keep the exposed first copy / last decode short (124 ms vs 128 ms at four per SM).
+    // bf16 / fp16 / p24 sources halve the copy, so the call becomes decode-bound and larger chunks -- more efficient
+    // GEMM waves per step -- win: measured 84.0 / 74.5 / 74.6 / 76.4 ms at 2 / 4 / 6 / 8 images per SM for bf16.
+    chunk = (dtype == CAPDEC_DT_F32 ? 2 : 4) * num_sms();
   }
   if (chunk > B) chunk = B;
   // One in-flight call per handle: the GEMM activation scratch and the lazily split weights are handle state, and this

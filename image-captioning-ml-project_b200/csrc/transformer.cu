@@ -5,8 +5,6 @@
 // projections of the image regions reuses mha_attention_kernel (attn_mha.cu); all dense layers go through gemm().
 #include <stdlib.h>
 
-#include <cuda_bf16.h>
-
 #include "transformer.cuh"
 
 namespace capdec {
@@ -280,183 +278,6 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   }
 }
 
-// Per-IMAGE form of the cached self-attention: one CTA per image, one warp per head, the warp walks the image's KB rows
-// (beams / samples) together.  Against the per-row kernel above it
-//   * reads the per-image prefix keys / values (GPT-2's 10-token image prefix: half of the ~20 keys a row sees on
-//     average) ONCE per image and head instead of once per row,
-//   * keeps KB independent cache loads in flight per lane (the rows' physical cache rows differ after a beam reorder),
-//   * optionally stores the cache as bf16 (BF16C; the single-pass bf16 mode: its consumers round K / V products to bf16
-//     operands anyway) -- half the cache bytes.  The current position's K / V are taken from this step's fp32 qkv.
-// Traffic per image, layer and step at GPT-2's shape (k = 5, P = 10, t = 10): 600 KB (per-row, fp32) -> 360 KB -> 210 KB (bf16).
-template <typename CT> __device__ __forceinline__ float4 cache_ld4(const CT* p);
-template <> __device__ __forceinline__ float4 cache_ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
-template <> __device__ __forceinline__ float4 cache_ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
-  const uint2 w = *reinterpret_cast<const uint2*>(p);
-  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
-                     __uint_as_float(w.y & 0xffff0000u));
-}
-__device__ __forceinline__ void cache_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void cache_st4(__nv_bfloat16* p, float4 v) {
-  float r0, r1;
-  uint2 w;
-  w.x = pack_bf16x2_(v.x, v.y, &r0, &r1);
-  w.y = pack_bf16x2_(v.z, v.w, &r0, &r1);
-  *reinterpret_cast<uint2*>(p) = w;
-}
-__device__ __forceinline__ float cache_ld1(const float* p) { return *p; }
-__device__ __forceinline__ float cache_ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-
-template <int KB, typename CT>
-__global__ void self_attn_image_kernel(const SelfAttnArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) float s_mem[];
-  const int img = blockIdx.x, r0 = img * KB;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = a.H, d = H / a.heads, d4 = d >> 2, T = a.T, t = a.t, P = a.n_prefix;
-  float* s_q = s_mem;                       // [KB][H]   queries of the image's rows
-  float* s_sc = s_mem + KB * H;             // [heads][KB][128]  scores, then softmax weights
-  CT* ck = reinterpret_cast<CT*>(a.cache_k);
-  CT* cv = reinterpret_cast<CT*>(a.cache_v);
-  // stage the queries; append this position's K / V to the cache (read back only by LATER steps)
-  for (int i = threadIdx.x; i < KB * (H >> 2); i += blockDim.x) {
-    const int b = i / (H >> 2), c = i - b * (H >> 2);
-    const float* qkv = a.qkv + (int64_t)(r0 + b) * a.ld_qkv;
-    reinterpret_cast<float4*>(s_q + b * H)[c] = reinterpret_cast<const float4*>(qkv)[c];
-    cache_st4(ck + ((int64_t)(r0 + b) * T + t) * H + 4 * c, reinterpret_cast<const float4*>(qkv + H)[c]);
-    cache_st4(cv + ((int64_t)(r0 + b) * T + t) * H + 4 * c, reinterpret_cast<const float4*>(qkv + 2 * H)[c]);
-  }
-  __syncthreads();
-  const int hd = warp;
-  if (hd >= a.heads) return;
-  const int n_keys = P + t + 1;
-  // ---- pass 1: scores.  GL lanes read one key's head slice (128-bit loads), 32 / GL keys per round
-  const int GL = d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
-  const int kpr = 32 / GL, sub = lane % GL, grp = lane / GL;
-  float* sc = s_sc + (size_t)hd * KB * 128;
-  float4 qv[KB];
-#pragma unroll
-  for (int b = 0; b < KB; ++b)
-    qv[b] = sub < d4 ? reinterpret_cast<const float4*>(s_q + b * H + hd * d)[sub] : make_float4(0.f, 0.f, 0.f, 0.f);
-  auto dot4 = [](const float4& x, const float4& y) { return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))); };
-  for (int p0 = 0; p0 < P; p0 += kpr) {       // prefix keys: one load serves the image's KB rows
-    const int p = p0 + grp;
-    const bool ok = p < P && sub < d4;
-    const float4 kv = ok ? reinterpret_cast<const float4*>(a.prefix_k + ((int64_t)img * P + (ok ? p : 0)) * H + hd * d)[sub]
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      float part = dot4(qv[b], kv);
-      for (int o = GL >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (sub == 0 && p < P) sc[b * 128 + p] = part * a.scale;
-    }
-  }
-  for (int pos0 = 0; pos0 < t; pos0 += kpr) {   // cached keys: row b's position pos lives in physical row anc[row][pos]
-    const int pos = pos0 + grp;
-    const bool ok = pos < t && sub < d4;
-    float4 kv[KB];
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      const int prow = (ok && a.anc) ? a.anc[(int64_t)(r0 + b) * T + pos] : r0 + b;
-      kv[b] = ok ? cache_ld4<CT>(ck + ((int64_t)prow * T + pos) * H + hd * d + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      float part = dot4(qv[b], kv[b]);
-      for (int o = GL >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (sub == 0 && pos < t) sc[b * 128 + P + pos] = part * a.scale;
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < KB; ++b) {               // the current position: K from this step's qkv
-    const float4 kv = (grp == 0 && sub < d4) ? reinterpret_cast<const float4*>(a.qkv + (int64_t)(r0 + b) * a.ld_qkv + H + hd * d)[sub]
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    float part = dot4(qv[b], kv);
-    for (int o = GL >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) sc[b * 128 + P + t] = part * a.scale;
-  }
-  __syncwarp();
-  // ---- softmax across the lanes (lane = key), weights written back in place
-#pragma unroll
-  for (int b = 0; b < KB; ++b) {
-    float x[4];
-    float m = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = lane + 32 * i;
-      x[i] = p < n_keys ? sc[b * 128 + p] : -INFINITY;
-      if (a.key_tok && p < n_keys && p >= P && a.key_tok[(int64_t)(r0 + b) * a.ld_key_tok + (p - P)] == a.key_pad) x[i] = -INFINITY;
-      m = fmaxf(m, x[i]);
-    }
-    m = warp_max(m);
-    float l = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { x[i] = expf(x[i] - m); l += x[i]; }
-    l = warp_sum(l);
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = lane + 32 * i;
-      if (p < n_keys) sc[b * 128 + p] = x[i] * inv;
-    }
-  }
-  __syncwarp();
-  // ---- pass 2: weighted values, lane = output element e = lane + 32 j (head_dim <= 128)
-  float acc[KB][4];
-#pragma unroll
-  for (int b = 0; b < KB; ++b)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
-  for (int p = 0; p < P; ++p) {                // prefix values, shared by the rows
-    const float* vp = a.prefix_v + ((int64_t)img * P + p) * H + hd * d;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const int e = lane + 32 * j; v[j] = e < d ? vp[e] : 0.f; }
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      const float w = sc[b * 128 + p];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[b][j] = fmaf(w, v[j], acc[b][j]);
-    }
-  }
-  for (int pos0 = 0; pos0 < t; pos0 += 2) {    // cached values: two positions x KB rows of loads in flight
-    float v[2][KB][4], w[2][KB];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int pos = pos0 + u;
-#pragma unroll
-      for (int b = 0; b < KB; ++b) {
-        const bool ok = pos < t;
-        const int prow = (ok && a.anc) ? a.anc[(int64_t)(r0 + b) * T + pos] : r0 + b;
-        const CT* vp = cv + ((int64_t)prow * T + (ok ? pos : 0)) * H + hd * d;
-        w[u][b] = ok ? sc[b * 128 + P + pos] : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const int e = lane + 32 * j; v[u][b][j] = (ok && e < d) ? cache_ld1(vp + e) : 0.f; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int b = 0; b < KB; ++b)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[b][j] = fmaf(w[u][b], v[u][b][j], acc[b][j]);
-  }
-#pragma unroll
-  for (int b = 0; b < KB; ++b) {               // current position's value + store
-    const float* vp = a.qkv + (int64_t)(r0 + b) * a.ld_qkv + 2 * H + hd * d;
-    const float w = sc[b * 128 + P + t];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = lane + 32 * j;
-      if (e < d) {
-        const float o = fmaf(w, vp[e], acc[b][j]);
-        a.out[(int64_t)(r0 + b) * a.ld_out + hd * d + e] = o;
-        split_store1(a.out_split, r0 + b, hd * d + e, o);
-      }
-    }
-  }
-}
-
 // anc_new[r][p] = (p < t_next) ? (p == t_next-1 ? src[r] : anc_old[src[r]][p]) : -  ; written for p < t_next
 __global__ void reorder_ancestors_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ anc_old,
                                          int32_t* __restrict__ anc_new, int rows, int T, int t_done) {
@@ -488,39 +309,14 @@ int add_layernorm(const float* x, const float* y, const float* gamma, const floa
   return CAPDEC_OK;
 }
 
-template <typename CT>
-static int launch_self_attn_image(const SelfAttnArgs& a, size_t smem, cudaStream_t s) {
-#define CAPDEC_SAI(KBV)                                                                                                   \
-  case KBV: {                                                                                                             \
-    auto kern = self_attn_image_kernel<KBV, CT>;                                                                          \
-    if (smem > 48 * 1024) CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    CAPDEC_CHECK_CUDA(launch_k(kern, dim3(a.rows / KBV), dim3(32 * a.heads), smem, s, true, a));                          \
-    break;                                                                                                                \
-  }
-  switch (a.rows_per_image) {
-    CAPDEC_SAI(1) CAPDEC_SAI(2) CAPDEC_SAI(3) CAPDEC_SAI(4) CAPDEC_SAI(5) CAPDEC_SAI(6) CAPDEC_SAI(7) CAPDEC_SAI(8)
-    default: return CAPDEC_ERR_UNSUPPORTED;
-  }
-#undef CAPDEC_SAI
-  CAPDEC_LAUNCH_CHECK();
-  return CAPDEC_OK;
-}
-
 int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
   CAPDEC_REQUIRE(a.heads >= 1 && a.heads <= 32 && a.H % a.heads == 0 && a.H / a.heads <= 128, CAPDEC_ERR_UNSUPPORTED,
                  "self_attn_decode: heads=%d head_dim=%d unsupported (head_dim <= 128, heads <= 32)", a.heads,
                  a.heads ? a.H / a.heads : 0);
   if (a.rows == 0) return CAPDEC_OK;
   const int n_keys = a.n_prefix + a.t + 1;
-  // per-image kernel: every shape of the path (prefix 10 + max_len <= 50 keys, head_dim 64 / 96, up to 8 rows per image)
-  const int k = a.rows_per_image;
-  const size_t smem_img = ((size_t)k * a.H + (size_t)a.heads * k * 128) * sizeof(float);
-  if (k >= 1 && k <= 8 && a.rows % k == 0 && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && a.H % 4 == 0 &&
-      smem_img <= 200 * 1024) {
-    return a.cache_bf16 ? launch_self_attn_image<__nv_bfloat16>(a, smem_img, s) : launch_self_attn_image<float>(a, smem_img, s);
-  }
-  CAPDEC_REQUIRE(!a.cache_bf16, CAPDEC_ERR_UNSUPPORTED, "self_attn_decode: the bf16 cache exists for the per-image kernel only");
-  if (n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
+  static const bool old_form = getenv("CAPDEC_SELFATTN_ONLINE") != nullptr;
+  if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
     const size_t smem = ((size_t)a.H + (size_t)a.heads * 128) * sizeof(float);
     const int d4 = a.H / a.heads / 4;
 #define CAPDEC_SA_LAUNCH(NKV)                                                                               \

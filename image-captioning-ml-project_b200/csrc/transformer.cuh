@@ -17,7 +17,6 @@ struct SelfAttnArgs {
   // optional (teacher-forced pass): cache position p of row r is masked as a KEY when key_tok[r*ld_key_tok + p] == key_pad
   // (nn.TransformerDecoder tgt_key_padding_mask, decoders.py:405; HF attention_mask, decoders.py:581)
   const int32_t* key_tok; int64_t ld_key_tok; int key_pad;
-  int cache_bf16;                        // cache_k / cache_v hold bf16 [R, T, H] (single-pass bf16 mode) instead of fp32
 };
 
 int embed_pos(const int32_t* tok, const float* emb, const float* pos_row, float* x, int rows, int H, cudaStream_t s,
