@@ -167,7 +167,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_init_bar = tmem_empty_bar + 2;    // [2]  stream-K: accumulator pre-loaded with the predecessor's partial sum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_init_bar + 2);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,6 +191,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   constexpr int BK = KIND == KIND_BF16 ? 64 : 32;   // elements per 128-byte K block
   const int num_kb = (p.K + BK - 1) / BK;
   constexpr uint32_t kTmemCols = 2 * BN;           // 256 or 512: a power of two >= 32
+  // ---- work items.  Default: whole tiles in the order above.  Stream-K (p.sk_part != nullptr; never with EPI_TOPK): the
+  // launch's num_tiles * num_kb K blocks are cut into num_groups EQUAL contiguous ranges, so a shape whose tile count is
+  // not a multiple of the resident CTA groups (80 gate-GEMM tiles on 74 pairs at 2560 rows: two waves, the second 8 %
+  // full) costs total / groups instead of ceil(tiles / groups) tile times.  A range covers the tail of one tile, whole
+  // tiles, and the head of another; a group walks its range BACKWARDS: the head part first (its raw accumulator goes to a
+  // scratch slot + an epoch-tagged flag per epilogue warp), the tail part last (its epilogue adds the parts other groups
+  // left for that tile -- they were those groups' FIRST items, so the wait is short and can never deadlock: every group
+  // of the persistent grid is resident).
+  const bool sk = EPI != EPI_TOPK && p.sk_part != nullptr;
+  const int64_t sk_total = (int64_t)num_tiles * num_kb;
+  auto sk_lo = [&](int g) { return (int)(sk_total * g / num_groups); };
+  struct Work { int tile, kb0, kb1; };
+  // cursor: next tile index (default) or the exclusive upper end of what is left of the range (stream-K)
+  const int cursor0 = sk ? sk_lo(group + 1) : tile_begin;
+  const int sk_begin = sk ? sk_lo(group) : 0;
+  auto next_work = [&](int& cursor, Work& w) -> bool {
+    if (sk) {
+      if (cursor <= sk_begin) return false;
+      w.tile = (cursor - 1) / num_kb;
+      const int tb = w.tile * num_kb, s0 = max(sk_begin, tb);
+      w.kb0 = s0 - tb; w.kb1 = cursor - tb;
+      cursor = s0;
+      return true;
+    }
+    if (cursor >= tile_end) return false;
+    w.tile = cursor; w.kb0 = 0; w.kb1 = num_kb;
+    cursor += tile_step;
+    return true;
+  };
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -199,7 +229,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
     }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * CG); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * CG); mbar_init(&tmem_init_bar[b], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -221,11 +251,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // ===== TMA producer (both CTAs of a pair: own 128 rows of A, own BN/CG rows of W) =====
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter across tiles -> ring stage / phase
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      int cursor = cursor0;
+      Work wk;
+      while (next_work(cursor, wk)) {
+        const int tile = wk.tile;
         const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
         const int a_row = m_tile * TM + (int)rank * BM;
         const int w_row = n_tile * BN + (int)rank * (BN / CG);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -262,12 +295,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       };
       auto commit = [&](uint64_t* bar) { if (CG == 2) tcgen05_commit_pair(bar); else tcgen05_commit(bar); };
       uint32_t it = 0, local = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+      int cursor = cursor0;
+      Work wk;
+      for (; next_work(cursor, wk); ++local) {
         const uint32_t ab = local & 1;                       // accumulator buffer
         mbar_wait(&tmem_empty_bar[ab], ((local >> 1) & 1) ^ 1);  // the epilogue warps (of both CTAs) drained this buffer
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + ab * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const bool cont = sk && wk.kb0 > 0;      // stream-K: continue the sum the epilogue warps loaded into this buffer
+        if (cont) { mbar_wait(&tmem_init_bar[ab], 0); tcgen05_fence_after(); }   // (at most one such item per group and launch)
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -279,7 +316,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
           for (int k = 0; k < kRowBytes / 32; ++k) {
             const uint32_t koff = k * 32;  // one MMA consumes 32 bytes along K (8 tf32 / 16 bf16) inside the 128-byte swizzle span
-            const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+            const uint32_t first = (kb == wk.kb0 && k == 0 && !cont) ? 0u : 1u;
             if (TERMS == 3) {
               mma(tmem_d, make_smem_desc(a_lo + koff), make_smem_desc(w_hi + koff), first);
               mma(tmem_d, make_smem_desc(a_hi + koff), make_smem_desc(w_lo + koff), 1u);
@@ -289,7 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             }
           }
           commit(&empty_bar[s]);                           // frees this shared-memory stage (in both CTAs) when the MMAs retire
-          if (kb == num_kb - 1) commit(&tmem_full_bar[ab]);  // accumulator complete
+          if (kb == wk.kb1 - 1) commit(&tmem_full_bar[ab]);  // accumulator (of this item's K range) complete
         }
       }
     }
@@ -332,12 +369,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
       for (int j = 0; j < PS / 4; ++j) dst[j] = make_float4(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3]);
     };
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+    int cursor = cursor0;
+    Work wk;
+    for (; next_work(cursor, wk); ++local) {
+      const int tile = wk.tile;
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
       const uint32_t ab = local & 1;
+      const int m = m_tile * TM + (int)rank * BM + q * 32 + lane;   // accumulator row == TMEM lane of this CTA
+      // stream-K roles of this item.  A part that starts inside the tile (kb0 > 0) CONTINUES the accumulation of the group
+      // before this one: its epilogue warps copy that group's published accumulator into this item's TMEM buffer
+      // (tcgen05.st) before the MMA warp issues with accumulate = 1, so the tile is summed in exactly the order a single
+      // group would have used -- results stay bit-identical whatever the batch size / schedule.  A part that ends before
+      // the tile's last K block (kb1 < num_kb) publishes its raw accumulator instead of running the epilogue.  Slot layout
+      // (per group and CTA of the pair): [32-column chunk][column][row of the CTA]: lanes touch contiguous floats.
+      const bool sk_publish = EPI != EPI_TOPK && sk && wk.kb1 < num_kb;
+      if (EPI != EPI_TOPK && sk && wk.kb0 > 0) {
+        if (lane == 0) {
+          const volatile int* f = p.sk_flag + ((size_t)(group - 1) * CG + rank) * 8 + (warp - 2);
+          for (uint32_t spin = 0; *f != p.sk_epoch; ++spin) if (spin > kSpinLimit) __trap();
+          __threadfence();
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
+          const float* src = p.sk_part + (((size_t)(group - 1) * CG + rank) * (BN / 32) + (c0 >> 5)) * (32 * BM) + q * 32 + lane;
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__ldcg(src + j * BM));
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0);
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+              "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+              :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                 "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                 "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+              : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {       // accumulator buffer `ab` of this CTA holds the predecessor's sum for this warp's lanes / columns
+          if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_init_bar[ab]), 0));
+          else asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_init_bar[ab])) : "memory");
+        }
+      }
       mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
       tcgen05_fence_after();
-      const int m = m_tile * TM + (int)rank * BM + q * 32 + lane;   // accumulator row == TMEM lane of this CTA
       if constexpr (EPI == EPI_TOPK) {
         if (m_tile != cur_block) {
           if (cur_block >= 0) tk_flush(cur_block);
@@ -375,6 +454,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           if (lane == 0) {
             if (CG == 2) mbar_arrive_cluster(leader_empty_bar0 + ab * 8);
             else asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
+          }
+        }
+        if constexpr (EPI != EPI_TOPK) {
+          if (sk_publish) {
+            float* dst = p.sk_part + (((size_t)group * CG + rank) * (BN / 32) + (c0 >> 5)) * (32 * BM) + q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(dst + j * BM, __uint_as_float(v[j]));
+            if (c0 + 32 >= (half + 1) * HN) {       // this warp's share of the part is written: publish it
+              __threadfence();
+              __syncwarp();
+              if (lane == 0) *(volatile int*)(p.sk_flag + ((size_t)group * CG + rank) * 8 + (warp - 2)) = p.sk_epoch;
+            }
+            continue;
           }
         }
         const int n0 = n_tile * BN + c0;
@@ -686,7 +778,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
       configured[dev_].store(true);                                                                               \
     }                                                                                                             \
     const int max_groups = tc_max_groups(CG);                                                                     \
-    const int groups = num_tiles < max_groups ? num_tiles : max_groups;                                           \
+    const int groups = (num_tiles < max_groups && !g.sk_part) ? num_tiles : max_groups;                           \
     cudaLaunchConfig_t cfg = {};                                                                                  \
     cfg.gridDim = dim3(groups * CG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;  \
     cudaLaunchAttribute at[2];                                                                                    \
@@ -861,6 +953,34 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     GemmArgs g = a;
     g.M = mc;
     g.K = pre ? K : Kp;
+    // stream-K when whole tiles would leave the last wave mostly idle (see the kernel): needs the handle's scratch
+    g.sk_part = nullptr; g.sk_flag = nullptr; g.sk_epoch = 0;
+    static const bool no_sk = getenv("CAPDEC_NO_STREAMK") != nullptr;   // A/B switch for the measurements in DESIGN.md
+    if (h && epilogue != EPI_TOPK && !no_sk) {
+      const int G = tc_max_groups(cg);
+      const int tiles = ceil_div(a.N, bn) * ceil_div(mc, BM * cg);
+      const int num_kb = ceil_div(g.K, kind == KIND_BF16 ? 64 : 32);
+      const int waves = ceil_div(tiles, G);
+      // cost model in K-block times: whole tiles take waves * num_kb; stream-K takes the even share plus ~30 blocks' worth of
+      // un-overlapped part hand-over (publish the head part, copy the predecessor's sum into TMEM) -- measured on B200 for the
+      // legacy gate GEMM (K = 2560): 80.1 vs 91.1 us at 2560 rows, 128.7 vs 136.1 at 5120, 244.8 vs 236.0 at 10240 rows
+      if (tiles > G && (int64_t)waves * num_kb * G > (int64_t)tiles * num_kb + (int64_t)30 * G) {
+        if (!h->sk_part) {
+          cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+          CAPDEC_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
+          if (cap == cudaStreamCaptureStatusNone) {
+            const size_t slots = (size_t)tc_max_groups(2) * 2 > (size_t)tc_max_groups(1) ? (size_t)tc_max_groups(2) * 2 : (size_t)tc_max_groups(1);
+            CAPDEC_CHECK_CUDA(cudaMalloc((void**)&h->sk_part, slots * BM * bn * sizeof(float)));
+            CAPDEC_CHECK_CUDA(cudaMalloc((void**)&h->sk_flag, slots * 8 * sizeof(int)));
+            CAPDEC_CHECK_CUDA(cudaMemsetAsync(h->sk_flag, 0, slots * 8 * sizeof(int), s));
+          }
+        }
+        if (h->sk_part) {
+          h->sk_epoch = (h->sk_epoch % 0x3fffffff) + 1;
+          g.sk_part = h->sk_part; g.sk_flag = h->sk_flag; g.sk_epoch = h->sk_epoch;
+        }
+      }
+    }
     g.C = a.C + (int64_t)m0 * a.ldc;
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
@@ -891,6 +1011,9 @@ void gemm_tc_release(capdec_handle* h) {
   h->tc_weights.clear();
   if (h->tc_scratch) cudaFree(h->tc_scratch);
   h->tc_scratch = nullptr; h->tc_scratch_bytes = 0;
+  if (h->sk_part) cudaFree(h->sk_part);
+  if (h->sk_flag) cudaFree(h->sk_flag);
+  h->sk_part = nullptr; h->sk_flag = nullptr;
 }
 
 }  // namespace capdec

@@ -55,6 +55,10 @@ struct capdec_handle {
   mutable std::map<const float*, float*> tc_weights;
   mutable float* tc_scratch = nullptr;
   mutable size_t tc_scratch_bytes = 0;
+  // stream-K: one accumulator-part slot per CTA of the persistent grid + epoch-tagged flags (8 epilogue warps per CTA)
+  mutable float* sk_part = nullptr;
+  mutable int* sk_flag = nullptr;
+  mutable int sk_epoch = 0;
 
   const DevTensor* find(const std::string& n) const {
     auto it = w.find(n);

@@ -140,3 +140,30 @@ def test_config5_scst_rollout_512_images(cuda):
     rows = tok.view(B, S + 1, -1)
     distinct = (rows[:, 0] != rows[:, 1]).any(dim=1).float().mean().item()
     assert distinct > 0.9, distinct
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3", "bf16"])
+def test_stream_k_gemm_keeps_batch_invariance(cuda, precision):
+    """At 512 images (2560 rows) the gate GEMM has 80 tiles for 74 resident CTA pairs and runs as stream-K: tiles are cut
+    at K-block boundaries between CTA groups, the later part CONTINUES the earlier part's accumulator (copied back into
+    TMEM), so every output is summed in the same order as by one group.  The captions must therefore equal, bit for bit,
+    those of the same images decoded in batches small enough for whole-tile scheduling -- the property the N-GPU sharded
+    decode relies on (bench.py asserts gathered == single-GPU)."""
+    B, k, T, V = 512, 5, 20, 10000
+    m, _ = legacy_weights(V, 0)
+    m.precision = precision
+    m = m.to(cuda)
+    enc = _rand((B, 196, 2048), 9, cuda, relu=True)
+    full = m.beam_search(enc, beam_size=k, max_length=T, trace=True)
+    for lo, hi in ((0, 256), (256, 512), (100, 164)):
+        part = m.beam_search(enc[lo:hi].contiguous(), beam_size=k, max_length=T, trace=True)
+        assert torch.equal(part["tokens"], full["tokens"][lo:hi]), (precision, lo)
+        assert torch.equal(part["scores"], full["scores"][lo:hi]), (precision, lo)
+        assert torch.equal(part["top_logprob"], full["top_logprob"][:, lo:hi]), (precision, lo)
+    # and at 1024 / 2048 images (160 / 320 tiles: 3 / 5 waves on 74 pairs, also stream-K)
+    big = _rand((2048, 196, 2048), 10, cuda, relu=True)
+    a = m.beam_search(big, beam_size=k, max_length=T)
+    b = m.beam_search(big[:1024].contiguous(), beam_size=k, max_length=T)
+    c = m.beam_search(big[1024:1280].contiguous(), beam_size=k, max_length=T)
+    assert torch.equal(b["tokens"], a["tokens"][:1024]) and torch.equal(b["scores"], a["scores"][:1024])
+    assert torch.equal(c["tokens"], a["tokens"][1024:1280]) and torch.equal(c["scores"], a["scores"][1024:1280])
