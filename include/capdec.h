@@ -13,7 +13,10 @@
  *     stated; all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as
  *     void*), no hidden synchronisation except in the *_host entry points.
  *   - the caller owns inputs, outputs and the workspace; the handle owns only packed weight
- *     copies.  A handle is not thread-safe.
+ *     copies and GEMM scratch.  A handle is not thread-safe and carries ONE call in flight at a time:
+ *     enqueue the next call on the same stream, or synchronise first (the *_host entry points drain
+ *     the device before they start, so they may follow an asynchronous call directly).  Handles bind
+ *     to the device that is current at capdec_create; one process may hold handles on several devices.
  *   - there is NO CPU fallback: without a CUDA device the calls fail with CAPDEC_ERR_CUDA.
  */
 #ifndef CAPDEC_H

@@ -63,8 +63,8 @@ if "c3" in which:
     ms, nl = timeit(lambda: m.generate(ef, 20, num_beams=3))
     out["c3_transformer_beam3_2048img_bf16x3"] = {"ms": ms, "images_per_s": 2048 / ms * 1e3, "launches": nl,
                                                   "stage_ms": stage(m, lambda: m.generate(ef, 20, num_beams=3))}
-if "c4" in which:
-    for prec in ("bf16", "bf16x3"):
+if "c4" in which or "c4only" in which:
+    for prec in (("bf16",) if "c4only" in which else ("bf16", "bf16x3")):
         m, _ = gpt2_decoder(H=768, layers=12, heads=12, V=50257, max_length=64); m.precision = prec; m = m.to(dev)
         ef = {"pooled_features": rnd((1024, 768), 6)}
         ms, nl = timeit(lambda: m.generate(ef, 20, num_beams=5))
