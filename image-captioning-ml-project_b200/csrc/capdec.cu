@@ -1176,6 +1176,16 @@ static int decode_beam_impl(capdec_handle* h, const float* feats, const TileSet*
     const float div_heur = div_fin;
     const size_t o = (size_t)(cur_len - 1) * B * k2;
     const bool more = cur_len + 1 < T;
+    if (S.fuse_k > 0 && !is_tf_family(h) && B <= kFusedSelectMaxImages) {
+      // small batches: candidate merge + beam bookkeeping + state reorder / embedding gather of an image in one CTA
+      GatherArgs ga{};
+      if (more) build_gather(h, S, S.src_row, nullptr, 0, -1, true, &ga);
+      StageScope sc(h, STAGE_BEAM, s);
+      CAPDEC_RETURN_IF(select_fused(S.tk_part, S.tk_lse, c.vocab_size, S.tk_ntotal, S.fuse_k, S.beam, B, k, T, cur_len,
+                                    c.eos_token_id, div_fin, div_heur, S.next_tok, S.src_row, dbg_lp ? dbg_lp + o : nullptr,
+                                    dbg_tok ? dbg_tok + o : nullptr, dbg_beam ? dbg_beam + o : nullptr, more ? &ga : nullptr, s));
+      continue;
+    }
     { StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(select_topk(h, S, k2, S.cand_lp, S.cand_idx, s)); }
     { StageScope sc(h, STAGE_BEAM, s);

@@ -527,6 +527,36 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const GatherArgs a) {
   gather_row(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
+// Per-image fusion of the three bookkeeping kernels of a beam step (fused top-k path) for SMALL batches, where each of
+// them sits on its launch-latency floor (15 + 16 + 10 us at 512 images): the image's k rows are merged from the
+// vocabulary GEMM's records into k sorted candidate lists in shared memory (one warp per row), warp 0 runs the HF beam
+// step on them, then the whole CTA gathers the image's new rows (state reorder by back-pointer + embedding).  Beams
+// reorder only inside an image, so no other CTA's results are needed.  From 1024 images up the three specialised kernels
+// win (the phases serialise inside a CTA), so the launcher uses this form only up to kFusedSelectMaxImages (select.cuh).
+template <int K>
+__global__ void __launch_bounds__(128) select_fused_kernel(const MergeArgs ma, const BeamState st, int T, int cur_len, int eos,
+                                                           float div_fin, float div_heur, int32_t* next_tok, int32_t* src_row,
+                                                           float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam,
+                                                           const GatherArgs ga, int do_gather) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ uint8_t s_pos[4][kMergeMaxRecords];
+  __shared__ float s_stage[4][kMergeStageFloats];
+  __shared__ float s_lp[2 * K * K];
+  __shared__ int32_t s_idx[2 * K * K];
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int k2 = 2 * K;
+  for (int b = warp; b < K; b += 4)
+    merge_row(ma, img * K + b, lane, s_pos[warp], s_lp + b * k2, s_idx + b * k2, nullptr, s_stage[warp]);
+  __syncthreads();
+  if (warp == 0)
+    beam_step_image<K>(st, img, lane, T, cur_len, eos, div_fin, div_heur, s_lp, s_idx, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam);
+  if (!do_gather) return;
+  __threadfence_block();
+  __syncthreads();   // next_tok / src_row of this image's rows are visible to the whole CTA
+  for (int b = 0; b < K; ++b) gather_row(ga, img * K + b, threadIdx.x, blockDim.x);
+}
+
 __global__ void __launch_bounds__(256) mean_regions_kernel(const float* __restrict__ feats, int L, int D,
                                                            float* __restrict__ out) {
   const int b = blockIdx.y;
@@ -651,6 +681,31 @@ int beam_finalize(const BeamState& st, int parity, int B, int k, int T, int32_t*
                   float* out_score, cudaStream_t s) {
   if (B == 0) return CAPDEC_OK;
   beam_finalize_kernel<<<ceil_div(B * T, 256), 256, 0, s>>>(st, parity, B, k, T, out_tok, out_len, out_score);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int select_fused(const float* part, const float* lse_part, int vocab, int n_total, int part_k, const BeamState& st, int B, int k,
+                 int T, int cur_len, int eos, float div_fin, float div_heur, int32_t* next_tok, int32_t* src_row,
+                 float* dbg_lp, int32_t* dbg_tok, int32_t* dbg_beam, const GatherArgs* ga, cudaStream_t s) {
+  const int rows = B * k, n_rec = tk_records(rows, n_total);
+  CAPDEC_REQUIRE(k >= 1 && k <= kMaxRowsPerImage && 2 * k <= tk_bucket(part_k) && n_rec <= kMergeMaxRecords, CAPDEC_ERR_INVALID,
+                 "select_fused: num_beams %d / record layout unsupported", k);
+  if (B == 0) return CAPDEC_OK;
+  MergeArgs ma{part, lse_part, tk_lse_pairs(vocab), vocab, n_rec, tk_stride(part_k), tk_bucket(part_k), rows, 2 * k, 0, 0, 0};
+  tk_schedule(rows, n_total, &ma.n_tiles, &ma.quota, &ma.block_rows);
+  GatherArgs g{};
+  if (ga) g = *ga;
+#define CAPDEC_SF_CASE(KV)                                                                                              \
+  case KV:                                                                                                              \
+    CAPDEC_CHECK_CUDA(launch_k(select_fused_kernel<KV>, dim3(B), dim3(128), 0, s, true, ma, st, T, cur_len, eos, div_fin, \
+                               div_heur, next_tok, src_row, dbg_lp, dbg_tok, dbg_beam, g, ga ? 1 : 0));                 \
+    break;
+  switch (k) {
+    CAPDEC_SF_CASE(1) CAPDEC_SF_CASE(2) CAPDEC_SF_CASE(3) CAPDEC_SF_CASE(4)
+    CAPDEC_SF_CASE(5) CAPDEC_SF_CASE(6) CAPDEC_SF_CASE(7) CAPDEC_SF_CASE(8)
+  }
+#undef CAPDEC_SF_CASE
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
