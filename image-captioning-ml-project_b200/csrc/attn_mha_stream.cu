@@ -336,9 +336,7 @@ bool plan(const MhaArgs& a, int KB, MhaLayout* y) {
 template <int KB>
 int launch_stream(const MhaArgs& a, const MhaLayout& y, cudaStream_t s) {
   const int nc = (a.H / 4 + kCtxThreads - 1) / kCtxThreads;
-  static const int cap = getenv("CAPDEC_ATTN_MAX_CTAS") ? atoi(getenv("CAPDEC_ATTN_MAX_CTAS")) : 0;
-  int grid = a.B < sm_count() ? a.B : sm_count();
-  if (cap > 0 && grid > cap) grid = cap;
+  const int grid = a.B < sm_count() ? a.B : sm_count();
   if (nc == 1) {
     auto kern = mha_attention_stream_kernel<KB, 1>;
     CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)y.total));
@@ -356,7 +354,7 @@ int launch_stream(const MhaArgs& a, const MhaLayout& y, cudaStream_t s) {
 
 // returns 1 when the streaming kernel took the call, 0 when the shape is left to the generic kernel, < 0 on error
 int mha_attention_stream(const MhaArgs& a, cudaStream_t s) {
-  static const bool disabled = getenv("CAPDEC_ATTN_GENERIC") != nullptr;
+  static const bool disabled = ab_switch("CAPDEC_ATTN_GENERIC");
   if (disabled || a.k < 1 || a.k > kMaxRowsPerImage || a.heads < 1 || a.H % a.heads || (a.H / a.heads) % 4) return 0;
   const int KB = a.k <= 6 ? a.k : 8;
   MhaLayout y{};

@@ -523,17 +523,14 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
   y->off_red = take(G > 1 ? (size_t)(G - 1) * KB * a.D * 4 : 16);
   y->off_bar = take((size_t)(2 * kMaxStagesA + 2 * kMaxStagesF + 2 * kEBuf) * 8 + 16);   // + s_misc: 2 range flags, sum(w)
   const size_t budget = 220 * 1024;
-  static const int stA_env = getenv("CAPDEC_ATTN_STAGES_A") ? atoi(getenv("CAPDEC_ATTN_STAGES_A")) : 0;
-  const int kStagesA = stA_env >= 2 && stA_env <= kMaxStagesA ? stA_env : 2;
+  constexpr int kStagesA = 2;
   y->stA = kStagesA;
-  static const int stF_env = getenv("CAPDEC_ATTN_STAGES_F") ? atoi(getenv("CAPDEC_ATTN_STAGES_F")) : 0;
-  const int kStagesF = stF_env >= 2 && stF_env <= kMaxStagesF ? stF_env : 3;   // measured at C2: 3 stages of 7 rows beat 4 x 5, 5 x 4, 6 x 3, 8 x 2 (21.5 / 21.9 / 22.4 / 23.6 / 25.2 ms)
+  constexpr int kStagesF = 3;   // measured at C2: 3 stages of 7 rows beat 4 x 5, 5 x 4, 6 x 3, 8 x 2 (21.5 / 21.9 / 22.4 / 23.6 / 25.2 ms)
   y->stF = kStagesF;
-  static const int rowsA_env = getenv("CAPDEC_ATTN_ROWS_A") ? atoi(getenv("CAPDEC_ATTN_ROWS_A")) : 0;
   if (fixed + kStagesA * rowA + kStagesF * rowF > budget) return false;
   // att1 ring: one full pass of the score warps (2 rows each) per stage when it fits; the feats ring gets the rest
   const size_t left = budget - fixed;
-  int rowsA = rowsA_env > 0 ? rowsA_env : 2 * kScoreWarps, rowsF = 0;
+  int rowsA = 2 * kScoreWarps, rowsF = 0;
   if (rowsA > a.L) rowsA = a.L;
   for (; rowsA >= 1; rowsA = rowsA > 1 ? rowsA / 2 : 0) {
     const size_t needA = (size_t)kStagesA * (((size_t)rowsA * rowA + 127) & ~(size_t)127);
@@ -561,9 +558,7 @@ bool plan(const AddAttnArgs& a, int KB, StreamLayout* y) {
 template <int KB>
 int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStream_t s) {
   const int nc = (a.D / 4 + kCtxThreads - 1) / kCtxThreads;
-  static const int cap = getenv("CAPDEC_ATTN_MAX_CTAS") ? atoi(getenv("CAPDEC_ATTN_MAX_CTAS")) : 0;   // experiments: SM partitioning
-  int grid = a.B < sm_count() ? a.B : sm_count();
-  if (cap > 0 && grid > cap) grid = cap;
+  const int grid = a.B < sm_count() ? a.B : sm_count();
 #define CAPDEC_STREAM_LAUNCH(ACTV, NCV, BFV)                                                                              \
   {                                                                                                                       \
     auto kern = additive_attention_stream_kernel<KB, ACTV, NCV, BFV>;                                                     \
@@ -590,7 +585,7 @@ int launch_stream(const AddAttnArgs& a, int act, const StreamLayout& y, cudaStre
 }  // namespace
 
 bool additive_attention_stream_supports(int A, int D, int L, int k, int tile_fmt) {
-  if (getenv("CAPDEC_ATTN_GENERIC") != nullptr || k < 1 || k > kMaxRowsPerImage) return false;
+  if (ab_switch("CAPDEC_ATTN_GENERIC") || k < 1 || k > kMaxRowsPerImage) return false;
   AddAttnArgs a{};
   a.A = A; a.D = D; a.L = L; a.k = k; a.tile_fmt = tile_fmt;
   StreamLayout y{};
@@ -599,7 +594,7 @@ bool additive_attention_stream_supports(int A, int D, int L, int k, int tile_fmt
 
 // returns 1 when the streaming kernel took the call, 0 when the shape is left to the generic kernel, < 0 on error
 int additive_attention_stream(const AddAttnArgs& a, int act, cudaStream_t s) {
-  static const bool disabled = getenv("CAPDEC_ATTN_GENERIC") != nullptr;
+  static const bool disabled = ab_switch("CAPDEC_ATTN_GENERIC");
   if (disabled || a.k < 1 || a.k > kMaxRowsPerImage) return 0;
   if (a.ld_att2 % 4 || a.ld_ctx % 4 || (a.gate && a.ld_gate % 4)) return 0;
   const int KB = a.k <= 6 ? a.k : 8;

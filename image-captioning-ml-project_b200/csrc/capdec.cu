@@ -170,7 +170,7 @@ bool tiles_p24(const capdec_handle* h) {
   const capdec_config& c = h->cfg;
   const int H = c.hidden_dim, E = c.embed_dim, D = c.feature_dim, A = c.attention_dim;
   return is_legacy(h) && c.precision == CAPDEC_PREC_BF16X3 && (E + D + H) % 8 == 0 && H % 8 == 0 && E % 4 == 0 && A % 16 == 0 &&
-         D % 16 == 0 && !getenv("CAPDEC_NO_PRESPLIT") && !getenv("CAPDEC_NO_MEAN_SPLIT") && !getenv("CAPDEC_NO_P24_TILES");
+         D % 16 == 0 && !ab_switch("CAPDEC_NO_PRESPLIT") && !ab_switch("CAPDEC_NO_P24_TILES");
 }
 // carve-up of a tile set for B images (base == nullptr: sizes only)
 TileSet tiles_layout(const capdec_handle* h, void* base, int B, int L) {
@@ -201,7 +201,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   // and top-k candidates, so no [R,V] logits buffer exists (sampling and the teacher-forced forward need full rows)
   const int want_k = mode == MODE_BEAM ? 2 * k : mode == MODE_GREEDY ? 1 : 0;
   S.fuse_k = 0;
-  if (want_k > 0 && c.precision != CAPDEC_PREC_FP32 && tk_supported(V, want_k) && !getenv("CAPDEC_NO_FUSED_TOPK"))
+  if (want_k > 0 && c.precision != CAPDEC_PREC_FP32 && tk_supported(V, want_k) && !ab_switch("CAPDEC_NO_FUSED_TOPK"))
     S.fuse_k = want_k;
   auto take_logits = [&]() {
     if (S.fuse_k > 0) {
@@ -221,7 +221,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.gprefix = ar.take<float>((size_t)B * S.n_prefix * H);
     }
     S.mx = S.msa = S.mff = SplitDst{};
-    if (c.precision != CAPDEC_PREC_FP32 && H % 8 == 0 && F % 8 == 0 && !getenv("CAPDEC_NO_PRESPLIT")) {
+    if (c.precision != CAPDEC_PREC_FP32 && H % 8 == 0 && F % 8 == 0 && !ab_switch("CAPDEC_NO_PRESPLIT")) {
       const int kind = tc_kind(c.precision);
       const size_t es = kind == KIND_BF16 ? 2 : 4;
       const bool lo = tc_terms(c.precision) == 3;
@@ -287,7 +287,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
   if (is_legacy(h)) {
     S.presplit = false;
     if (c.precision != CAPDEC_PREC_FP32 && mode != MODE_TEACHER && mode != MODE_ATTENTION && (E + D + H) % 8 == 0 && H % 8 == 0 &&
-        E % 4 == 0 && !getenv("CAPDEC_NO_PRESPLIT")) {
+        E % 4 == 0 && !ab_switch("CAPDEC_NO_PRESPLIT")) {
       const size_t es = tc_kind(c.precision) == KIND_BF16 ? 2 : 4;
       const bool lo = tc_terms(c.precision) == 3;
       S.xs_hi = ar.take<char>(R * (E + D + H) * es);
@@ -295,13 +295,13 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.hs_hi = ar.take<char>(R * H * es);
       S.hs_lo = lo ? ar.take<char>(R * H * es) : nullptr;
       S.presplit = true;
-      if (c.precision == CAPDEC_PREC_BF16 && A % 8 == 0 && D % 8 == 0 && !getenv("CAPDEC_NO_BF16_TILES") &&
+      if (c.precision == CAPDEC_PREC_BF16 && A % 8 == 0 && D % 8 == 0 && !ab_switch("CAPDEC_NO_BF16_TILES") &&
           additive_attention_stream_supports(A, D, L, k, true)) {
         S.feats_h = ar.take<char>((size_t)B * L * D * 2);
         S.att1_h = ar.take<char>((size_t)B * L * A * 2);
-      } else if (D % 8 == 0 && !getenv("CAPDEC_NO_MEAN_SPLIT")) {
+      } else if (D % 8 == 0) {
         // operand copies of the features for the hoisted enc_att GEMM, written by the same pass that takes the region mean
-        const bool p24 = c.precision == CAPDEC_PREC_BF16X3 && !getenv("CAPDEC_NO_P24_TILES") && additive_attention_stream_supports(A, D, L, k, 2);
+        const bool p24 = c.precision == CAPDEC_PREC_BF16X3 && !ab_switch("CAPDEC_NO_P24_TILES") && additive_attention_stream_supports(A, D, L, k, 2);
         if (S.ext.valid && S.ext.p24) {
           if (!p24) return CAPDEC_ERR_UNSUPPORTED;   // the planes are all there is: no fp32 features to fall back to
           S.feats_h = S.ext.hi; S.feats_l = S.ext.lo; S.feats_b8 = S.ext.b8;
@@ -503,7 +503,7 @@ int run_attention(const capdec_handle* h, Session& S, const float* feats, const 
     a.gate = nullptr; a.ctx = base_dst; a.ld_ctx = ld_base; a.alpha = alpha; a.ld_alpha = ld_alpha;
     a.B = images; a.L = S.L; a.A = H; a.D = H; a.k = k;
     // exact tanhf in the fp32 mode; the MUFU form (1e-6) in the tensor-core modes, whose GEMM noise is 100x larger
-    const int act = (c.precision == CAPDEC_PREC_FP32 || getenv("CAPDEC_EXACT_TANH")) ? ACT_TANH : ACT_TANH_FAST;
+    const int act = (c.precision == CAPDEC_PREC_FP32 || ab_switch("CAPDEC_EXACT_TANH")) ? ACT_TANH : ACT_TANH_FAST;
     { StageScope sc(h, STAGE_ATTENTION, s); CAPDEC_RETURN_IF(additive_attention(a, act, s)); }
   }
 
@@ -1046,14 +1046,14 @@ int capdec_finalize(capdec_handle* h, void* stream) {
     CAPDEC_RETURN_IF(scatter_rows(h->w_hproj + A * H, H, 1, 0, 0, h->W("f_beta.weight"), H, (int)D, (int)H, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj, 1, 1, 0, 0, h->W("dec_att.bias"), 1, (int)A, 1, false, s));
     CAPDEC_RETURN_IF(scatter_rows(h->b_hproj + A, 1, 1, 0, 0, h->W("f_beta.bias"), 1, (int)D, 1, false, s));
-    if (c.precision != CAPDEC_PREC_FP32 && !getenv("CAPDEC_NO_EMB_TABLE")) {
+    if (c.precision != CAPDEC_PREC_FP32) {
       CAPDEC_RETURN_IF(dev_alloc(h, &h->emb_gates, (size_t)V * 4 * H));
       GemmArgs g{};
       g.A = h->W("embedding.weight"); g.lda = E; g.W = h->w_gates[0]; g.ldw = E + D + H; g.bias = nullptr;
       g.C = h->emb_gates; g.ldc = 4 * H; g.M = (int)V; g.N = (int)(4 * H); g.K = (int)E;
       CAPDEC_RETURN_IF(gemm_ffma(g, EPI_STORE, s));
     }
-    if (c.precision != CAPDEC_PREC_FP32 && !getenv("CAPDEC_NO_HPROJ_TAIL")) {
+    if (c.precision != CAPDEC_PREC_FP32) {
       const int64_t Vp = (V + 255) / 256 * 256, Nc = Vp + A + D;
       CAPDEC_RETURN_IF(dev_alloc(h, &h->w_vocab_cat, (size_t)Nc * H));
       CAPDEC_RETURN_IF(dev_alloc(h, &h->b_vocab_cat, (size_t)Nc));
@@ -1455,23 +1455,10 @@ static int decode_beam_host_impl(capdec_handle* h, const void* feats_host, int l
   const size_t pool_chunk = align_up((size_t)chunk * pooled_w * sizeof(float), 256);
   const size_t mask_chunk = mask_host ? align_up((size_t)chunk * L, 256) : 0;
   const size_t tiles_bytes = (have_feats && !direct) ? tiles_layout(h, nullptr, chunk, L).bytes : 0;
-  // Chunk schedule: the copy engine runs back to back from t = 0, so the call ends one chunk-decode after the last
-  // byte lands (and starts decoding one chunk-copy after the first).  Ramp the chunk size up from chunk/8 at the start
-  // and down to chunk/8 at the end so both exposed pieces are small; full-size chunks in between keep the GEMMs efficient.
+  // Chunk schedule: equal chunks.  (Ramping the chunk size up at the start and down at the end, to shorten the exposed
+  // first copy / last decode, was measured slower on B200: small chunks decode too inefficiently for the ramp to pay.)
   std::vector<int> sizes;
-  {
-    const int small = chunk / 8 > 32 ? chunk / 8 : (chunk < 32 ? chunk : 32);
-    std::vector<int> head, tail;
-    int left = B;
-    const char* ramp = getenv("CAPDEC_E2E_RAMP");   // "0" (default): none, "1": tail only, "2": head and tail.  Measured on B200: small chunks decode too slowly
-                                                    // (K-serial GEMM tiles, launch latency) for the ramp to pay, so it is off
-    const int mode = ramp ? atoi(ramp) : 0;
-    if (mode >= 2) for (int n = small; n < chunk && left > 2 * chunk; n *= 2) { head.push_back(n); left -= n; }
-    if (mode >= 1) for (int n = small; n < chunk && left > 2 * chunk; n *= 2) { tail.push_back(n); left -= n; }
-    sizes = head;
-    while (left > 0) { const int n = left < chunk ? left : chunk; sizes.push_back(n); left -= n; }
-    for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
-  }
+  for (int left = B; left > 0;) { const int n = left < chunk ? left : chunk; sizes.push_back(n); left -= n; }
   // the fused top-k record count is not monotone in the row count, so size the shared workspace for every chunk size used
   size_t ws_bytes = 0;
   {

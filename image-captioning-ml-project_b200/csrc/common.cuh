@@ -64,6 +64,20 @@ inline int current_device() {
 int num_sms();   // SM count of the current device (capdec.cu)
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- A/B switches ----------------------------------------------------------------------------------------------
+// The library has a small, closed set of environment switches, each selecting an ALTERNATIVE TESTED CODE PATH so that a
+// measurement or a parity test can compare the two in one process (DESIGN.md section 6 lists them).  They are never needed
+// in production; everything else about the schedule (ring depths, grid sizes, chunking) is a compile-time constant.
+//   CAPDEC_NO_FUSED_TOPK   vocabulary GEMM stores logits, lse_topk_kernel selects
+//   CAPDEC_NO_PRESPLIT     GEMMs split their A operand themselves (no producer-written hi / lo mirrors)
+//   CAPDEC_NO_P24_TILES    bf16x3 mode streams fp32 region tiles instead of the p24 planes
+//   CAPDEC_NO_BF16_TILES   bf16 mode streams fp32 region tiles
+//   CAPDEC_EXACT_TANH      soft attention uses tanhf in the tensor-core modes too
+//   CAPDEC_ATTN_GENERIC    one-CTA-per-image attention kernels instead of the persistent TMA-streamed ones
+//   CAPDEC_NO_STREAMK      tcgen05 GEMM always schedules whole tiles
+//   CAPDEC_NO_PDL          launches without programmatic dependent launch
+inline bool ab_switch(const char* name) { return getenv(name) != nullptr; }
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------
 // The decode loop is a chain of dependent kernels on one stream.  Kernels launched through launch_k(..., pdl = true)
 // may become resident while their predecessor is still draining (every kernel calls pdl_trigger() first thing) and do
@@ -73,7 +87,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 inline bool pdl_enabled() {
-  static const bool on = getenv("CAPDEC_NO_PDL") == nullptr;
+  static const bool on = !ab_switch("CAPDEC_NO_PDL");
   return on;
 }
 template <typename... KArgs, typename... Args>

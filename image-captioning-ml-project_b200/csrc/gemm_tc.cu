@@ -754,13 +754,11 @@ int tc_max_groups(int cg) {
   }
   cudaGetLastError();
   if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
-  if (const char* e = getenv("CAPDEC_GEMM_MAX_GROUPS")) { const int c = atoi(e); if (c > 0 && c < n) n = c; }   // experiments: SM partitioning
   cache[2].store(n);
   return n;
 }
 int tc_cta_group(int M) {
-  static const bool no_pair = getenv("CAPDEC_NO_CTA_PAIR") != nullptr;
-  return (M > BM && !no_pair) ? 2 : 1;   // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile
+  return M > BM ? 2 : 1;   // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile
 }
 
 template <int BN, int TERMS, int CG, int KIND>
@@ -955,7 +953,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     g.K = pre ? K : Kp;
     // stream-K when whole tiles would leave the last wave mostly idle (see the kernel): needs the handle's scratch
     g.sk_part = nullptr; g.sk_flag = nullptr; g.sk_epoch = 0;
-    static const bool no_sk = getenv("CAPDEC_NO_STREAMK") != nullptr;   // A/B switch for the measurements in DESIGN.md
+    static const bool no_sk = ab_switch("CAPDEC_NO_STREAMK");
     if (h && epilogue != EPI_TOPK && !no_sk) {
       const int G = tc_max_groups(cg);
       const int tiles = ceil_div(a.N, bn) * ceil_div(mc, BM * cg);

@@ -315,8 +315,7 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
                  a.heads ? a.H / a.heads : 0);
   if (a.rows == 0) return CAPDEC_OK;
   const int n_keys = a.n_prefix + a.t + 1;
-  static const bool old_form = getenv("CAPDEC_SELFATTN_ONLINE") != nullptr;
-  if (!old_form && n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
+  if (n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
     const size_t smem = ((size_t)a.H + (size_t)a.heads * 128) * sizeof(float);
     const int d4 = a.H / a.heads / 4;
 #define CAPDEC_SA_LAUNCH(NKV)                                                                               \
