@@ -155,7 +155,9 @@ struct Session {
   int tk_ntotal = 0;                    // N of the fused vocabulary GEMM (vocab, or vocab padded + the legacy [dec_att|f_beta] tail)
   bool hproj_ready = false;             // legacy: S.hproj already holds the projections of the CURRENT hidden state (pre-reorder rows)
   const int32_t* row_src = nullptr;     // back-pointers of the last commit (nullptr = identity)
-  int64_t logits_ld = 0;                // row stride of S.logits (0 = vocab_size); capdec_forward_tokens writes [R, t, V] blocks
+  int64_t logits_ld = 0;                // row stride of S.logits (0 = vocab_size).  The workspace buffer pads rows to a multiple of
+                                        // 4 floats so the GEMM epilogue stores whole float4s (V = 50257: the scalar path made the
+                                        // GPT-2 logits GEMM store-bound); capdec_forward_tokens writes [R, t, V] blocks
   // teacher-forced pass (capdec_forward_tokens), transformer family: key positions whose forced token is pad are masked
   const int32_t* key_tok = nullptr; int64_t ld_key_tok = 0; int key_pad = -1;
   // encoder hand-off (capdec_ingest_features): the p24 planes / lo operand / region mean already exist in a caller-owned
@@ -209,7 +211,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.tk_part = ar.take<float>(R * tk_records(S.R, S.tk_ntotal) * tk_stride(S.fuse_k));
       S.tk_lse = ar.take<float>(R * tk_lse_pairs(V) * 2);
     }
-    else S.logits = ar.take<float>(R * V);
+    else { S.logits_ld = (V + 3) & ~3; S.logits = ar.take<float>(R * S.logits_ld); }
   };
   if (is_tf_family(h)) {
     const DevTensor* f1 = h->find(is_gpt2(h) ? "model.transformer.h.0.mlp.c_fc.weight" : "transformer_decoder.layers.0.linear1.weight");
@@ -387,7 +389,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
 int select_topk(const capdec_handle* h, Session& S, int topk, float* out_lp, int32_t* out_idx, cudaStream_t s) {
   const int V = h->cfg.vocab_size;
   if (S.fuse_k > 0) return topk_merge(S.tk_part, S.tk_lse, S.R, V, S.tk_ntotal, S.fuse_k, topk, out_lp, out_idx, nullptr, s);
-  return lse_topk(S.logits, V, S.R, V, topk, out_lp, out_idx, nullptr, s);
+  return lse_topk(S.logits, S.logits_ld ? S.logits_ld : V, S.R, V, topk, out_lp, out_idx, nullptr, s);
 }
 
 int prologue_legacy(const capdec_handle* h, Session& S, const float* feats, bool expand, cudaStream_t s) {
@@ -1287,18 +1289,19 @@ int capdec_forward_tokens(capdec_handle* h, const float* feats, const float* poo
   if (mask_pad_keys && is_tf_family(h)) { S.key_tok = tokens; S.ld_key_tok = tok_stride; S.key_pad = c.pad_token_id; }
   CAPDEC_RETURN_IF(prologue_any(h, S, feats, pooled, s));
   float* const logits_buf = S.logits;
+  const int64_t ld_buf = S.logits_ld ? S.logits_ld : V;
   const bool direct = logits_out != nullptr && V % 4 == 0;   // step t's GEMM writes straight into logits_out[:, t, :]
   for (int t = 0; t < n_tok; ++t) {
     CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(S.next_tok, sizeof(int32_t), tokens + t, (size_t)tok_stride * sizeof(int32_t),
                                         sizeof(int32_t), S.R, cudaMemcpyDeviceToDevice, s));
     CAPDEC_RETURN_IF(commit(h, S, nullptr, nullptr, 0, -1, t > 0, s));
     if (direct) { S.logits = logits_out + (size_t)t * V; S.logits_ld = (int64_t)n_tok * V; }
-    else        { S.logits = logits_buf; S.logits_ld = 0; }
+    else        { S.logits = logits_buf; S.logits_ld = ld_buf; }
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, alpha_out ? alpha_out + (size_t)t * L : nullptr, (int64_t)n_tok * L, t, s));
     const int64_t ld = S.logits_ld ? S.logits_ld : V;
     if (logits_out && !direct)
       CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(logits_out + (size_t)t * V, (size_t)n_tok * V * sizeof(float), logits_buf,
-                                          (size_t)V * sizeof(float), (size_t)V * sizeof(float), S.R, cudaMemcpyDeviceToDevice, s));
+                                          (size_t)ld_buf * sizeof(float), (size_t)V * sizeof(float), S.R, cudaMemcpyDeviceToDevice, s));
     if (logprob_out && t + 1 < n_tok) {
       StageScope sc(h, STAGE_SELECT, s);
       CAPDEC_RETURN_IF(token_logprob(S.logits, ld, S.R, V, tokens + t + 1, tok_stride, logprob_out + t, n_tok - 1, s));
@@ -1354,7 +1357,7 @@ int capdec_decode_sample(capdec_handle* h, const float* feats, const float* pool
   for (int t = 0; t + 1 < T; ++t) {  // trainer.py:413
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, t, s));
     { StageScope sc(h, STAGE_SELECT, s);
-      CAPDEC_RETURN_IF(sample_rows(S.logits, c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
+      CAPDEC_RETURN_IF(sample_rows(S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
                                    with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s)); }
     if (out_lp) {
       // out_lp[r, t] = step_lp[r]

@@ -185,17 +185,28 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a, floa
 }
 
 // One CTA per row: inverse-CDF draw in vocabulary index order (double prefix sums), or argmax for the greedy slot.
+//   token = #{v : cdf[v] <= u * S},  cdf[v] = sum_{i <= v} exp(x_i - M)            (src/train/trainer.py:423-425 with the draw
+//   driven by a shared uniform instead of torch's RNG stream)
+// The row is NOT staged in shared memory (a 50257-entry row is 200 KB: one CTA per SM, every phase serialised -- 837 us
+// per launch at 3072 rows); it is read three times from L2 / HBM with coalesced loads instead: (1) row max (+ argmax for
+// the greedy slot), (2) each warp sums its CONTIGUOUS eighth of the row, lanes striding it, (3) only the warp whose
+// segment contains the target walks it in 32-element groups with a warp inclusive scan.  No shared-memory row means
+// 8 CTAs per SM and ~0.6 MB of loads in flight per SM.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restrict__ logits, int64_t ld, int V,
                                                           const float* __restrict__ uniforms, int64_t ld_u, int step,
                                                           int rows_per_image, int greedy_slot,
                                                           int32_t* __restrict__ out_tok, float* __restrict__ out_lp) {
-  extern __shared__ float row[];
   __shared__ float s_tmp[kThreads / 32];
   __shared__ float s_v[kThreads / 32];
   __shared__ int s_i[kThreads / 32];
-  __shared__ double s_part[kThreads];
-  __shared__ double s_total;
-  __shared__ int s_cnt[kThreads / 32];
+  __shared__ double s_wsum[kThreads / 32];
+  __shared__ int s_tok;
+  constexpr int NW = kThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x;
   const float* x = logits + (int64_t)r * ld;
@@ -204,56 +215,70 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
   int bi = INT_MAX;
   for (int i = tid; i < V; i += kThreads) {
     const float v = x[i];
-    row[i] = v;
     if (v > bv) { bv = v; bi = i; }
   }
-  const float M = block_max(bv, s_tmp);  // includes the barrier that publishes row[]
+  const float M = block_max(bv, s_tmp);
   const bool greedy = greedy_slot >= 0 && (r % rows_per_image) == greedy_slot;
 
-  // contiguous chunk per thread so prefix sums follow index order
-  const int chunk = (V + kThreads - 1) / kThreads;
-  const int beg = min(V, tid * chunk), end = min(V, beg + chunk);
+  // contiguous segment per warp (a multiple of 32 elements), lanes striding it: prefix sums follow index order
+  const int seg = ((V + NW - 1) / NW + 31) & ~31;
+  const int beg = min(V, warp * seg), end = min(V, beg + seg);
   double local = 0.0;
-  for (int i = beg; i < end; ++i) local += (double)expf(row[i] - M);
-  s_part[tid] = local;
+  for (int i = beg + lane; i < end; i += 32) local += (double)expf(x[i] - M);
+  local = warp_sum_d(local);
+  if (lane == 0) s_wsum[warp] = local;
   __syncthreads();
-  if (tid == 0) {  // serial exclusive scan over 256 partials (tiny)
-    double run = 0.0;
-    for (int t = 0; t < kThreads; ++t) { const double v = s_part[t]; s_part[t] = run; run += v; }
-    s_total = run;
-  }
-  __syncthreads();
-  const double S = s_total;
-  int tok;
+  double S = 0.0, before = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { if (w == warp) before = S; S += s_wsum[w]; }
+
   if (greedy) {  // block-uniform branch
     float v = bv; int i = bi;
     warp_argmax(v, i);
     if (lane == 0) { s_v[warp] = v; s_i[warp] = i; }
     __syncthreads();
-    float wv = s_v[0]; int wi = s_i[0];
+    if (tid == 0) {
+      float wv = s_v[0]; int wi = s_i[0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w)
-      if (better(s_v[w], s_i[w], wv, wi)) { wv = s_v[w]; wi = s_i[w]; }
-    tok = wi;
+      for (int w = 1; w < NW; ++w)
+        if (better(s_v[w], s_i[w], wv, wi)) { wv = s_v[w]; wi = s_i[w]; }
+      s_tok = wi;
+    }
   } else {
     const double target = (double)uniforms[(int64_t)r * ld_u + step] * S;
-    double run = s_part[tid];
-    int cnt = 0;
-    for (int i = beg; i < end; ++i) {
-      run += (double)expf(row[i] - M);
-      cnt += (run <= target) ? 1 : 0;
-    }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) s_cnt[warp] = cnt;
+    // the one warp whose segment holds the first cdf value above the target finds it; if no value is above it (u*S
+    // rounds to >= the total) the draw is the last token, as torch's clamp does
+    // (before(w+1) == before(w) + s_wsum[w] exactly, so at most one warp qualifies)
+    const bool mine = before <= target && before + s_wsum[warp] > target;
+    if (tid == 0) s_tok = V - 1;
     __syncthreads();
-    int total = 0;
+    if (mine && beg < end) {
+      double base = before;
+      int tok = -1;
+      for (int g = beg; g < end && tok < 0; g += 32) {
+        const int i = g + lane;
+        double inc = i < end ? (double)expf(x[i] - M) : 0.0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) total += s_cnt[w];
-    tok = min(total, V - 1);
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const unsigned below = __ballot_sync(0xffffffffu, i < end && base + inc <= target);
+        const int n_valid = min(32, end - g);
+        const int cnt = __popc(below);
+        if (cnt < n_valid) tok = g + cnt;       // cdf is non-decreasing: the first element above the target
+        base += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      // (the scan re-associates the segment's sum: if its last value lands a rounding below the target, the first element
+      //  above it is the next segment's first)
+      if (lane == 0) s_tok = min(tok >= 0 ? tok : end, V - 1);
+    }
   }
+  __syncthreads();
   if (tid == 0) {
+    const int tok = s_tok;
     out_tok[r] = tok;
-    if (out_lp) out_lp[r] = (row[tok] - M) - logf((float)S);
+    if (out_lp) out_lp[r] = (x[tok] - M) - logf((float)S);
   }
 }
 
@@ -620,14 +645,9 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
 
 int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const float* uniforms, int64_t ld_u, int step,
                 int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s) {
-  CAPDEC_REQUIRE(vocab >= 1 && (size_t)vocab * 4 <= 200 * 1024, CAPDEC_ERR_UNSUPPORTED,
-                 "sample_rows: vocab %d does not fit a shared-memory row", vocab);
+  CAPDEC_REQUIRE(vocab >= 1, CAPDEC_ERR_INVALID, "sample_rows: empty vocabulary");
   if (rows == 0) return CAPDEC_OK;
-  const size_t smem = (size_t)vocab * sizeof(float);
-  if (smem > 48 * 1024)
-    CAPDEC_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sample_kernel<<<rows, kThreads, smem, s>>>(logits, ld, vocab, uniforms, ld_u, step, rows_per_image, greedy_slot,
-                                             out_tok, out_lp);
+  sample_kernel<<<rows, kThreads, 0, s>>>(logits, ld, vocab, uniforms, ld_u, step, rows_per_image, greedy_slot, out_tok, out_lp);
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
