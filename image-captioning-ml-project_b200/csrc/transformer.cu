@@ -29,7 +29,60 @@ __global__ void __launch_bounds__(128) embed_pos_kernel(const int32_t* __restric
 }
 
 // s = x + y (y may be null); optionally store s; out = LayerNorm(s) * gamma + beta   (eps inside the sqrt, biased var).
-// 128-bit loads / stores; `split` (optional) also writes out as the hi/lo operand copies of the GEMM that consumes it.
+// One WARP per row, the row held in registers (up to 32 floats per lane, H <= 1024): no shared memory and no block barrier
+// -- the block-per-row form spent its time in two __syncthreads around 3 KB of work.  128-bit loads / stores; `split`
+// (optional) also writes out as the hi/lo operand copies of the GEMM that consumes it.
+constexpr int kLnRowsPerCta = 8;
+template <int NV>   // float4 groups per lane: H <= 128 * NV
+__global__ void __launch_bounds__(32 * kLnRowsPerCta) add_layernorm_warp_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                                float* __restrict__ sum_out, float* __restrict__ out,
+                                                                                int rows, int H, float eps, const SplitDst split) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kLnRowsPerCta + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int H4 = H >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)r * H);
+  const float4* yr = y ? reinterpret_cast<const float4*>(y + (int64_t)r * H) : nullptr;
+  float4 v[NV];
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < H4) {
+      v[j] = xr[i];
+      if (yr) { const float4 w = yr[i]; v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w; }
+      part += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(part) / (float)H;
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (lane + 32 * j < H4) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      var += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < H4) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[i], bt = reinterpret_cast<const float4*>(beta)[i];
+      if (sum_out) reinterpret_cast<float4*>(sum_out + (int64_t)r * H)[i] = v[j];
+      const float4 o = make_float4((v[j].x - mean) * rstd * g.x + bt.x, (v[j].y - mean) * rstd * g.y + bt.y,
+                                   (v[j].z - mean) * rstd * g.z + bt.z, (v[j].w - mean) * rstd * g.w + bt.w);
+      reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;
+      split_store4(split, r, i * 4, o);
+    }
+  }
+}
+
+// block-per-row form for wider rows (H > 1024)
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ sum_out, float* __restrict__ out, int H,
@@ -303,8 +356,13 @@ int add_layernorm(const float* x, const float* y, const float* gamma, const floa
                   int rows, int H, float eps, cudaStream_t s, const SplitDst* split) {
   if (rows == 0) return CAPDEC_OK;
   CAPDEC_REQUIRE(H % 4 == 0, CAPDEC_ERR_UNSUPPORTED, "add_layernorm: H must be a multiple of 4");
-  CAPDEC_CHECK_CUDA(launch_k(add_layernorm_kernel, dim3(rows), dim3(256), (size_t)H * sizeof(float), s, true, x, y, gamma, beta,
-                             sum_out, out, H, eps, split ? *split : SplitDst{}));
+  const SplitDst sp = split ? *split : SplitDst{};
+  const dim3 grid(ceil_div(rows, kLnRowsPerCta)), block(32 * kLnRowsPerCta);
+  if (H <= 256)       CAPDEC_CHECK_CUDA(launch_k(add_layernorm_warp_kernel<2>, grid, block, 0, s, true, x, y, gamma, beta, sum_out, out, rows, H, eps, sp));
+  else if (H <= 512)  CAPDEC_CHECK_CUDA(launch_k(add_layernorm_warp_kernel<4>, grid, block, 0, s, true, x, y, gamma, beta, sum_out, out, rows, H, eps, sp));
+  else if (H <= 1024) CAPDEC_CHECK_CUDA(launch_k(add_layernorm_warp_kernel<8>, grid, block, 0, s, true, x, y, gamma, beta, sum_out, out, rows, H, eps, sp));
+  else CAPDEC_CHECK_CUDA(launch_k(add_layernorm_kernel, dim3(rows), dim3(256), (size_t)H * sizeof(float), s, true, x, y, gamma, beta,
+                                  sum_out, out, H, eps, sp));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }
