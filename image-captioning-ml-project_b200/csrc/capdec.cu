@@ -140,6 +140,7 @@ struct Session {
   // transformer family, tensor-core modes: hi/lo operand mirrors of the activations that feed GEMMs, written by the
   // kernels that produce them (embedding / LayerNorm / self-attention / GELU epilogue) instead of by a split pass
   SplitDst mx{}, msa{}, mff{};        // mirrors of tx (transformer) or txn (GPT-2), of tsa, of tff
+  SplitDst mmem{};                    // transformer prologue: mirror of the projected memory (A operand of the 2 x layers hoisted K / V GEMMs)
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
   float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
   // legacy, tensor-core modes: the producers of the gate / vocabulary GEMM operands (attention context, state gather,
@@ -222,7 +223,7 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.txn = ar.take<float>(R * H);
       S.gprefix = ar.take<float>((size_t)B * S.n_prefix * H);
     }
-    S.mx = S.msa = S.mff = SplitDst{};
+    S.mx = S.msa = S.mff = S.mmem = SplitDst{};
     if (c.precision != CAPDEC_PREC_FP32 && H % 8 == 0 && F % 8 == 0 && !ab_switch("CAPDEC_NO_PRESPLIT")) {
       const int kind = tc_kind(c.precision);
       const size_t es = kind == KIND_BF16 ? 2 : 4;
@@ -233,6 +234,10 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
         return d;
       };
       S.mx = mk(H); S.msa = mk(H); S.mff = mk(F);
+      if (!is_gpt2(h)) {   // written once by the visual_projection epilogue instead of being re-split by each of the 2 x layers GEMMs
+        S.mmem.hi = ar.take<char>((size_t)B * L * H * es); S.mmem.lo = lo ? ar.take<char>((size_t)B * L * H * es) : nullptr;
+        S.mmem.ld = H; S.mmem.kind = kind;
+      }
     }
     S.tx = ar.take<float>(R * H); S.tqkv = ar.take<float>(R * 3 * H); S.tsa = ar.take<float>(R * H);
     S.ty = ar.take<float>(R * H); S.tqc = ar.take<float>(R * H); S.tca = ar.take<float>(R * H);
@@ -640,13 +645,13 @@ int prologue_transformer(const capdec_handle* h, Session& S, const float* feats,
   const int H = h->cfg.hidden_dim, rows = S.B * S.L;
   // memory = visual_projection(features)  (decoders.py:453), then every layer's cross-attention K|V projection of
   // it, hoisted out of the step loop (nn.MultiheadAttention in_proj rows [H:3H) are the packed k and v projections)
-  CAPDEC_RETURN_IF(linear(h, feats, H, "visual_projection", S.tmem, H, rows, EPI_STORE, s));
+  CAPDEC_RETURN_IF(linear(h, feats, H, "visual_projection", S.tmem, H, rows, EPI_STORE, s, nullptr, 0, nullptr, &S.mmem));
   for (int l = 0; l < h->cfg.num_layers; ++l) {
     const float* w = h->W(tl(l, "multihead_attn.in_proj_weight"));
     const float* b = h->W(tl(l, "multihead_attn.in_proj_bias"));
     // K and V into separate dense [B,L,H] buffers (what the streaming attention kernel's bulk copies want)
-    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)H * H, H, b + H, S.tck[l], H, rows, H, H, EPI_STORE, s));
-    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)2 * H * H, H, b + 2 * H, S.tcv[l], H, rows, H, H, EPI_STORE, s));
+    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)H * H, H, b + H, S.tck[l], H, rows, H, H, EPI_STORE, s, &S.mmem));
+    CAPDEC_RETURN_IF(gemm_w(h, S.tmem, H, w + (size_t)2 * H * H, H, b + 2 * H, S.tcv[l], H, rows, H, H, EPI_STORE, s, &S.mmem));
   }
   S.anc_cur = -1;
   return CAPDEC_OK;

@@ -979,10 +979,17 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
         }
       }
     }
-    g.C = a.C + (int64_t)m0 * a.ldc;
+    g.C = a.C ? a.C + (int64_t)m0 * a.ldc : nullptr;
     if (a.C2) g.C2 = a.C2 + (int64_t)m0 * a.ldc2;
     if (a.c_in) g.c_in = a.c_in + (int64_t)m0 * a.ldcin;
     if (a.c_out) g.c_out = a.c_out + (int64_t)m0 * a.ldcout;
+    if (a.c_split.hi && m0 > 0) {      // the output mirror advances with the row chunk too
+      const size_t ces = a.c_split.kind == KIND_BF16 ? 2 : 4;
+      g.c_split.hi = (char*)a.c_split.hi + (size_t)m0 * a.c_split.ld * ces;
+      if (a.c_split.lo) g.c_split.lo = (char*)a.c_split.lo + (size_t)m0 * a.c_split.ld * ces;
+      if (a.c_split.b8) g.c_split.b8 = a.c_split.b8 + (size_t)m0 * a.c_split.ld;
+    }
+    if (a.row_index) g.row_index = a.row_index + m0;
     int st;
 #define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
     if (kind == KIND_TF32) {
