@@ -32,7 +32,7 @@ namespace {
 constexpr int kScoreWarps = 8, kCtxWarps = 8;
 constexpr int kScoreThreads = 32 * kScoreWarps, kCtxThreads = 32 * kCtxWarps;
 constexpr int kThreads = 64 + kScoreThreads + kCtxThreads;   // 576
-constexpr int kMaxStagesA = 4, kMaxStagesF = 8;                // att1 ring: StreamLayout::stA stages (2; CAPDEC_ATTN_STAGES_A overrides: 3 and 4 measured slower, they shrink the feats ring)
+constexpr int kMaxStagesA = 4, kMaxStagesF = 8;                // att1 ring: StreamLayout::stA stages (2: 3 and 4 measured slower, they shrink the feats ring)
 constexpr int kEBuf = 3;                                     // alpha buffers: scores of image i+1 while context reads image i
 constexpr uint32_t kSpinLimit = 1u << 24;
 
