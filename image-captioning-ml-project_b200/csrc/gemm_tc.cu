@@ -30,6 +30,19 @@ constexpr int kRowBytes = 128;        // one K block = one 128-byte swizzle row:
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kSpinLimit = 1u << 22;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
+#ifdef CAPDEC_TIMELINE
+// debug build only (scripts/gemm_timeline.py): per-CTA time stamps of the phases of one launch
+__device__ unsigned long long g_timeline[2][320][64];
+__device__ __forceinline__ void tl_stamp(int i) {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_timeline[0][blockIdx.x][i] = t;
+  g_timeline[1][blockIdx.x][i] = (unsigned long long)clock64();
+}
+#define TL(i) tl_stamp(i)
+#else
+#define TL(i)
+#endif
+
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -145,10 +158,9 @@ struct SmemLayout {
   static constexpr uint32_t kOffWLo = kOffWHi + kWBytes;                        // (3-term only)
   static constexpr int kStages = (CG == 2 ? 3 : 2) * (TERMS == 3 ? 1 : 2);
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
-  static constexpr uint32_t kStashOffset = kBarOffset + 256;   // EPI_TOPK only: 8 warps x 32 columns x 32 lanes floats
+  static constexpr uint32_t kStashOffset = kBarOffset + 256;   // 8 epilogue warps x (32 x 32 floats): store transpose / top-k candidates
   static constexpr uint32_t kStashBytes = 8 * 32 * 32 * 4;
-  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
-  static constexpr uint32_t kTotalTopk = kTotal + kStashBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024 + kStashBytes;  // barriers + slack for manual 1024-byte alignment + stash
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
@@ -170,6 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   uint64_t* tmem_init_bar = tmem_empty_bar + 2;    // [2]  stream-K: accumulator pre-loaded with the predecessor's partial sum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_init_bar + 2);
 
+  if (threadIdx.x == 0) TL(0);
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; rank 0 issues the MMAs
@@ -245,7 +258,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers initialised + TMEM allocated in BOTH CTAs of the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(1);
   pdl_wait();   // set-up above overlapped the predecessor's tail; its outputs (our operands) are visible from here on
+  if (threadIdx.x == 0) TL(2);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair: own 128 rows of A, own BN/CG rows of W) =====
@@ -282,8 +297,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               tma_load_2d(st + SL::kOffWLo, &map_w_lo, &full_bar[s], kb * BK, w_row);
             }
           }
+          if (it == 0) TL(3);
         }
       }
+      TL(4);
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread; in pair mode only the leader CTA, its MMAs drive both SMs' tensor cores) =====
@@ -309,6 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
+          if (it == 0) TL(5);
           const uint32_t a_hi = smem_u32(smem + s * SL::kStageBytes);
           const uint32_t a_lo = a_hi + SL::kOffALo;
           const uint32_t w_hi = a_hi + SL::kOffWHi;
@@ -328,6 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           commit(&empty_bar[s]);                           // frees this shared-memory stage (in both CTAs) when the MMAs retire
           if (kb == wk.kb1 - 1) commit(&tmem_full_bar[ab]);  // accumulator (of this item's K range) complete
         }
+        if (local < 8) TL(8 + local);
       }
     }
     __syncwarp();
@@ -338,7 +357,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     constexpr int HN = BN / 2;
     uint32_t local = 0;
     const uint32_t leader_empty_bar0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
-    float* stash = reinterpret_cast<float*>(smem + SL::kStashOffset);   // (allocated for EPI_TOPK launches only)
+    float* stash = reinterpret_cast<float*>(smem + SL::kStashOffset);   // 4 KB per epilogue warp
+    // Coalesced chunk store.  tcgen05.ld hands every thread ONE ROW of the chunk (32 consecutive columns), so storing
+    // from those registers makes each warp-wide 16-byte store touch 32 different rows: 32 half-filled sectors per
+    // instruction.  At that request rate the L2 takes ~28 k cycles to absorb one 128 x 256 tile (measured with the phase
+    // time stamps of scripts/gemm_timeline.py: 14.5 us per tile against 3.2 us of MMA time for a K = 768 GPT-2
+    // projection -- every small-K GEMM was bound by its epilogue stores).  The chunk is therefore transposed through the
+    // warp's 4 KB slab (XOR-swizzled 16-byte cells: conflict-free for the row-wise writes and the column-group reads) so
+    // that 8 lanes cover one row's 128 bytes and a store instruction writes four complete 128-byte lines.
+    float* slab = stash + (size_t)(warp - 2) * 1024;
+    auto store_chunk = [&](const float (&o)[32], int row0, int col0, bool mirrors) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3), c4 = lane & 7;
+        const float4 t = *reinterpret_cast<const float4*>(slab + r * 32 + ((c4 ^ (r & 7)) << 2));
+        const int64_t row = row0 + r;
+        if (row < p.M) {
+          const int col = col0 + c4 * 4;
+          if (p.C) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = t;
+          if (mirrors) {
+            if (p.C2) *reinterpret_cast<float4*>(p.C2 + row * p.ldc2 + col) = t;
+            split_store4(p.c_split, row, col, t);
+          }
+        }
+      }
+      __syncwarp();
+    };
     const int V = EPI == EPI_TOPK ? p.tk_vocab : p.N;                  // vocabulary columns; [n_vtiles*BN, N) is the tail block
     const int n_vtiles = (V + BN - 1) / BN;
     // EPI_TOPK state carried across the tiles of one row block: online log-sum-exp and a sorted top-TK list of this
@@ -417,6 +465,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       }
       mbar_wait(&tmem_full_bar[ab], (local >> 1) & 1);
       tcgen05_fence_after();
+      if (warp == 2 && lane == 0 && local < 16) TL(16 + 2 * local);
       if constexpr (EPI == EPI_TOPK) {
         if (m_tile != cur_block) {
           if (cur_block >= 0) tk_flush(cur_block);
@@ -476,7 +525,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             // tail block behind the (padded) vocabulary columns: a plain projection of the same A rows, stored to C with
             // sigmoid on its columns >= n_split (the legacy step's [dec_att | f_beta] of the NEXT step rides here)
             const int c_tail = n0 - n_vtiles * BN;
-            if (m < p.M) {
+            if (n0 + 32 <= p.N) {
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = pre_b ? bia[j >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[j] = __uint_as_float(v[j]) + b.x;         o[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+                o[j + 2] = __uint_as_float(v[j + 2]) + b.z; o[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+                if (c_tail + j >= p.n_split) {   // (n_split % 4 == 0: the tail block's halves are multiples of 4 wide)
+                  o[j] = sigmoid_fast_(o[j]); o[j + 1] = sigmoid_fast_(o[j + 1]); o[j + 2] = sigmoid_fast_(o[j + 2]); o[j + 3] = sigmoid_fast_(o[j + 3]);
+                }
+              }
+              store_chunk(o, m - lane, c_tail, false);
+            } else if (m < p.M) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int col = c_tail + j;
@@ -485,9 +546,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                   float4 t = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
                                          __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
                   if (col >= p.n_split) { t.x = sigmoid_fast_(t.x); t.y = sigmoid_fast_(t.y); t.z = sigmoid_fast_(t.z); t.w = sigmoid_fast_(t.w); }
-#ifdef CAPDEC_EXP_NOSTORE
-                  if (t.x == 1234.5f)
-#endif
                   *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + col) = t;
                 }
               }
@@ -588,38 +646,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               h2[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); h2[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
             }
             split_store8(p.c_split, m, j0, hv);
-          } else if (epi_is_store_family(EPI) && p.c_split.hi != nullptr && m < p.M && nb0 + 32 <= p.N &&
-                     (p.ldc & 3) == 0 && (p.c_split.ld & 7) == 0) {
-            // store-family epilogue whose output is (also) the next GEMM's operand: 8 columns at a time so each mirror
-            // store is 16 bytes; the fp32 copy is optional (C == nullptr when only the GEMM reads it)
+          } else if (epi_is_store_family(EPI) && nb0 + 32 <= p.N && (p.ldc & 3) == 0 && (!p.C2 || (p.ldc2 & 3) == 0) &&
+                     (p.c_split.hi == nullptr || (p.c_split.ld & 3) == 0)) {
+            // store-family epilogue on a full chunk: bias / activation in registers, then the coalesced store (fp32 copy
+            // optional: C == nullptr when only the next GEMM reads the output, through its operand mirror)
+            float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float4 b = pre_b ? bia[(j + u) >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float bb = ((j + u) & 3) == 0 ? b.x : ((j + u) & 3) == 1 ? b.y : ((j + u) & 3) == 2 ? b.z : b.w;
-                float tv = __uint_as_float(v[j + u]) + bb;
-                if (EPI == EPI_SIGMOID_TAIL && n0 + j + u >= p.n_split) tv = sigmoid_fast_(tv);
-                if (EPI == EPI_TANH) tv = tanh_fast_(tv);
-                if (EPI == EPI_GELU) tv = gelu_erf_(tv);
-                if (EPI == EPI_GELU_TANH) tv = gelu_tanh_(tv);
-                o[u] = tv;
-              }
-              if (p.C) {
-                float4* dst = reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n0 + j);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-              }
-              split_store8(p.c_split, m, n0 + j, o);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = pre_b ? bia[j >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[j] = __uint_as_float(v[j]) + b.x;         o[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + b.z; o[j + 3] = __uint_as_float(v[j + 3]) + b.w;
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (EPI == EPI_SIGMOID_TAIL && n0 + j >= p.n_split) o[j] = sigmoid_fast_(o[j]);
+              if (EPI == EPI_TANH) o[j] = tanh_fast_(o[j]);
+              if (EPI == EPI_GELU) o[j] = gelu_erf_(o[j]);
+              if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_(o[j]);
+            }
+            store_chunk(o, m - lane, n0, true);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bj = pre_b ? bia[j >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
               epilogue4<EPI, true>(p, m, n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]), pre_b ? &bia[j >> 2] : nullptr);
+                                   __uint_as_float(v[j + 3]), pre_b ? &bj : nullptr);
+            }
           }
         }
       }
+      if (warp == 2 && lane == 0 && local < 16) TL(17 + 2 * local);
       if constexpr (EPI == EPI_TOPK) {
         // {max, sum exp(x - max)} of this row over this tile half.  Kept per tile (not folded along the run) so that the
         // merge kernel can combine them in one canonical order: the result does not depend on how the tiles were
@@ -633,7 +689,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
   }
   tcgen05_fence_before();
+  if (threadIdx.x == 64) TL(62);
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair mode: the peer's shared memory / barriers stay alive until both are done
+  if (threadIdx.x == 0) TL(63);
   if (warp == 1) {
     tcgen05_fence_after();
     if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -768,7 +826,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
     auto kern = gemm_tcgen05_kernel<BN, E, TERMS, TKV, CG, KIND>;                                                 \
-    constexpr int smem = E == EPI_TOPK ? SmemLayout<BN, CG, TERMS>::kTotalTopk : SmemLayout<BN, CG, TERMS>::kTotal; \
+    constexpr int smem = SmemLayout<BN, CG, TERMS>::kTotal;                                                         \
     static std::atomic<bool> configured[kMaxDevices];   /* function attributes are per device */                 \
     const int dev_ = current_device();                                                                            \
     if (!configured[dev_].load()) {                                                                               \
@@ -1022,3 +1080,14 @@ void gemm_tc_release(capdec_handle* h) {
 }
 
 }  // namespace capdec
+
+#ifdef CAPDEC_TIMELINE
+extern "C" int capdec_debug_timeline(unsigned long long* host_out, int clear) {
+  if (clear) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, capdec::g_timeline) != cudaSuccess) return -1;
+    return cudaMemset(p, 0, sizeof(capdec::g_timeline)) == cudaSuccess ? 0 : -1;
+  }
+  return cudaMemcpyFromSymbol(host_out, capdec::g_timeline, sizeof(capdec::g_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif
