@@ -130,6 +130,12 @@ __device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.f + e
 __device__ __forceinline__ float gelu_tanh_(float x) {   // transformers.activations.NewGELUActivation
   return 0.5f * x * (1.f + tanhf(0.79788456080286535588f * (x + 0.044715f * x * x * x)));
 }
+// tensor-core modes: tanh through ex2.approx / rcp.approx (absolute error ~1e-7 on the (1 + tanh) factor; tanhf is ~30
+// instructions per element, which made the GPT-2 c_fc epilogue -- 32 k elements per 128 x 256 tile -- twice as long as
+// the tile's MMAs)
+__device__ __forceinline__ float gelu_tanh_fast_(float x) {
+  return 0.5f * x * (1.f + tanh_fast_(0.79788456080286535588f * (x + 0.044715f * x * x * x)));
+}
 __host__ __device__ constexpr bool epi_is_store_family(int e) { return e == 0 || e == 1 || e == 3 || e == 5 || e == 6; }
 
 // streaming 128-bit load: read-only path, do not allocate in L1 (tiles are read once per CTA)

@@ -23,7 +23,7 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
         if (EPI == EPI_SIGMOID_TAIL && n + j >= p.n_split) t = sig(t);
         if (EPI == EPI_TANH) t = th(t);
         if (EPI == EPI_GELU) t = gelu_erf_(t);
-        if (EPI == EPI_GELU_TANH) t = gelu_tanh_(t);
+        if (EPI == EPI_GELU_TANH) t = FAST ? gelu_tanh_fast_(t) : gelu_tanh_(t);
         if (p.C) p.C[(int64_t)m * p.ldc + n + j] = t;
         if (p.C2) p.C2[(int64_t)m * p.ldc2 + n + j] = t;
         split_store1(p.c_split, m, n + j, t);
@@ -43,7 +43,10 @@ __device__ __forceinline__ void epilogue4(const GemmArgs& p, int m, int n, float
     }
     if (EPI == EPI_TANH) { v0 = th(v0); v1 = th(v1); v2 = th(v2); v3 = th(v3); }
     if (EPI == EPI_GELU) { v0 = gelu_erf_(v0); v1 = gelu_erf_(v1); v2 = gelu_erf_(v2); v3 = gelu_erf_(v3); }
-    if (EPI == EPI_GELU_TANH) { v0 = gelu_tanh_(v0); v1 = gelu_tanh_(v1); v2 = gelu_tanh_(v2); v3 = gelu_tanh_(v3); }
+    if (EPI == EPI_GELU_TANH) {
+      if (FAST) { v0 = gelu_tanh_fast_(v0); v1 = gelu_tanh_fast_(v1); v2 = gelu_tanh_fast_(v2); v3 = gelu_tanh_fast_(v3); }
+      else      { v0 = gelu_tanh_(v0); v1 = gelu_tanh_(v1); v2 = gelu_tanh_(v2); v3 = gelu_tanh_(v3); }
+    }
     if (p.C) *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v0, v1, v2, v3);
     if (p.C2) *reinterpret_cast<float4*>(p.C2 + (int64_t)m * p.ldc2 + n) = make_float4(v0, v1, v2, v3);
     split_store4(p.c_split, m, n, make_float4(v0, v1, v2, v3));

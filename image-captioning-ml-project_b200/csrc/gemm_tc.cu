@@ -367,6 +367,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // that 8 lanes cover one row's 128 bytes and a store instruction writes four complete 128-byte lines.
     float* slab = stash + (size_t)(warp - 2) * 1024;
     auto store_chunk = [&](const float (&o)[32], int row0, int col0, bool mirrors) {
+#ifdef CAPDEC_EXP_NOSMEM
+      if (o[0] == 1234.5f && o[7] == 3.f && o[31] == o[13]) p.C[0] = o[3];
+      return;
+#endif
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -376,6 +380,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const int r = i * 4 + (lane >> 3), c4 = lane & 7;
         const float4 t = *reinterpret_cast<const float4*>(slab + r * 32 + ((c4 ^ (r & 7)) << 2));
         const int64_t row = row0 + r;
+#ifdef CAPDEC_EXP_NOGSTORE
+        if (t.x == 1234.5f && t.y == 77.f)
+#endif
         if (row < p.M) {
           const int col = col0 + c4 * 4;
           if (p.C) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = t;
@@ -662,7 +669,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               if (EPI == EPI_SIGMOID_TAIL && n0 + j >= p.n_split) o[j] = sigmoid_fast_(o[j]);
               if (EPI == EPI_TANH) o[j] = tanh_fast_(o[j]);
               if (EPI == EPI_GELU) o[j] = gelu_erf_(o[j]);
-              if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_(o[j]);
+              if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_fast_(o[j]);
             }
             store_chunk(o, m - lane, n0, true);
           } else {

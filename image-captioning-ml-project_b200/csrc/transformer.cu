@@ -198,26 +198,29 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
   }
 }
 
-// Two-pass form for up to 128 keys (every config of the path: prefix 10 + max_len <= 50), one warp per (row, head).
-// Pass 1: lane = key -- every lane resolves the address of ITS key once (prefix row or ancestor-indirected cache row)
-// and computes one COMPLETE q.k dot with 128-bit loads of the key's head slice (q is broadcast from shared memory), so
-// there is no per-key warp reduction; the softmax runs across the lanes.
-// Pass 2: lane = output element -- key p's value pointer and weight come from lane p by shuffle, the loads are coalesced.
+// Two-pass form for up to 128 keys (every config of the path: prefix 10 + max_len <= 50), one WARP per (row, head) and
+// nothing shared between the warps of a CTA: no staging of q through shared memory, no block barrier.  (The CTA-per-row
+// form this replaces spent its time in dependent phases -- ancestor lookup, q/k/v staging + barrier, two score rounds,
+// four value rounds of scalar loads -- at 16 % DRAM utilisation: 114 us per launch at 5120 rows x 12 heads.)
+//   lane = key:  every lane resolves the address of ITS key once (prefix row, ancestor-indirected cache row, or -- for
+//                the current position -- this step's projection output itself, so nothing waits for the cache append);
+//   pass 1:      a group of GL lanes (8 / 16 / 32 >= head_dim / 4) reads one key's head slice with one 128-bit load per
+//                lane, 32 / GL keys per round, 8 rounds in flight; the dot needs log2(GL) shuffle steps; scores pass
+//                through the warp's shared-memory strip to land in lane = key; softmax across the lanes;
+//   pass 2:      the same lane groups read the value slices (128-bit loads, 8 rounds in flight), each group accumulates
+//                its keys, the groups are summed with shuffles at the end.
+constexpr int kSaWarps = 4;
 template <int NK, int D4T>   // keys per lane (n_keys <= 32 * NK); head_dim / 4 when known at compile time (0 = runtime)
-__global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
+__global__ void __launch_bounds__(32 * kSaWarps) self_attn_decode3_kernel(const SelfAttnArgs a) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ __align__(16) float s_q[];   // [H] query of this row, then [heads][128] scores
-  const int r = blockIdx.x;
+  __shared__ float s_sc[kSaWarps][32 * NK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kSaWarps + warp;
+  if (item >= a.rows * a.heads) return;
+  const int r = item / a.heads, hd = item - r * a.heads;
   const int H = a.H, d = H / a.heads, d4 = D4T > 0 ? D4T : (d >> 2), T = a.T, t = a.t;
-  float* s_sc = s_q + H;
-  const float* qkv = a.qkv + (int64_t)r * a.ld_qkv;
-  float* kc = a.cache_k + ((int64_t)r * T + t) * H;
-  float* vc = a.cache_v + ((int64_t)r * T + t) * H;
-  // every lane resolves the address of its key(s) first: the ancestor-table lookup does not depend on this step's q/k/v,
-  // so its latency overlaps the q/k/v staging below
-  const int hd = warp;
+  const float* qkv = a.qkv + (int64_t)r * a.ld_qkv + hd * d;   // this head's slice of q; k at + H, v at + 2H
   const int img = r / a.rows_per_image;
   const int n_keys = a.n_prefix + t + 1;
   const float* kptr[NK];
@@ -225,49 +228,49 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
 #pragma unroll
   for (int i = 0; i < NK; ++i) {
     const int p = lane + 32 * i;
-    kptr[i] = a.cache_k; vptr[i] = a.cache_v;
-    if (p < n_keys && hd < a.heads) {
+    kptr[i] = qkv + H; vptr[i] = qkv + 2 * H;    // the current position (and a valid address for the unused lanes)
+    if (p < n_keys - 1) {
       if (p < a.n_prefix) {
         const int64_t off = ((int64_t)img * a.n_prefix + p) * H + hd * d;
         kptr[i] = a.prefix_k + off; vptr[i] = a.prefix_v + off;
       } else {
         const int pos = p - a.n_prefix;
-        const int prow = (pos == t || !a.anc) ? r : a.anc[(int64_t)r * T + pos];
+        const int prow = a.anc ? a.anc[(int64_t)r * T + pos] : r;
         const int64_t off = ((int64_t)prow * T + pos) * H + hd * d;
         kptr[i] = a.cache_k + off; vptr[i] = a.cache_v + off;
       }
     }
   }
-  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
-    reinterpret_cast<float4*>(s_q)[i] = reinterpret_cast<const float4*>(qkv)[i];
-    reinterpret_cast<float4*>(kc)[i] = reinterpret_cast<const float4*>(qkv + H)[i];
-    reinterpret_cast<float4*>(vc)[i] = reinterpret_cast<const float4*>(qkv + 2 * H)[i];
-  }
-  __syncthreads();
-  if (hd >= a.heads) return;
-  // ---- pass 1: scores.  A group of GL lanes (8 / 16 / 32 >= head_dim / 4) reads one key's head slice with one coalesced
-  // 128-bit load per lane, so a warp handles 32 / GL keys per round and the dot needs log2(GL) shuffle steps; the
-  // key's address comes from the lane that resolved it.  Scores pass through shared memory to land in lane = key.
-  const float4* q4 = reinterpret_cast<const float4*>(s_q + hd * d);
-  float* my_sc = s_sc + warp * 128;
   const int GL = d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
   const int kpr = 32 / GL, sub = lane % GL, grp = lane / GL;
-  const float4 qv = sub < d4 ? q4[sub] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 qv = sub < d4 ? reinterpret_cast<const float4*>(qkv)[sub] : zero4;
+  if (grp == 0 && sub < d4) {   // append this position's K / V head slice to the cache (read by LATER steps only)
+    const int64_t off = ((int64_t)r * T + t) * H + hd * d;
+    reinterpret_cast<float4*>(a.cache_k + off)[sub] = reinterpret_cast<const float4*>(qkv + H)[sub];
+    reinterpret_cast<float4*>(a.cache_v + off)[sub] = reinterpret_cast<const float4*>(qkv + 2 * H)[sub];
+  }
+  // the address held by lane (p & 31), slot (p >> 5)
+  auto ptr_of = [&](const float* const (&tab)[NK], int p) {
+    const float* sel = nullptr;
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const float* cand = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)tab[i], p & 31));
+      if (i == (p >> 5)) sel = cand;
+    }
+    return sel;
+  };
+  float* my_sc = s_sc[warp];
   constexpr int UR = 8;
-  for (int p0 = 0; p0 < n_keys; p0 += UR * kpr) {   // UR rounds at a time: their key loads are all in flight together
+  // ---- pass 1: scores
+  for (int p0 = 0; p0 < n_keys; p0 += UR * kpr) {
     int pk[UR];
     float4 kv[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       pk[u] = p0 + u * kpr + grp;
-      const int p = min(pk[u], n_keys - 1);
-      const float* kp = nullptr;
-#pragma unroll
-      for (int i = 0; i < NK; ++i) {
-        const float* cand = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)kptr[i], p & 31));
-        if (i == (p >> 5)) kp = cand;
-      }
-      kv[u] = sub < d4 ? reinterpret_cast<const float4*>(kp)[sub] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* kp = ptr_of(kptr, min(pk[u], n_keys - 1));
+      kv[u] = sub < d4 ? reinterpret_cast<const float4*>(kp)[sub] : zero4;
     }
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
@@ -295,39 +298,39 @@ __global__ void self_attn_decode2_kernel(const SelfAttnArgs a) {
   for (int i = 0; i < NK; ++i) { sc[i] = expf(sc[i] - m); l += sc[i]; }   // exp(-inf) = 0 for the unused slots
   l = warp_sum(l);
   const float inv = 1.f / l;
-  // ---- pass 2: weighted values, lane = output element (up to 4 strided elements of the head dimension, d <= 128)
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- pass 2: weighted values
+  float4 acc = zero4;
+  for (int p0 = 0; p0 < n_keys; p0 += UR * kpr) {
+    float w[UR];
+    float4 vv[UR];
 #pragma unroll
-  for (int i = 0; i < NK; ++i) {
-    const int n_here = min(32, n_keys - 32 * i);
-    for (int p0 = 0; p0 < n_here; p0 += 8) {   // 8 keys per round: up to 16-32 independent loads in flight per lane
-      float w[8];
-      const float* vp[8];
+    for (int u = 0; u < UR; ++u) {
+      const int pku = p0 + u * kpr + grp;
+      const int p = min(pku, n_keys - 1);
+      float wv = 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int pl = min(p0 + u, n_here - 1);
-        const float wv = __shfl_sync(0xffffffffu, sc[i], pl);
-        vp[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)vptr[i], pl));
-        w[u] = p0 + u < n_here ? wv : 0.f;
+      for (int i = 0; i < NK; ++i) {
+        const float cand = __shfl_sync(0xffffffffu, sc[i], p & 31);
+        if (i == (p >> 5)) wv = cand;
       }
-      float x[8][4];
+      w[u] = pku < n_keys ? wv : 0.f;
+      const float* vp = ptr_of(vptr, p);
+      vv[u] = sub < d4 ? reinterpret_cast<const float4*>(vp)[sub] : zero4;
+    }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const int e = lane + 32 * j; x[u][j] = e < d ? vp[u][e] : 0.f; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[u], x[u][j], acc[j]);
+    for (int u = 0; u < UR; ++u) {
+      acc.x = fmaf(w[u], vv[u].x, acc.x); acc.y = fmaf(w[u], vv[u].y, acc.y);
+      acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int e = lane + 32 * j;
-    if (e < d) {
-      a.out[(int64_t)r * a.ld_out + hd * d + e] = acc[j] * inv;
-      split_store1(a.out_split, r, hd * d + e, acc[j] * inv);
-    }
+  for (int o = GL; o < 32; o <<= 1) {   // sum the key groups
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (grp == 0 && sub < d4) {
+    const float4 o4 = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    reinterpret_cast<float4*>(a.out + (int64_t)r * a.ld_out + hd * d)[sub] = o4;
+    split_store4(a.out_split, r, hd * d + sub * 4, o4);
   }
 }
 
@@ -373,13 +376,15 @@ int self_attn_decode(const SelfAttnArgs& a, cudaStream_t s) {
                  a.heads ? a.H / a.heads : 0);
   if (a.rows == 0) return CAPDEC_OK;
   const int n_keys = a.n_prefix + a.t + 1;
-  if (n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && (a.H + a.heads * 128) * sizeof(float) <= 48 * 1024) {
-    const size_t smem = ((size_t)a.H + (size_t)a.heads * 128) * sizeof(float);
+  if (n_keys <= 128 && (a.H / a.heads) % 4 == 0 && a.ld_qkv % 4 == 0 && a.ld_out % 4 == 0 && a.H % 4 == 0 &&
+      (a.out_split.hi == nullptr || a.out_split.ld % 4 == 0) &&
+      ((((uintptr_t)a.qkv | (uintptr_t)a.cache_k | (uintptr_t)a.cache_v | (uintptr_t)a.prefix_k | (uintptr_t)a.prefix_v | (uintptr_t)a.out) & 15) == 0)) {
     const int d4 = a.H / a.heads / 4;
+    const dim3 grid(ceil_div(a.rows * a.heads, kSaWarps)), block(32 * kSaWarps);
 #define CAPDEC_SA_LAUNCH(NKV)                                                                               \
-    if (d4 == 16)      CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 16>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));  \
-    else if (d4 == 24) CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 24>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));  \
-    else               CAPDEC_CHECK_CUDA(launch_k(self_attn_decode2_kernel<NKV, 0>, dim3(a.rows), dim3(32 * a.heads), smem, s, true, a));
+    if (d4 == 16)      CAPDEC_CHECK_CUDA(launch_k(self_attn_decode3_kernel<NKV, 16>, grid, block, 0, s, true, a));  \
+    else if (d4 == 24) CAPDEC_CHECK_CUDA(launch_k(self_attn_decode3_kernel<NKV, 24>, grid, block, 0, s, true, a));  \
+    else               CAPDEC_CHECK_CUDA(launch_k(self_attn_decode3_kernel<NKV, 0>, grid, block, 0, s, true, a));
     if (n_keys <= 32)      { CAPDEC_SA_LAUNCH(1) }
     else if (n_keys <= 64) { CAPDEC_SA_LAUNCH(2) }
     else                   { CAPDEC_SA_LAUNCH(4) }
