@@ -752,9 +752,11 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
   { StageScope sc(h, STAGE_GATHER, s);
     CAPDEC_RETURN_IF(embed_pos(S.next_tok, h->W("model.transformer.wte.weight"), wpe->p + (size_t)(P + t) * H, S.tx, rows, H, s)); }
   const float* pending = nullptr;
+  // the pre-LN outputs feed GEMMs only: when those read the operand mirror (S.mx) the fp32 copy is never written
+  float* const txn_out = S.mx.hi ? nullptr : S.txn;
   for (int l = 0; l < c.num_layers; ++l) {
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W(gl(l, "ln_1.weight")), h->W(gl(l, "ln_1.bias")), pending ? S.tx : nullptr, S.txn, rows, H, eps, s, &S.mx));
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W(gl(l, "ln_1.weight")), h->W(gl(l, "ln_1.bias")), pending ? S.tx : nullptr, txn_out, rows, H, eps, s, &S.mx));
       CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "attn.c_attn"), S.tqkv, 3 * H, rows, EPI_STORE, s, nullptr, 0, &S.mx)); }
     { StageScope sc(h, STAGE_ATTENTION, s);
       SelfAttnArgs a{};
@@ -767,14 +769,14 @@ int step_gpt2(const capdec_handle* h, Session& S, int t, cudaStream_t s) {
       CAPDEC_RETURN_IF(self_attn_decode(a, s)); }
     { StageScope sc(h, STAGE_SMALL_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.tsa, H, gl(l, "attn.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.msa));
-      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(gl(l, "ln_2.weight")), h->W(gl(l, "ln_2.bias")), S.tx, S.txn, rows, H, eps, s, &S.mx)); }
+      CAPDEC_RETURN_IF(add_layernorm(S.tx, S.ty, h->W(gl(l, "ln_2.weight")), h->W(gl(l, "ln_2.bias")), S.tx, txn_out, rows, H, eps, s, &S.mx)); }
     { StageScope sc(h, STAGE_GATE_GEMM, s);
       CAPDEC_RETURN_IF(linear(h, S.txn, H, gl(l, "mlp.c_fc"), S.mff.hi ? nullptr : S.tff, F, rows, EPI_GELU_TANH, s, nullptr, 0, &S.mx, &S.mff));
       CAPDEC_RETURN_IF(linear(h, S.tff, F, gl(l, "mlp.c_proj"), S.ty, H, rows, EPI_STORE, s, nullptr, 0, &S.mff)); }
     pending = S.ty;
   }
   { StageScope sc(h, STAGE_SMALL_GEMM, s);
-    CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, S.txn, rows, H, eps, s, &S.mx)); }
+    CAPDEC_RETURN_IF(add_layernorm(S.tx, pending, h->W("model.transformer.ln_f.weight"), h->W("model.transformer.ln_f.bias"), S.tx, txn_out, rows, H, eps, s, &S.mx)); }
   StageScope sc(h, STAGE_VOCAB_GEMM, s);
   // lm_head is tied to wte and has no bias
   return vocab_project(h, S, S.txn, H, h->W("model.lm_head.weight"), nullptr, rows, S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, s);

@@ -176,10 +176,14 @@ __device__ __forceinline__ void p24_encode4_(float4 v, uint2* hi, uint32_t* q, f
   *rem = make_float4(v.x - __uint_as_float(b0 & 0xffff0000u), v.y - __uint_as_float(b1 & 0xffff0000u),
                      v.z - __uint_as_float(b2 & 0xffff0000u), v.w - __uint_as_float(b3 & 0xffff0000u));
 }
+// {bf16_rn(a), bf16_rn(b)} in one word (a in the low half) + the remainders a - hi, b - hi.  One packed conversion
+// (F2FP.BF16.PACK_AB) instead of two scalar F2F.BF16.F32: the scalar form runs on the quarter-rate conversion / MUFU pipe,
+// which the GELU epilogues and the attention kernels' operand mirrors saturate.
 __device__ __forceinline__ uint32_t pack_bf16x2_(float a, float b, float* ra, float* rb) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  *ra = a - __bfloat162float(ha); *rb = b - __bfloat162float(hb);
-  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  *ra = a - __uint_as_float(d << 16); *rb = b - __uint_as_float(d & 0xffff0000u);
+  return d;
 }
 // write v (4 consecutive columns starting at `col`, col % 4 == 0) of row `row` into the split copies
 __device__ __forceinline__ void split_store4(const SplitDst& d, int64_t row, int col, float4 v) {

@@ -38,7 +38,11 @@ __device__ __forceinline__ void tl_stamp(int i) {
   g_timeline[0][blockIdx.x][i] = t;
   g_timeline[1][blockIdx.x][i] = (unsigned long long)clock64();
 }
+#ifdef CAPDEC_TL_EPI
+#define TL(i) do { if (EPI == CAPDEC_TL_EPI) tl_stamp(i); } while (0)   /* only launches with this epilogue (in-situ probe) */
+#else
 #define TL(i) tl_stamp(i)
+#endif
 #else
 #define TL(i)
 #endif
@@ -366,11 +370,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // warp's 4 KB slab (XOR-swizzled 16-byte cells: conflict-free for the row-wise writes and the column-group reads) so
     // that 8 lanes cover one row's 128 bytes and a store instruction writes four complete 128-byte lines.
     float* slab = stash + (size_t)(warp - 2) * 1024;
+    // Mirror-only output (C == nullptr: only the next GEMM reads it) in the bf16 operand type: the chunk is converted
+    // first and transposed as packed bf16 -- a row of the chunk is 64 bytes, 4 lanes x 16 bytes, 8 rows per store.
+    auto store_chunk_bf16 = [&](const float (&o)[32], int row0, int col0) {
+      uint32_t hw[16], lw[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float r0, r1, d0, d1;
+        hw[j] = pack_bf16x2_(o[2 * j], o[2 * j + 1], &r0, &r1);
+        lw[j] = TERMS == 3 ? pack_bf16x2_(r0, r1, &d0, &d1) : 0u;
+      }
+      uint4* cell = reinterpret_cast<uint4*>(slab);   // [32 rows][4 cells of 16 bytes], cell index XOR-swizzled by (row >> 1) & 3
+#pragma unroll
+      for (int pass = 0; pass < (TERMS == 3 ? 2 : 1); ++pass) {
+        const uint32_t* w = pass ? lw : hw;
+        char* plane = reinterpret_cast<char*>(pass ? p.c_split.lo : p.c_split.hi);
+        if (pass) __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          cell[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2), c = lane & 3;
+          const uint4 t = cell[r * 4 + (c ^ ((r >> 1) & 3))];
+          const int64_t row = row0 + r;
+          if (row < p.M) *reinterpret_cast<uint4*>(plane + (row * p.c_split.ld + col0 + c * 8) * 2) = t;
+        }
+      }
+      __syncwarp();
+    };
     auto store_chunk = [&](const float (&o)[32], int row0, int col0, bool mirrors) {
-#ifdef CAPDEC_EXP_NOSMEM
-      if (o[0] == 1234.5f && o[7] == 3.f && o[31] == o[13]) p.C[0] = o[3];
-      return;
-#endif
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -380,9 +410,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const int r = i * 4 + (lane >> 3), c4 = lane & 7;
         const float4 t = *reinterpret_cast<const float4*>(slab + r * 32 + ((c4 ^ (r & 7)) << 2));
         const int64_t row = row0 + r;
-#ifdef CAPDEC_EXP_NOGSTORE
-        if (t.x == 1234.5f && t.y == 77.f)
-#endif
         if (row < p.M) {
           const int col = col0 + c4 * 4;
           if (p.C) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = t;
@@ -669,9 +696,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               if (EPI == EPI_SIGMOID_TAIL && n0 + j >= p.n_split) o[j] = sigmoid_fast_(o[j]);
               if (EPI == EPI_TANH) o[j] = tanh_fast_(o[j]);
               if (EPI == EPI_GELU) o[j] = gelu_erf_(o[j]);
-              if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_fast_(o[j]);
+              if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_fast_(o[j]);   // (MUFU.TANH's 2^-11 was measured: it breaks the bf16 mode's 2e-2 bar at 124M)
             }
-            store_chunk(o, m - lane, n0, true);
+            if (KIND == KIND_BF16 && p.C == nullptr && p.C2 == nullptr && p.c_split.hi != nullptr && p.c_split.kind == KIND_BF16 &&
+                p.c_split.b8 == nullptr && (TERMS == 3) == (p.c_split.lo != nullptr) && (p.c_split.ld & 7) == 0)
+              store_chunk_bf16(o, m - lane, n0);
+            else
+              store_chunk(o, m - lane, n0, true);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -733,18 +764,15 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t ld, int rows, 
     reinterpret_cast<float4*>(hi)[i] = h;
     if (lo) reinterpret_cast<float4*>(lo)[i] = l;
   } else {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                        h3 = __float2bfloat16_rn(v.w);
+    float r0, r1, r2, r3, d0, d1;
     uint2 hp;
-    hp.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    hp.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    hp.x = pack_bf16x2_(v.x, v.y, &r0, &r1);
+    hp.y = pack_bf16x2_(v.z, v.w, &r2, &r3);
     reinterpret_cast<uint2*>(hi)[i] = hp;
     if (lo) {
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                          l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
       uint2 lp;
-      lp.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-      lp.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+      lp.x = pack_bf16x2_(r0, r1, &d0, &d1);
+      lp.y = pack_bf16x2_(r2, r3, &d0, &d1);
       reinterpret_cast<uint2*>(lo)[i] = lp;
     }
   }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(32 * kLnRowsPerCta) add_layernorm_warp_kernel(
       if (sum_out) reinterpret_cast<float4*>(sum_out + (int64_t)r * H)[i] = v[j];
       const float4 o = make_float4((v[j].x - mean) * rstd * g.x + bt.x, (v[j].y - mean) * rstd * g.y + bt.y,
                                    (v[j].z - mean) * rstd * g.z + bt.z, (v[j].w - mean) * rstd * g.w + bt.w);
-      reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;
+      if (out) reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;   // (nullptr: only the operand mirror is consumed)
       split_store4(split, r, i * 4, o);
     }
   }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     if (sum_out) reinterpret_cast<float4*>(sum_out + (int64_t)r * H)[i] = sv;
     const float4 o = make_float4((sv.x - mean) * rstd * g.x + bt.x, (sv.y - mean) * rstd * g.y + bt.y,
                                  (sv.z - mean) * rstd * g.z + bt.z, (sv.w - mean) * rstd * g.w + bt.w);
-    reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;
+    if (out) reinterpret_cast<float4*>(out + (int64_t)r * H)[i] = o;
     split_store4(split, r, i * 4, o);
   }
 }
@@ -201,7 +201,10 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 // Two-pass form for up to 128 keys (every config of the path: prefix 10 + max_len <= 50), one WARP per (row, head) and
 // nothing shared between the warps of a CTA: no staging of q through shared memory, no block barrier.  (The CTA-per-row
 // form this replaces spent its time in dependent phases -- ancestor lookup, q/k/v staging + barrier, two score rounds,
-// four value rounds of scalar loads -- at 16 % DRAM utilisation: 114 us per launch at 5120 rows x 12 heads.)
+// four value rounds of scalar loads -- at 16 % DRAM utilisation: 114 us per launch at 5120 rows x 12 heads; this form
+// 88 us, issue-bound.  A single-pass online-softmax variant with K and V loads in flight together and no weight / pointer
+// shuffles in the value pass was measured SLOWER, 112 us: 70 instead of 48 registers and every lane of a key group
+// repeating the key's exp.)
 //   lane = key:  every lane resolves the address of ITS key once (prefix row, ancestor-indirected cache row, or -- for
 //                the current position -- this step's projection output itself, so nothing waits for the cache append);
 //   pass 1:      a group of GL lanes (8 / 16 / 32 >= head_dim / 4) reads one key's head slice with one 128-bit load per

@@ -28,6 +28,53 @@ def fetch():
     return buf
 
 
+def report(g, c, title):
+    live = g[:, 0] > 0
+    g, c = g[live].astype(np.int64), c[live].astype(np.int64)
+    t0 = g[:, 0].min()
+    print(f"== {title}: {live.sum()} CTAs; first entry -> last exit {(g[:, 63].max() - t0) / 1e3:.2f} us")
+
+    def med(i):
+        x = g[:, i]
+        x = x[x > 0]
+        return (np.median(x) - t0) / 1e3 if len(x) else float("nan")
+
+    def mx(i):
+        x = g[:, i]
+        x = x[x > 0]
+        return (x.max() - t0) / 1e3 if len(x) else float("nan")
+
+    def cyc(i, j):
+        ok = (c[:, i] > 0) & (c[:, j] > 0)
+        return float(np.median(c[ok, i] - c[ok, j])) if ok.any() else float("nan")
+    print(f"   entry med {med(0):.2f} max {mx(0):.2f} | setup done {med(1):.2f} | pdl wait done {med(2):.2f} | first TMA issued {med(3):.2f} "
+          f"| first operands landed {med(5):.2f} | last TMA issued {med(4):.2f}")
+    items = [i for i in range(8) if (g[:, 8 + i] > 0).any()]
+    print("   MMAs of item i issued:   " + "  ".join(f"{i}:{med(8 + i):.2f}" for i in items))
+    items = [i for i in range(16) if (g[:, 16 + 2 * i] > 0).any()]
+    print("   epilogue start / end:    " + "  ".join(f"{i}:{med(16 + 2 * i):.2f}/{med(17 + 2 * i):.2f}" for i in items))
+    print(f"   cycles: setup {cyc(1, 0):.0f}, pdl wait {cyc(2, 1):.0f}, first operands after wait {cyc(5, 2):.0f}, "
+          f"epilogue of item 0 {cyc(17, 16):.0f}, last epilogue end -> exit {cyc(63, 62):.0f}")
+    print(f"   epilogue warps done med {med(62):.2f} max {mx(62):.2f} | exit med {med(63):.2f} max {mx(63):.2f}")
+
+
+if prec == "decode":
+    # in-situ probe (build with -DCAPDEC_TL_EPI=<epilogue id>): the LAST launch with that epilogue inside a GPT-2 124M decode
+    from tests.helpers import gpt2_decoder
+    torch.set_grad_enabled(False)
+    mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    m, _ = gpt2_decoder(H=768, layers=12, heads=12, V=50257, max_length=64); m.precision = mode; m = m.to(dev)
+    ef = {"pooled_features": torch.randn(1024, 768, device=dev)}
+    for _ in range(2):
+        m.generate(ef, 20, num_beams=5)
+    torch.cuda.synchronize()
+    lib.capdec_debug_timeline(None, 1)
+    m.generate(ef, 20, num_beams=5)
+    torch.cuda.synchronize()
+    g, c = fetch()
+    report(g, c, f"last stamped GEMM launch of a GPT-2 124M beam-5 decode, 1024 images, {mode}")
+    sys.exit(0)
+
 for name, M, N, K in SHAPES:
     a = torch.randn(M, K, device=dev)
     w = torch.randn(N, K, device=dev) * 0.02
