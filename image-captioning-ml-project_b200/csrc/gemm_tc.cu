@@ -606,23 +606,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (n0 + j >= V) x[j] = -INFINITY;
             }
-            float cm = x[0];
+            // The epilogue of a vocabulary tile has to fit under the tile's MMAs (K = 512, three terms: ~12 k cycles) with
+            // two epilogue warps per scheduler, so dependent chains and issue slots both count (phase time stamps of
+            // scripts/gemm_timeline.py: 8.5 us of epilogue against 7.7 us of MMA per tile before this form): the chunk
+            // maximum is a tree and the exponentials are FADD + FMUL + MUFU.EX2 (expf's range fix-up is not needed: terms
+            // below 2^-126 may flush to zero in a sum that contains exp(0) = 1).
+            float t8[8];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, x[j]);
-            if (cm > rmax) { rsum *= __expf(rmax - cm); rmax = cm; }   // x[0] is always a real column, so cm is finite
+            for (int j = 0; j < 8; ++j) t8[j] = fmaxf(fmaxf(x[4 * j], x[4 * j + 1]), fmaxf(x[4 * j + 2], x[4 * j + 3]));
+            const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
+            constexpr float kLog2e = 1.4426950408889634f;
+            if (cm > rmax) { rsum *= ex2_approx_((rmax - cm) * kLog2e); rmax = cm; }   // x[0] is always a real column, so cm is finite
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rsum += __expf(x[j] - rmax);
+            for (int j = 0; j < 32; ++j) rsum += ex2_approx_((x[j] - rmax) * kLog2e);   // (column order: the sum's bits are part of the parity record)
             // Candidates of this chunk: columns above the row's current TK-th best.  Lanes (rows) find theirs at
             // different columns, so walking the columns in lockstep would make the warp pay for the union; instead the
             // chunk is parked in shared memory ([column][lane], conflict-free) and every lane pops ITS next candidate per
-            // round -- the number of rounds is the largest per-lane count, not the size of the union.
-            float* st = stash + (size_t)(warp - 2) * 1024 + lane;
-            unsigned cand = 0u;
+            // round -- the number of rounds is the largest per-lane count, not the size of the union.  A chunk in which no
+            // row of the warp has a candidate (cm <= its threshold everywhere) is not parked at all.
             const float thr = tv[TK - 1];
+            unsigned cand = 0u;
+            float* st = stash + (size_t)(warp - 2) * 1024 + lane;
+            if (__any_sync(0xffffffffu, cm > thr)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              st[j * 32] = x[j];
-              cand |= (x[j] > thr ? 1u : 0u) << j;
+              for (int j = 0; j < 32; ++j) {
+                st[j * 32] = x[j];
+                if (x[j] > thr) cand |= 1u << j;
+              }
             }
             while (__any_sync(0xffffffffu, cand != 0u)) {
               if (cand != 0u) {

@@ -58,6 +58,23 @@ def report(g, c, title):
     print(f"   epilogue warps done med {med(62):.2f} max {mx(62):.2f} | exit med {med(63):.2f} max {mx(63):.2f}")
 
 
+if prec == "legacy":
+    # in-situ probe on the headline config (legacy decoder, beam 5, 4096 images, bf16x3): -DCAPDEC_TL_EPI=7 stamps the
+    # vocabulary GEMM (fused top-k), =2 the gate GEMM (LSTM epilogue)
+    from tests.helpers import legacy_weights
+    torch.set_grad_enabled(False)
+    m, _ = legacy_weights(10000, 0); m.precision = "bf16x3"; m = m.to(dev)
+    enc = torch.randn(int(sys.argv[2]) if len(sys.argv) > 2 else 4096, 196, 2048, device=dev).relu_()
+    for _ in range(2):
+        m.beam_search(enc, beam_size=5, max_length=20)
+    torch.cuda.synchronize()
+    lib.capdec_debug_timeline(None, 1)
+    m.beam_search(enc, beam_size=5, max_length=20)
+    torch.cuda.synchronize()
+    g, c = fetch()
+    report(g, c, f"last stamped GEMM launch of the legacy beam-5 decode, {enc.shape[0]} images, bf16x3")
+    sys.exit(0)
+
 if prec == "decode":
     # in-situ probe (build with -DCAPDEC_TL_EPI=<epilogue id>): the LAST launch with that epilogue inside a GPT-2 124M decode
     from tests.helpers import gpt2_decoder
