@@ -50,6 +50,30 @@ __device__ __forceinline__ void tl_stamp(int i) {
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// explicit shared-space accesses for the epilogue's staging slab: its address comes out of integer alignment arithmetic on
+// the dynamic shared-memory base, so plain dereferences compile to GENERIC ld / st (ST.E / LD.E in the SASS)
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -369,7 +393,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // projection -- every small-K GEMM was bound by its epilogue stores).  The chunk is therefore transposed through the
     // warp's 4 KB slab (XOR-swizzled 16-byte cells: conflict-free for the row-wise writes and the column-group reads) so
     // that 8 lanes cover one row's 128 bytes and a store instruction writes four complete 128-byte lines.
-    float* slab = stash + (size_t)(warp - 2) * 1024;
+    const uint32_t slab_a = smem_u32(stash) + (uint32_t)(warp - 2) * 4096u;   // this warp's 4 KB slab (shared-space address)
     // Mirror-only output (C == nullptr: only the next GEMM reads it) in the bf16 operand type: the chunk is converted
     // first and transposed as packed bf16 -- a row of the chunk is 64 bytes, 4 lanes x 16 bytes, 8 rows per store.
     auto store_chunk_bf16 = [&](const float (&o)[32], int row0, int col0) {
@@ -380,7 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         hw[j] = pack_bf16x2_(o[2 * j], o[2 * j + 1], &r0, &r1);
         lw[j] = TERMS == 3 ? pack_bf16x2_(r0, r1, &d0, &d1) : 0u;
       }
-      uint4* cell = reinterpret_cast<uint4*>(slab);   // [32 rows][4 cells of 16 bytes], cell index XOR-swizzled by (row >> 1) & 3
+      // slab as [32 rows][4 cells of 16 bytes], cell index XOR-swizzled by (row >> 1) & 3
 #pragma unroll
       for (int pass = 0; pass < (TERMS == 3 ? 2 : 1); ++pass) {
         const uint32_t* w = pass ? lw : hw;
@@ -388,12 +412,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         if (pass) __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          cell[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          sts128u(slab_a + (uint32_t)(lane * 4 + (j ^ ((lane >> 1) & 3))) * 16u, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + (lane >> 2), c = lane & 3;
-          const uint4 t = cell[r * 4 + (c ^ ((r >> 1) & 3))];
+          const uint4 t = lds128u(slab_a + (uint32_t)(r * 4 + (c ^ ((r >> 1) & 3))) * 16u);
           const int64_t row = row0 + r;
           if (row < p.M) *reinterpret_cast<uint4*>(plane + (row * p.c_split.ld + col0 + c * 8) * 2) = t;
         }
@@ -403,12 +427,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     auto store_chunk = [&](const float (&o)[32], int row0, int col0, bool mirrors) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        sts128(slab_a + (uint32_t)(lane * 32 + ((j ^ (lane & 7)) << 2)) * 4u, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + (lane >> 3), c4 = lane & 7;
-        const float4 t = *reinterpret_cast<const float4*>(slab + r * 32 + ((c4 ^ (r & 7)) << 2));
+        const float4 t = lds128(slab_a + (uint32_t)(r * 32 + ((c4 ^ (r & 7)) << 2)) * 4u);
         const int64_t row = row0 + r;
         if (row < p.M) {
           const int col = col0 + c4 * 4;
@@ -626,11 +650,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             // row of the warp has a candidate (cm <= its threshold everywhere) is not parked at all.
             const float thr = tv[TK - 1];
             unsigned cand = 0u;
-            float* st = stash + (size_t)(warp - 2) * 1024 + lane;
+            const uint32_t st = slab_a + (uint32_t)lane * 4u;   // [column][lane]
             if (__any_sync(0xffffffffu, cm > thr)) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                st[j * 32] = x[j];
+                sts32(st + (uint32_t)j * 128u, x[j]);
                 if (x[j] > thr) cand |= 1u << j;
               }
             }
@@ -638,7 +662,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               if (cand != 0u) {
                 const int j = __ffs(cand) - 1;
                 cand &= cand - 1u;
-                const float xv = st[j * 32];
+                const float xv = lds32(st + (uint32_t)j * 128u);
                 if (xv > tv[TK - 1]) {
                   // branch-free sorted insert: x lands behind any equal value, so the lower vocabulary index stays
                   // ahead among equal logits (columns are popped in increasing order)
