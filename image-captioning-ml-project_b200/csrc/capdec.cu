@@ -143,6 +143,7 @@ struct Session {
   SplitDst mmem{};                    // transformer prologue: mirror of the projected memory (A operand of the 2 x layers hoisted K / V GEMMs)
   // fused vocabulary projection + log-softmax + top-k (EPI_TOPK): partial records instead of logits
   float* tk_part = nullptr; float* tk_lse = nullptr; int fuse_k = 0;
+  float* samp_lse = nullptr;            // sampling on the tensor-core path: the logits GEMM's {max, sum exp} partials [R, tk_lse_pairs(V), 2]
   // legacy, tensor-core modes: the producers of the gate / vocabulary GEMM operands (attention context, state gather,
   // LSTM epilogue) write the hi/lo operand copies themselves, so no split pass runs inside the step loop
   void* xs_hi = nullptr; void* xs_lo = nullptr; void* hs_hi = nullptr; void* hs_lo = nullptr; bool presplit = false;
@@ -212,7 +213,10 @@ int carve(const capdec_handle* h, Arena& ar, Session& S, int B, int L, int k, in
       S.tk_part = ar.take<float>(R * tk_records(S.R, S.tk_ntotal) * tk_stride(S.fuse_k));
       S.tk_lse = ar.take<float>(R * tk_lse_pairs(V) * 2);
     }
-    else { S.logits_ld = (V + 3) & ~3; S.logits = ar.take<float>(R * S.logits_ld); }
+    else {
+      S.logits_ld = (V + 3) & ~3; S.logits = ar.take<float>(R * S.logits_ld);
+      if (mode == MODE_SAMPLE && c.precision != CAPDEC_PREC_FP32) S.samp_lse = ar.take<float>(R * tk_lse_pairs(V) * 2);
+    }
   };
   if (is_tf_family(h)) {
     const DevTensor* f1 = h->find(is_gpt2(h) ? "model.transformer.h.0.mlp.c_fc.weight" : "transformer_decoder.layers.0.linear1.weight");
@@ -387,6 +391,7 @@ int vocab_project(const capdec_handle* h, Session& S, const float* A, int64_t ld
     return gemm(h, c.precision, g, EPI_TOPK, s);
   }
   g.C = logits; g.ldc = ld_logits;
+  if (S.samp_lse && logits == S.logits) { g.tk_lse = S.samp_lse; g.tk_vocab = c.vocab_size; }   // partials for the sampler
   return gemm(h, c.precision, g, EPI_STORE, s);
 }
 
@@ -1364,8 +1369,12 @@ int capdec_decode_sample(capdec_handle* h, const float* feats, const float* pool
   for (int t = 0; t + 1 < T; ++t) {  // trainer.py:413
     CAPDEC_RETURN_IF(step_any(h, S, feats, mask, nullptr, 0, t, s));
     { StageScope sc(h, STAGE_SELECT, s);
-      CAPDEC_RETURN_IF(sample_rows(S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
-                                   with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s)); }
+      if (S.samp_lse)
+        CAPDEC_RETURN_IF(sample_rows_partials(S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, S.R, c.vocab_size, S.samp_lse, uniforms,
+                                              T - 1, t, k, with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s));
+      else
+        CAPDEC_RETURN_IF(sample_rows(S.logits, S.logits_ld ? S.logits_ld : c.vocab_size, S.R, c.vocab_size, uniforms, T - 1, t, k,
+                                     with_greedy ? k - 1 : -1, S.next_tok, S.step_lp, s)); }
     if (out_lp) {
       // out_lp[r, t] = step_lp[r]
       CAPDEC_CHECK_CUDA(cudaMemcpy2DAsync(out_lp + t, (size_t)(T - 1) * sizeof(float), S.step_lp, sizeof(float),

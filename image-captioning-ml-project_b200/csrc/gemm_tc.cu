@@ -532,6 +532,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
         rmax = -INFINITY; rsum = 0.f;   // log-sum-exp partials are per (row, tile half): see tk_lse below
       }
+      // EPI_STORE with tk_lse (the sampling path's logits GEMM): the same per-(row, tile half) {max, sum exp} partials next
+      // to the stored logits, so the sampler locates its draw from 2 * ceil(V / 256) pairs instead of re-reading the row
+      const bool store_lse = EPI == EPI_STORE && p.tk_lse != nullptr && !sk_publish;
+      if (EPI == EPI_STORE) { rmax = -INFINITY; rsum = 0.f; }
+      auto lse_chunk = [&](const float (&o)[32]) {   // o: this row's 32 logits of the chunk, -inf beyond the last column
+        float t8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t8[j] = fmaxf(fmaxf(o[4 * j], o[4 * j + 1]), fmaxf(o[4 * j + 2], o[4 * j + 3]));
+        const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
+        constexpr float kLog2e = 1.4426950408889634f;
+        if (cm > rmax) { rsum *= ex2_approx_((rmax - cm) * kLog2e); rmax = cm; }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rsum += ex2_approx_((o[j] - rmax) * kLog2e);
+      };
 #pragma unroll 1
       for (int c0 = half * HN; c0 < (half + 1) * HN; c0 += 32) {
         uint32_t v[32];
@@ -732,12 +746,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               if (EPI == EPI_GELU) o[j] = gelu_erf_(o[j]);
               if (EPI == EPI_GELU_TANH) o[j] = gelu_tanh_fast_(o[j]);   // (MUFU.TANH's 2^-11 was measured: it breaks the bf16 mode's 2e-2 bar at 124M)
             }
+            if (store_lse) lse_chunk(o);
             if (KIND == KIND_BF16 && p.C == nullptr && p.C2 == nullptr && p.c_split.hi != nullptr && p.c_split.kind == KIND_BF16 &&
                 p.c_split.b8 == nullptr && (TERMS == 3) == (p.c_split.lo != nullptr) && (p.c_split.ld & 7) == 0)
               store_chunk_bf16(o, m - lane, n0);
             else
               store_chunk(o, m - lane, n0, true);
           } else {
+            if (store_lse) {   // (a ragged last chunk: columns beyond N do not exist)
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                o[j] = n0 + j < p.N ? __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f) : -INFINITY;
+              lse_chunk(o);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 bj = pre_b ? bia[j >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -748,6 +770,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
       }
       if (warp == 2 && lane == 0 && local < 16) TL(17 + 2 * local);
+      if (EPI == EPI_STORE && store_lse && m < p.M && n_tile * BN + half * HN < p.N)
+        *reinterpret_cast<float2*>(p.tk_lse + ((int64_t)m * (2 * n_tiles) + n_tile * 2 + half) * 2) = make_float2(rmax, rsum);
       if constexpr (EPI == EPI_TOPK) {
         // {max, sum exp(x - max)} of this row over this tile half.  Kept per tile (not folded along the run) so that the
         // merge kernel can combine them in one canonical order: the result does not depend on how the tiles were
@@ -1081,7 +1105,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     // stream-K when whole tiles would leave the last wave mostly idle (see the kernel): needs the handle's scratch
     g.sk_part = nullptr; g.sk_flag = nullptr; g.sk_epoch = 0;
     static const bool no_sk = ab_switch("CAPDEC_NO_STREAMK");
-    if (h && epilogue != EPI_TOPK && !no_sk) {
+    if (h && epilogue != EPI_TOPK && !no_sk && a.tk_lse == nullptr) {
       const int G = tc_max_groups(cg);
       const int tiles = ceil_div(a.N, bn) * ceil_div(mc, BM * cg);
       const int num_kb = ceil_div(g.K, kind == KIND_BF16 ? 64 : 32);
@@ -1117,6 +1141,7 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
       if (a.c_split.b8) g.c_split.b8 = a.c_split.b8 + (size_t)m0 * a.c_split.ld;
     }
     if (a.row_index) g.row_index = a.row_index + m0;
+    if (a.tk_lse && epilogue != EPI_TOPK) g.tk_lse = a.tk_lse + (size_t)m0 * tk_lse_pairs(a.N) * 2;
     int st;
 #define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
     if (kind == KIND_TF32) {

@@ -282,6 +282,99 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
   }
 }
 
+// The same draw from the per-(row, 128-column half tile) {max, sum exp(x - max)} partials the logits GEMM's epilogue
+// leaves next to the logits (tensor-core modes): the row is NOT re-read -- one warp per row sums the n_lse partials in
+// index order (double), finds the half tile whose cdf range holds the target, and scans only that half tile's 128
+// logits.  The greedy slot takes the first position of the row maximum the same way.  6.5 -> 0.4 ms per decode at
+// configs[4] (3072 rows x 50257 logits per step: 617 MB read three times per step before).
+__global__ void __launch_bounds__(128) sample_partials_kernel(const float* __restrict__ logits, int64_t ld, int V,
+                                                              const float* __restrict__ lse_part, int n_lse,
+                                                              const float* __restrict__ uniforms, int64_t ld_u, int step,
+                                                              int rows, int rows_per_image, int greedy_slot,
+                                                              int32_t* __restrict__ out_tok, float* __restrict__ out_lp) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* x = logits + (int64_t)r * ld;
+  const float2* pp = reinterpret_cast<const float2*>(lse_part) + (int64_t)r * n_lse;
+  const int n_half = (V + 127) / 128;                 // half tiles that hold columns (<= n_lse)
+  const int nb = (n_half + 31) / 32;                  // contiguous half tiles per lane: prefix sums follow index order
+  const int t0 = min(n_half, lane * nb), t1 = min(n_half, t0 + nb);
+  float bm = -INFINITY;
+  int bt = INT_MAX;
+  for (int t = t0; t < t1; ++t) { const float m = pp[t].x; if (m > bm) { bm = m; bt = t; } }   // first half tile of the lane's maximum
+  float M = bm; int mt = bt;
+  warp_argmax(M, mt);                                 // row maximum and the first half tile that reaches it
+  const bool greedy = greedy_slot >= 0 && (r % rows_per_image) == greedy_slot;
+  double local = 0.0;
+  for (int t = t0; t < t1; ++t) { const float2 v = pp[t]; local += (double)v.y * (double)expf(v.x - M); }
+  double incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const double S = __shfl_sync(0xffffffffu, incl, 31);
+  int half_tile = mt;
+  double base = 0.0, target = 0.0;
+  if (!greedy) {
+    target = (double)uniforms[(int64_t)r * ld_u + step] * S;
+    const double before = incl - local;
+    // the lane whose block holds the first cdf value above the target walks it; no lane (u * S rounds to >= the total):
+    // the draw is the last token, as torch's clamp does
+    int found = -1;
+    double fbase = 0.0;
+    if (before <= target && incl > target) {
+      double b = before;
+      for (int t = t0; t < t1; ++t) {
+        const float2 v = pp[t];
+        const double pt = (double)v.y * (double)expf(v.x - M);
+        if (b + pt > target || t == t1 - 1) { found = t; fbase = b; break; }
+        b += pt;
+      }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, found >= 0);
+    if (who == 0u) {
+      if (lane == 0) { out_tok[r] = V - 1; if (out_lp) out_lp[r] = (x[V - 1] - M) - logf((float)S); }
+      return;
+    }
+    const int src = __ffs(who) - 1;
+    half_tile = __shfl_sync(0xffffffffu, found, src);
+    base = __shfl_sync(0xffffffffu, fbase, src);
+  }
+  int tok = -1;
+  const int beg = half_tile * 128, end = min(V, beg + 128);
+  for (int g = beg; g < end && tok < 0; g += 32) {
+    const int i = g + lane;
+    const float xv = i < end ? x[i] : -INFINITY;
+    if (greedy) {
+      const unsigned hit = __ballot_sync(0xffffffffu, xv == M);
+      if (hit) tok = g + __ffs(hit) - 1;
+    } else {
+      double inc = i < end ? (double)expf(xv - M) : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      const unsigned below = __ballot_sync(0xffffffffu, i < end && base + inc <= target);
+      const int n_valid = min(32, end - g);
+      const int cnt = __popc(below);
+      if (cnt < n_valid) tok = g + cnt;       // cdf is non-decreasing: the first element above the target
+      base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  // (the half tile's partial is an fp32 sum in another order: if its re-summed last value lands a rounding below the
+  //  target, the first element above it is the next half tile's first)
+  tok = min(tok >= 0 ? tok : end, V - 1);
+  if (lane == 0) {
+    out_tok[r] = tok;
+    if (out_lp) out_lp[r] = (x[tok] - M) - logf((float)S);
+  }
+}
+
 // lp[r] = logits[r, tok[r]] - logsumexp(logits[r, :])   (log-prob of a GIVEN token: re-scoring of sampled captions,
 // src/train/trainer.py:423-428 without the draw).  One CTA per row, two passes over the row (it sits in L2).
 __global__ void __launch_bounds__(kThreads) token_logprob_kernel(const float* __restrict__ logits, int64_t ld, int V,
@@ -648,6 +741,16 @@ int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const floa
   CAPDEC_REQUIRE(vocab >= 1, CAPDEC_ERR_INVALID, "sample_rows: empty vocabulary");
   if (rows == 0) return CAPDEC_OK;
   sample_kernel<<<rows, kThreads, 0, s>>>(logits, ld, vocab, uniforms, ld_u, step, rows_per_image, greedy_slot, out_tok, out_lp);
+  CAPDEC_LAUNCH_CHECK();
+  return CAPDEC_OK;
+}
+
+int sample_rows_partials(const float* logits, int64_t ld, int rows, int vocab, const float* lse_part, const float* uniforms,
+                         int64_t ld_u, int step, int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s) {
+  CAPDEC_REQUIRE(vocab >= 1 && lse_part, CAPDEC_ERR_INVALID, "sample_rows_partials: empty vocabulary / no partials");
+  if (rows == 0) return CAPDEC_OK;
+  CAPDEC_CHECK_CUDA(launch_k(sample_partials_kernel, dim3(ceil_div(rows, 4)), dim3(128), 0, s, true, logits, ld, vocab, lse_part,
+                             tk_lse_pairs(vocab), uniforms, ld_u, step, rows, rows_per_image, greedy_slot, out_tok, out_lp));
   CAPDEC_LAUNCH_CHECK();
   return CAPDEC_OK;
 }

@@ -20,6 +20,9 @@ int topk_merge(const float* part, const float* lse_part, int rows, int vocab, in
 // rows whose (r % rows_per_image) == greedy_slot take the argmax instead (greedy_slot < 0: none).
 int sample_rows(const float* logits, int64_t ld, int rows, int vocab, const float* uniforms, int64_t ld_u, int step,
                 int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s);
+// the same draw from the {max, sum exp} partials the logits GEMM leaves per (row, 128-column half tile) (tensor-core modes)
+int sample_rows_partials(const float* logits, int64_t ld, int rows, int vocab, const float* lse_part, const float* uniforms,
+                         int64_t ld_u, int step, int rows_per_image, int greedy_slot, int32_t* out_tok, float* out_lp, cudaStream_t s);
 
 // out_lp[r*ld_out] = log_softmax(logits[r,:])[tok[r*ld_tok]]
 int token_logprob(const float* logits, int64_t ld, int rows, int vocab, const int32_t* tok, int64_t ld_tok, float* out_lp,
