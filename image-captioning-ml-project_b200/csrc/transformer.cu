@@ -204,7 +204,9 @@ __global__ void self_attn_decode_kernel(const SelfAttnArgs a) {
 // four value rounds of scalar loads -- at 16 % DRAM utilisation: 114 us per launch at 5120 rows x 12 heads; this form
 // 88 us, issue-bound.  A single-pass online-softmax variant with K and V loads in flight together and no weight / pointer
 // shuffles in the value pass was measured SLOWER, 112 us: 70 instead of 48 registers and every lane of a key group
-// repeating the key's exp.)
+// repeating the key's exp.  Eight-lane key groups with two float4s per lane (four keys per round, 40 % fewer instructions
+// per key) were also measured slower, 107 us: the kernel is bound by how many distinct rows a load instruction touches,
+// not by its instruction count.)
 //   lane = key:  every lane resolves the address of ITS key once (prefix row, ancestor-indirected cache row, or -- for
 //                the current position -- this step's projection output itself, so nothing waits for the cache append);
 //   pass 1:      a group of GL lanes (8 / 16 / 32 >= head_dim / 4) reads one key's head slice with one 128-bit load per

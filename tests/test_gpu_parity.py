@@ -411,6 +411,24 @@ def test_legacy_greedy_and_sample_vs_oracle(cuda):
     _check_sampling(stp, stok.cpu(), slp.cpu(), u, B, k, T, greedy_slot=2, ref_greedy=ref_tok)
 
 
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16x3", "bf16"])
+def test_legacy_sampling_from_gemm_partials(cuda, precision):
+    """Tensor-core modes draw from the {max, sum exp} partials the logits GEMM leaves per (row, 128-column half tile) and
+    scan one half tile (sample_partials_kernel) instead of re-reading the row.  V = 3000 ends in a ragged tile (a full
+    half, then one full and one 24-column chunk); 3 samples + the greedy row per image; every draw must be the oracle's
+    inverse-CDF draw unless u sits within the mode's log-prob tolerance of a CDF edge."""
+    B, T, V, k = 12, 10, 3000, 4
+    m, sd = legacy_weights(V, 5)
+    m.precision = precision
+    enc = legacy_features(B, seed=6)
+    u = torch.rand(B * k, T - 1, generator=torch.Generator().manual_seed(7))
+    stok, slp = m.to(cuda).sample(enc.to(cuda), num_samples=3, with_greedy=True, max_length=T, uniforms=u.to(cuda))
+    loose = precision == "bf16"
+    _check_sampling(olegacy.LegacyStepper(sd, enc, k), stok.cpu(), slp.cpu(), u, B, k, T, greedy_slot=3,
+                    logp_tol=2e-2 if loose else LOGP_TOL, edge_tol=2e-2 if loose else 1e-3,
+                    margin=0.1 if loose else MARGIN_EXCUSE[precision])
+
+
 def _assert_tokens_match(tok, ref_tok, margins, what, precision="fp32"):
     bad = (tok != ref_tok)
     n_bad_rows = int(bad.any(dim=1).sum())
