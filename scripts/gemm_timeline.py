@@ -3,7 +3,11 @@ Every CTA stamps %globaltimer / clock64 at: entry (0), set-up done (1), pdl wait
 issued (4), first operands landed (5), MMAs of work item i issued (8+i), epilogue of item i started / finished (16+2i /
 17+2i), epilogue warps done (62), exit (63).  Prints medians over the CTAs in microseconds relative to the launch's
 first entry stamp.
-  python scripts/gemm_timeline.py [precision]"""
+  python scripts/gemm_timeline.py [precision]            stand-alone GPT-2 / legacy shapes through capdec_linear
+  python scripts/gemm_timeline.py decode [precision]     in situ: the LAST stamped GEMM launch of a GPT-2 124M beam-5 decode
+  python scripts/gemm_timeline.py legacy [images]        in situ: ... of the headline legacy decode (bf16x3)
+For the in-situ modes build with -DCAPDEC_TL_EPI=<epilogue id> (0 store, 2 LSTM, 6 GELU-tanh, 7 fused top-k) so that only
+launches with that epilogue stamp; scripts/build_variant.sh builds such variants next to the product library."""
 import ctypes as C
 import os
 import sys
