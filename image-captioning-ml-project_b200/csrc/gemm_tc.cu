@@ -185,10 +185,12 @@ struct SmemLayout {
   static constexpr uint32_t kOffWHi = TERMS == 3 ? 2 * kABytes : kABytes;
   static constexpr uint32_t kOffWLo = kOffWHi + kWBytes;                        // (3-term only)
   static constexpr int kStages = (CG == 2 ? 3 : 2) * (TERMS == 3 ? 1 : 2);
-  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
-  static constexpr uint32_t kStashOffset = kBarOffset + 256;   // 8 epilogue warps x (32 x 32 floats): store transpose / top-k candidates
+  // 8 epilogue warps x (32 x 32 floats): store transpose / top-k candidates.  The slabs sit on 1024-byte boundaries: a
+  // slab written with the XOR swizzle of store_chunk IS a SWIZZLE_128B box, so a TMA tensor store can read it directly
+  static constexpr uint32_t kStashOffset = kStages * kStageBytes;
   static constexpr uint32_t kStashBytes = 8 * 32 * 32 * 4;
-  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024 + kStashBytes;  // barriers + slack for manual 1024-byte alignment + stash
+  static constexpr uint32_t kBarOffset = kStashOffset + kStashBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // + barriers + slack for manual 1024-byte alignment
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest,
@@ -198,7 +200,7 @@ template <int BN, int EPI, int TERMS, int TK, int CG, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                    const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap map_c, const GemmArgs p) {
   using SL = SmemLayout<BN, CG, TERMS>;
   constexpr int kStages = SL::kStages;
   extern __shared__ uint8_t smem_dyn[];
@@ -423,6 +425,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
       }
       __syncwarp();
+    };
+    // C alone (no second copy, no operand mirror): the swizzled slab is handed to the TMA as a 32 x 32 box -- the warp
+    // issues 8 shared stores and one bulk tensor store instead of 8 shared loads + 8 global stores, rows beyond M are
+    // clipped by the tensor map.  The slab is rewritten only after the previous box has been read out.
+    bool tma_pending = false;
+    auto store_chunk_tma = [&](const float (&o)[32], int row0, int col0) {
+      if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(slab_a + (uint32_t)(lane * 32 + ((j ^ (lane & 7)) << 2)) * 4u, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(&map_c), "r"(slab_a), "r"(col0), "r"(row0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      tma_pending = true;
     };
     auto store_chunk = [&](const float (&o)[32], int row0, int col0, bool mirrors) {
 #pragma unroll
@@ -750,6 +771,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             if (KIND == KIND_BF16 && p.C == nullptr && p.C2 == nullptr && p.c_split.hi != nullptr && p.c_split.kind == KIND_BF16 &&
                 p.c_split.b8 == nullptr && (TERMS == 3) == (p.c_split.lo != nullptr) && (p.c_split.ld & 7) == 0)
               store_chunk_bf16(o, m - lane, n0);
+            else if (p.c_tma)
+              store_chunk_tma(o, m - lane, n0);
             else
               store_chunk(o, m - lane, n0, true);
           } else {
@@ -783,6 +806,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     if constexpr (EPI == EPI_TOPK) {
       if (cur_block >= 0) tk_flush(cur_block);
     }
+    if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the bulk stores are complete before the CTA retires
   }
   tcgen05_fence_before();
   if (threadIdx.x == 64) TL(62);
@@ -914,7 +938,7 @@ int tc_cta_group(int M) {
 
 template <int BN, int TERMS, int CG, int KIND>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-              const GemmArgs& g, int epi, cudaStream_t s) {
+              const CUtensorMap& c_map, const GemmArgs& g, int epi, cudaStream_t s) {
   const int num_tiles = ceil_div(g.N, BN) * ceil_div(g.M, BM * CG);
 #define CAPDEC_TC_LAUNCH(E, TKV)                                                                                  \
   {                                                                                                               \
@@ -936,7 +960,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                \
     at[1].val.programmaticStreamSerializationAllowed = 1;                                                         \
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;                                                         \
-    CAPDEC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, g));                                 \
+    CAPDEC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, c_map, g));                          \
   }
 #define CAPDEC_TC_CASE(E) case E: CAPDEC_TC_LAUNCH(E, 0) break;
   switch (epi) {
@@ -1143,7 +1167,14 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     if (a.row_index) g.row_index = a.row_index + m0;
     if (a.tk_lse && epilogue != EPI_TOPK) g.tk_lse = a.tk_lse + (size_t)m0 * tk_lse_pairs(a.N) * 2;
     int st;
-#define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, g, epilogue, s)
+    // C stored by TMA (plain store-family output, nothing else written per element): a [rows, N] fp32 map with 32 x 32 boxes
+    CUtensorMap map_c = map_w_hi;   // (placeholder when unused)
+    g.c_tma = 0;
+    if (epi_is_store_family(epilogue) && g.C && !g.C2 && !g.c_split.hi && a.N >= 32 && (a.ldc & 3) == 0 && (((uintptr_t)g.C) & 15) == 0) {
+      CAPDEC_RETURN_IF(make_map(&map_c, KIND_TF32, g.C, mc, a.N, a.ldc, 32));
+      g.c_tma = 1;
+    }
+#define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, map_c, g, epilogue, s)
     if (kind == KIND_TF32) {
       if (cg == 1) st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 1, KIND_TF32) : CAPDEC_TC_DISPATCH(1, 1, KIND_TF32);
       else         st = terms == 3 ? CAPDEC_TC_DISPATCH(3, 2, KIND_TF32) : CAPDEC_TC_DISPATCH(1, 2, KIND_TF32);
