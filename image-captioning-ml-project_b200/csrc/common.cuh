@@ -314,7 +314,7 @@ struct GemmArgs {
   float* tk_part; int tk_k;         // EPI_TOPK: candidate records [M, tk_records(M,N), tk_stride(tk_k)], requested list length
   float* tk_lse;                    // EPI_TOPK: {max, sum exp} per (row, 128-column tile half): [M, tk_lse_pairs(tk_vocab), 2]
   float* sk_part; int* sk_flag; int sk_epoch;   // stream-K (gemm_tc.cu, set by the launcher): part scratch, per-warp flags, launch tag
-  int c_tma;                        // tensor-core path, set by the launcher: C (alone: no C2 / mirror) is stored with TMA bulk tensor stores
+  int c_tma;                        // tensor-core path, set by the launcher: 1 = C (alone: no C2 / mirror), 2 = the single bf16 mirror plane (alone) is stored with TMA bulk tensor stores
   int tk_vocab;                     // EPI_TOPK: vocabulary columns V <= N.  Columns [ceil(V/256)*256, N) are a tail block stored
                                     // to C (ld ldc) as a plain projection, sigmoid on tail columns >= n_split
 };

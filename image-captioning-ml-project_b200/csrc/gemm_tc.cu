@@ -398,6 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const uint32_t slab_a = smem_u32(stash) + (uint32_t)(warp - 2) * 4096u;   // this warp's 4 KB slab (shared-space address)
     // Mirror-only output (C == nullptr: only the next GEMM reads it) in the bf16 operand type: the chunk is converted
     // first and transposed as packed bf16 -- a row of the chunk is 64 bytes, 4 lanes x 16 bytes, 8 rows per store.
+    bool tma_pending = false;   // this warp's slab is the source of a bulk tensor store that may not have been read out yet
     auto store_chunk_bf16 = [&](const float (&o)[32], int row0, int col0) {
       uint32_t hw[16], lw[16];
 #pragma unroll
@@ -406,7 +407,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         hw[j] = pack_bf16x2_(o[2 * j], o[2 * j + 1], &r0, &r1);
         lw[j] = TERMS == 3 ? pack_bf16x2_(r0, r1, &d0, &d1) : 0u;
       }
-      // slab as [32 rows][4 cells of 16 bytes], cell index XOR-swizzled by (row >> 1) & 3
+      // slab as [32 rows][4 cells of 16 bytes], cell index XOR-swizzled by (row >> 1) & 3 -- which is the SWIZZLE_64B box
+      // layout, so a single-plane mirror (the single-term modes) leaves through one TMA bulk tensor store per chunk
+      if (TERMS == 1 && p.c_tma == 2) {
+        if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128u(slab_a + (uint32_t)(lane * 4 + (j ^ ((lane >> 1) & 3))) * 16u, hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&map_c), "r"(slab_a), "r"(col0), "r"(row0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        tma_pending = true;
+        return;
+      }
 #pragma unroll
       for (int pass = 0; pass < (TERMS == 3 ? 2 : 1); ++pass) {
         const uint32_t* w = pass ? lw : hw;
@@ -429,7 +447,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // C alone (no second copy, no operand mirror): the swizzled slab is handed to the TMA as a 32 x 32 box -- the warp
     // issues 8 shared stores and one bulk tensor store instead of 8 shared loads + 8 global stores, rows beyond M are
     // clipped by the tensor map.  The slab is rewritten only after the previous box has been read out.
-    bool tma_pending = false;
     auto store_chunk_tma = [&](const float (&o)[32], int row0, int col0) {
       if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
@@ -771,7 +788,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             if (KIND == KIND_BF16 && p.C == nullptr && p.C2 == nullptr && p.c_split.hi != nullptr && p.c_split.kind == KIND_BF16 &&
                 p.c_split.b8 == nullptr && (TERMS == 3) == (p.c_split.lo != nullptr) && (p.c_split.ld & 7) == 0)
               store_chunk_bf16(o, m - lane, n0);
-            else if (p.c_tma)
+            else if (p.c_tma == 1)
               store_chunk_tma(o, m - lane, n0);
             else
               store_chunk(o, m - lane, n0, true);
@@ -891,17 +908,18 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 // 2-D tensor [rows, cols] of tf32/bf16 elements with row stride ld (elements); box = [box_rows, one 128-byte K block];
 // 128-byte swizzle; OOB -> 0
-int make_map(CUtensorMap* m, int kind, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* m, int kind, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_row_bytes = kRowBytes) {
   EncodeTiledFn fn;
   CAPDEC_RETURN_IF(get_encode_fn(&fn));
   const size_t es = kind == KIND_BF16 ? 2 : 4;
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
-  const cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / es), (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)(box_row_bytes / es), (cuuint32_t)box_rows};   // box rows of 128 bytes (operands, fp32 outputs) or 64
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(m, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        box_row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CAPDEC_REQUIRE(r == CUDA_SUCCESS, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)",
                  (int)r, (long long)rows, (long long)cols, (long long)ld);
   return CAPDEC_OK;
@@ -1173,6 +1191,11 @@ int gemm_tc(const capdec_handle* h, int precision, const GemmArgs& a, int epilog
     if (epi_is_store_family(epilogue) && g.C && !g.C2 && !g.c_split.hi && a.N >= 32 && (a.ldc & 3) == 0 && (((uintptr_t)g.C) & 15) == 0) {
       CAPDEC_RETURN_IF(make_map(&map_c, KIND_TF32, g.C, mc, a.N, a.ldc, 32));
       g.c_tma = 1;
+    } else if (epi_is_store_family(epilogue) && !g.C && !g.C2 && kind == KIND_BF16 && terms == 1 && g.c_split.hi && !g.c_split.lo && !g.c_split.b8 &&
+               g.c_split.kind == KIND_BF16 && a.N >= 32 && (g.c_split.ld & 7) == 0 && (((uintptr_t)g.c_split.hi) & 15) == 0) {
+      // mirror-only output of a single-term mode (one bf16 plane): 32 x 32 boxes of 64-byte rows
+      CAPDEC_RETURN_IF(make_map(&map_c, KIND_BF16, g.c_split.hi, mc, a.N, g.c_split.ld, 32, 64));
+      g.c_tma = 2;
     }
 #define CAPDEC_TC_DISPATCH(TERMSV, CGV, KINDV) launch_tc<256, TERMSV, CGV, KINDV>(map_a_hi, map_a_lo, map_w_hi, map_w_lo, map_c, g, epilogue, s)
     if (kind == KIND_TF32) {
