@@ -6,6 +6,7 @@ first entry stamp.
   python scripts/gemm_timeline.py [precision]            stand-alone GPT-2 / legacy shapes through capdec_linear
   python scripts/gemm_timeline.py decode [precision]     in situ: the LAST stamped GEMM launch of a GPT-2 124M beam-5 decode
   python scripts/gemm_timeline.py legacy [images]        in situ: ... of the headline legacy decode (bf16x3)
+  python scripts/gemm_timeline.py c3                     in situ: ... of the configs[2] transformer decode (bf16x3)
 For the in-situ modes build with -DCAPDEC_TL_EPI=<epilogue id> (0 store, 2 LSTM, 6 GELU-tanh, 7 fused top-k) so that only
 launches with that epilogue stamp; scripts/build_variant.sh builds such variants next to the product library."""
 import ctypes as C
@@ -77,6 +78,23 @@ if prec == "legacy":
     torch.cuda.synchronize()
     g, c = fetch()
     report(g, c, f"last stamped GEMM launch of the legacy beam-5 decode, {enc.shape[0]} images, bf16x3")
+    sys.exit(0)
+
+if prec == "c3":
+    # in-situ probe on configs[2] (transformer decoder, 2048 images, beam 3, bf16x3): -DCAPDEC_TL_EPI=5 stamps linear1 + GELU,
+    # =0 the plain projections (the last one of a decode is the last layer's linear2)
+    from tests.helpers import transformer_decoder
+    torch.set_grad_enabled(False)
+    m, _ = transformer_decoder(H=768, layers=6, heads=8, V=10000, max_length=50); m.precision = "bf16x3"; m = m.to(dev)
+    ef = {"features": torch.randn(2048, 196, 768, device=dev)}
+    for _ in range(2):
+        m.generate(ef, 20, num_beams=3)
+    torch.cuda.synchronize()
+    lib.capdec_debug_timeline(None, 1)
+    m.generate(ef, 20, num_beams=3)
+    torch.cuda.synchronize()
+    g, c = fetch()
+    report(g, c, "last stamped GEMM launch of the configs[2] transformer decode, 2048 images, beam 3, bf16x3")
     sys.exit(0)
 
 if prec == "decode":
